@@ -1,0 +1,202 @@
+/* ptfnn.h -- C ABI of libptfnn.so: the B200 (sm_100a) parallel-tempering Bayesian-FNN sampler.
+ *
+ * The reference (sydney-machine-learning/parallel-tempering-neural-net) is pure Python and has NO
+ * FFI of its own; its boundary is the class surface Network / ptReplica / ParallelTempering
+ * (SURVEY.md section 8b).  This header is the interface a reference maintainer would bind with
+ * ctypes underneath those classes (INTEGRATION.md shows the stub).  Every entry point cites the
+ * reference code it replaces:
+ *
+ *   R: = multicore-pt-regression/pt_timeseries_regression.py
+ *   C: = multicore-pt-classification/pt_classification.py
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every call returns int (0 = PTFNN_OK, < 0 = error) and never
+ *     throws across the boundary; ptfnn_last_error() gives the text.
+ *   - host arrays are row-major float64, exactly the ndarrays the reference passes around
+ *     (caller-owned, copied on entry); traces come back in caller-allocated float64 buffers.
+ *     Device arithmetic is float32 with float64 scalar reductions ("numerics").
+ *   - weight vector layout (R:80-97): [W1 (I x H row-major), W2 (H x O row-major), B1 (H), B2 (O)].
+ *   - a handle is not re-entrant: one host thread per handle.  Kernels run asynchronously on the
+ *     handle's stream; ptfnn_get_* / ptfnn_sync synchronise.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with PTFNN_E_CUDA.
+ */
+#ifndef PTFNN_H_
+#define PTFNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTFNN_ABI_VERSION 1
+
+#define PTFNN_OK 0
+#define PTFNN_E_INVALID (-1)     /* bad argument / shape */
+#define PTFNN_E_CUDA (-2)        /* CUDA runtime error, or no device */
+#define PTFNN_E_STATE (-3)       /* call order violated (e.g. run before set_data) */
+#define PTFNN_E_UNSUPPORTED (-4) /* e.g. regression with n_out != 1 (the reference requires it, R:132) */
+#define PTFNN_E_NOMEM (-5)
+
+#define PTFNN_TASK_REGRESSION 0     /* R: Gaussian likelihood, tau^2 (eta) proposals */
+#define PTFNN_TASK_CLASSIFICATION 1 /* C: softmax-of-sigmoid multinomial likelihood */
+
+#define PTFNN_SWAP_RULE_AUTO (-1)
+#define PTFNN_SWAP_RULE_AFTER_I 0   /* R:427  swap when i % s == 0 and i != 0 */
+#define PTFNN_SWAP_RULE_BEFORE_I1 1 /* C:438  swap when (i+1) % s == 0 */
+
+typedef struct ptfnn_sampler ptfnn_sampler;
+
+/* Mirrors the arguments of ParallelTempering.__init__ (R:489 / C:499) and the constants hard-coded
+ * in ptReplica.run (R:258-275, R:301). */
+typedef struct ptfnn_config {
+    int32_t abi_version;            /* PTFNN_ABI_VERSION */
+    int32_t task;                   /* PTFNN_TASK_* */
+    int32_t n_in, n_hidden, n_out;  /* topology [I, H, O] */
+    int32_t n_replicas;             /* temperatures held by THIS handle (one handle per GPU) */
+    int32_t n_replicas_global;      /* whole ladder; == n_replicas on a single GPU */
+    int32_t replica_offset;         /* ladder index of this handle's first temperature */
+    int32_t samples;                /* S = int(NumSample / num_chains), R:506 */
+    int32_t swap_interval;          /* R:496 */
+    int32_t swap_rule;              /* PTFNN_SWAP_RULE_*; AUTO picks the task's own rule */
+    int32_t use_langevin_gradients; /* R:168 */
+    int32_t common_random_numbers;  /* free-running mode: 1 = every replica sees the same lx / proposal
+                                       noise / eta noise, as the forked reference does */
+    int32_t memoize_gradient;       /* 1 = reuse langevin_gradient(w) while w is unchanged
+                                       (bit-identical results) */
+    int32_t device;                 /* CUDA ordinal */
+    int32_t threads_per_block;      /* 0 = auto */
+    int32_t debug_traces;           /* 1 = also record prior_prop / diff_prop / mh_prob / accepted */
+    int32_t reserved0;
+    uint64_t seed;                  /* Philox key (free-running mode) */
+    double l_prob;                  /* langevin_prob, R:174 (C:192 fixes 0.5) */
+    double learn_rate;              /* R:172 */
+    double step_w;                  /* 0.025, R:258 */
+    double step_eta;                /* 0.2,   R:260 */
+    double sigma_squared;           /* 25,    R:273 */
+    double nu_1, nu_2;              /* 0, 0,  R:274-275 */
+    double pt_fraction;             /* 0.6,   R:301 */
+} ptfnn_config;
+
+/* Draws for replay mode, covering steps [i0, i0+n) of every local replica (i0 = current step).
+ * float32 on purpose: these are the numbers the device consumes.  SURVEY Q5 gives the order in
+ * which the reference draws them. */
+typedef struct ptfnn_draws {
+    const float *lx;     /* [n_replicas, n]      R:327 np.random.uniform                           */
+    const float *z;      /* [n_replicas, n, P]   R:331 / R:353 standard normals (proposal = loc + step_w*z) */
+    const float *z_eta;  /* [n_replicas, n]      R:355 (regression only; may be NULL otherwise)    */
+    const float *u;      /* [n_replicas, n]      R:387 random.uniform (MH accept)                  */
+    const float *u_swap; /* [rounds_in_span, n_replicas_global-1]  R:677 coordinator uniforms      */
+    int32_t n;           /* steps covered */
+    int32_t n_swap_rounds; /* rows of u_swap */
+} ptfnn_draws;
+
+/* Caller-allocated float64 outputs, rows [first, first+count) of each replica's trace; any pointer
+ * may be NULL.  Semantics are the reference's arrays: row 0 is the initial row
+ * (pos_w = 1, likelihood = -100, rest 0), row i+1 is written by step i. */
+typedef struct ptfnn_traces {
+    double *pos_w;       /* [n_replicas, count, P]  R:240, R:408, R:417 */
+    double *lik_prop;    /* [n_replicas, count]     likeh_list[:,0]  R:391 (tempered) / C:404 (x adapttemp) */
+    double *rmse_train;  /* [n_replicas, count]     R:412 / R:420 */
+    double *rmse_test;   /* [n_replicas, count] */
+    double *acc_train;   /* [n_replicas, count]     C:414 (only on accept), R:403 (always 0) */
+    double *acc_test;    /* [n_replicas, count] */
+    double *accept_list; /* [n_replicas, count]     R:380 (# accepted BEFORE the step) */
+    /* debug_traces only (not reference outputs; used by the parity tests) */
+    double *prior_prop;  /* [n_replicas, count] */
+    double *diff_prop;   /* [n_replicas, count] */
+    double *mh_prob;     /* [n_replicas, count] */
+    uint8_t *accepted;   /* [n_replicas, count] */
+} ptfnn_traces;
+
+/* ---- library ---- */
+int ptfnn_abi_version(void);
+const char *ptfnn_build_info(void);            /* arch, compiler, specialised topologies */
+int ptfnn_device_count(void);                  /* < 0 on CUDA error, 0 if no device */
+void ptfnn_default_config(ptfnn_config *cfg);  /* reference defaults (R:258-275, R:301) */
+const char *ptfnn_last_error(const ptfnn_sampler *s); /* s == NULL: last error of a failed create / op */
+
+/* ---- lifetime: replaces ParallelTempering.__init__ + initialize_chains (R:489-527, R:639-650) ---- */
+int ptfnn_create(const ptfnn_config *cfg, const double *temperatures /* [n_replicas], R:615-636 */,
+                 ptfnn_sampler **out);
+int ptfnn_destroy(ptfnn_sampler *s);
+int ptfnn_set_stream(ptfnn_sampler *s, void *cuda_stream); /* cudaStream_t, e.g. torch's current stream */
+
+/* traindata / testdata as passed to ParallelTempering (R:491-492): row-major [rows, n_cols] float64,
+ * inputs in columns [0, I), target (R:201) or integer class label (C:210) in column I. */
+int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_train, const double *test,
+                   int32_t n_test, int32_t n_cols);
+
+/* w: [n_replicas, P] initial weights (R:649 np.random.randn).  Runs the pre-loop part of
+ * ptReplica.run (R:266-285 / C:271-284): eta = log var(fx_train - y) (regression), tau, prior,
+ * current likelihood / T, and resets traces, counters and the step index to 0. */
+int ptfnn_init_chains(ptfnn_sampler *s, const double *w);
+
+/* Overwrite / read the chain state between runs (teacher-forced replay, checkpointing).
+ * Any pointer may be NULL.  lik is the current TEMPERED log-likelihood (R:397), tau the last
+ * PROPOSED tau^2 (R:356). */
+int ptfnn_set_state(ptfnn_sampler *s, const double *w, const double *eta, const double *lik,
+                    const double *prior, const double *tau);
+int ptfnn_get_state(ptfnn_sampler *s, double *w, double *eta, double *lik, double *prior, double *tau,
+                    int32_t *num_accepted);
+int ptfnn_get_step(const ptfnn_sampler *s, int32_t *step, int32_t *swap_rounds_done);
+
+/* ---- the hot path: replaces ptReplica.run's loop (R:313-437 / C:313-448) for all local replicas
+ * plus, on a single GPU, the coordinator's swap rounds (R:719-752) ----
+ * Advances at most n_steps steps (stops at S-1).  With n_replicas_global > n_replicas the call
+ * returns early right after a step at which a swap is due (*steps_done tells), and the host
+ * completes the round with ptfnn_swap_* below. */
+int ptfnn_run(ptfnn_sampler *s, int32_t n_steps, int32_t *steps_done);                 /* Philox draws */
+int ptfnn_replay(ptfnn_sampler *s, const ptfnn_draws *d, int32_t *steps_done);        /* recorded draws */
+int ptfnn_sync(ptfnn_sampler *s);
+
+/* Dump the Philox draws free-running mode will use for steps [i0, i0+n) (verification only). */
+int ptfnn_generate_draws(ptfnn_sampler *s, int32_t i0, int32_t n, float *lx, float *z, float *z_eta,
+                         float *u);
+int ptfnn_swap_uniforms(const ptfnn_sampler *s, int32_t round, float *u_row /* [n_replicas_global-1] */);
+
+int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, const ptfnn_traces *out);
+/* num_swap / total_swap_proposals (R:501-502, R:769) and the per-pair decisions of every round */
+int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total_swap_proposals,
+                         uint8_t *swapped /* [max_rounds, n_replicas_global-1] or NULL */, int32_t max_rounds);
+
+/* ---- multi-GPU round (ladder partitioned over ranks).  Device pointers are owned by
+ * the caller (torch tensors), so that NCCL can move them:
+ *   lhood_local  [n_replicas]        float64  swap field of each local replica (R:430 / C:439)
+ *   rows_local   [n_replicas, P+1]   float32  (w, eta) of each local replica
+ * After all-gathering lhood over ranks, ptfnn_swap_plan runs the reference's sequential sweep
+ * (R:741-748) with the same device code every rank and returns src[k] = ladder slot whose vector
+ * ends up in slot k.  Rows whose source is remote are received into rows_in (same shape as
+ * rows_local, indexed by local destination slot); ptfnn_swap_apply installs them. */
+int ptfnn_swap_pending(const ptfnn_sampler *s, int32_t *pending, int32_t *is_final_round);
+int ptfnn_swap_export(ptfnn_sampler *s, void *lhood_local_dev, void *rows_local_dev);
+int ptfnn_swap_plan(ptfnn_sampler *s, const void *lhood_global_dev, const float *u_row /* host, NULL = Philox */,
+                    int32_t *src /* host [n_replicas_global] */, uint8_t *swapped /* host [n_replicas_global-1] */);
+int ptfnn_swap_apply(ptfnn_sampler *s, const int32_t *src /* host [n_replicas_global] */,
+                     const void *rows_local_dev, const void *rows_in_dev);
+
+/* ---- single operations (stateless; each replaces one reference method for drop-in use and for
+ * per-function parity tests).  data: row-major [rows, n_cols] float64 host array. ---- */
+/* Network.evaluate_proposal (R:120-134 -> fx; C:134-153 -> fx = argmax, prob = softmax(out)) */
+int ptfnn_op_evaluate_proposal(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                               const double *data, int32_t rows, int32_t n_cols, const double *w,
+                               double *fx /* [rows] */, double *prob /* [rows, O] or NULL */);
+/* Network.langevin_gradient (R:99-118 / C:114-132): depth epochs of online SGD, rows in order */
+int ptfnn_op_langevin_gradient(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                               const double *data, int32_t rows, int32_t n_cols, const double *w,
+                               double learn_rate, int32_t depth, double *w_out /* [P] */);
+/* ptReplica.likelihood_func (R:200-205 / C:209-222): out = {loglik/adapttemp, rmse, accuracy} */
+int ptfnn_op_likelihood(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                        const double *data, int32_t rows, int32_t n_cols, const double *w, double tau_sq,
+                        double adapttemp, double *out3, double *fx /* [rows] or NULL */);
+/* ptReplica.prior_likelihood (R:215-221 / C:224-230) */
+int ptfnn_op_prior(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                   const double *w, double sigma_squared, double nu_1, double nu_2, double tausq, double *out);
+/* ParallelTempering.swap_procedure applied as the sequential sweep of run_chains (R:659-690, R:741-748) */
+int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row,
+                        int32_t *src, uint8_t *swapped);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTFNN_H_ */

@@ -122,7 +122,7 @@ def run_pt(cfg: on.PTConfig, train, test, temperatures, w0, draws: on.Draws, wit
                      _p(tr.pos_w), _p(tr.lik_prop), _p(tr.lik_prop_t), _p(tr.prior_prop), _p(tr.diff_prop),
                      _p(tr.mh_prob), _p(tr.rmse_train), _p(tr.rmse_test), _p(tr.acc_train), _p(tr.acc_test),
                      _p(tr.accept_list), _p(accepted), _p(swapped), _p(tr.state_w), _p(tr.state_eta),
-                     _p(tr.state_lik), _p(tr.state_prior), _p(counters))
+                     _p(tr.state_lik), _p(tr.state_prior), _p(tr.state_tau), _p(counters))
     tr.accepted = accepted.astype(bool)
     tr.swapped = swapped[:rounds, :max(R - 1, 0)].astype(bool)
     tr.num_swap, tr.total_swap_proposals = int(counters[0]), int(counters[1])

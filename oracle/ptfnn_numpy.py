@@ -256,6 +256,7 @@ class Traces:
     state_eta: np.ndarray = None   # [R, S]
     state_lik: np.ndarray = None   # [R, S]  current (tempered) likelihood after step
     state_prior: np.ndarray = None
+    state_tau: np.ndarray = None   # [R, S]  last PROPOSED tau^2 (R:356; Q11)
     final_w: np.ndarray = None
     final_eta: np.ndarray = None
     extra: dict = field(default_factory=dict)
@@ -389,6 +390,7 @@ def new_traces(R, S, P, rounds) -> Traces:
     tr.state_eta = z(R, S)
     tr.state_lik = z(R, S)
     tr.state_prior = z(R, S)
+    tr.state_tau = z(R, S)
     return tr
 
 
@@ -401,6 +403,7 @@ def run_pt(cfg: PTConfig, train, test, temperatures, w0, draws: Draws, n_steps=N
     for k, rep in enumerate(reps):
         tr.state_w[k, 0], tr.state_eta[k, 0] = rep.w, rep.eta
         tr.state_lik[k, 0], tr.state_prior[k, 0] = rep.likelihood, rep.prior_current
+        tr.state_tau[k, 0] = rep.tau_pro
     tr.extra["init_eta"] = np.array([rep.eta for rep in reps])
     tr.extra["init_lik"] = np.array([rep.likelihood for rep in reps])
     tr.extra["init_prior"] = np.array([rep.prior_current for rep in reps])
@@ -423,6 +426,7 @@ def run_pt(cfg: PTConfig, train, test, temperatures, w0, draws: Draws, n_steps=N
         for k, rep in enumerate(reps):
             tr.state_w[k, i + 1], tr.state_eta[k, i + 1] = rep.w, rep.eta
             tr.state_lik[k, i + 1], tr.state_prior[k, i + 1] = rep.likelihood, rep.prior_current
+            tr.state_tau[k, i + 1] = rep.tau_pro
     if last == S - 1 and rnd < rounds and R > 1:
         # left-over coordinator round on the exit vectors [w, eta, likelihood, ...] (R:442; Q9):
         # the lhood field is the tempered likelihood itself, for both tasks.

@@ -1,0 +1,161 @@
+"""ctypes binding of the C ABI in include/ptfnn.h (libptfnn.so).
+
+There is no fallback: if the library has not been built (``python __graft_entry__.py``) or no CUDA
+device is present, calls raise ``PtfnnError`` -- nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libptfnn.so")
+
+OK, E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4, -5
+TASK_REGRESSION, TASK_CLASSIFICATION = 0, 1
+SWAP_RULE_AUTO, SWAP_RULE_AFTER_I, SWAP_RULE_BEFORE_I1 = -1, 0, 1
+ABI_VERSION = 1
+
+# every symbol include/ptfnn.h declares (tests/test_capi_symbols.py checks the header against this)
+SYMBOLS = [
+    "ptfnn_abi_version", "ptfnn_build_info", "ptfnn_device_count", "ptfnn_default_config", "ptfnn_last_error",
+    "ptfnn_create", "ptfnn_destroy", "ptfnn_set_stream", "ptfnn_set_data", "ptfnn_init_chains",
+    "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
+    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
+    "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
+    "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
+    "ptfnn_op_swap_sweep",
+]
+
+
+class PtfnnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libptfnn error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "task", "n_in", "n_hidden", "n_out", "n_replicas", "n_replicas_global", "replica_offset",
+        "samples", "swap_interval", "swap_rule", "use_langevin_gradients", "common_random_numbers",
+        "memoize_gradient", "device", "threads_per_block", "debug_traces", "reserved0")] + \
+        [("seed", C.c_uint64)] + \
+        [(n, C.c_double) for n in ("l_prob", "learn_rate", "step_w", "step_eta", "sigma_squared", "nu_1", "nu_2",
+                                   "pt_fraction")]
+
+
+class Draws(C.Structure):
+    _fields_ = [("lx", C.c_void_p), ("z", C.c_void_p), ("z_eta", C.c_void_p), ("u", C.c_void_p),
+                ("u_swap", C.c_void_p), ("n", C.c_int32), ("n_swap_rounds", C.c_int32)]
+
+
+class Traces(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos_w", "lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test",
+                                          "accept_list", "prior_prop", "diff_prop", "mh_prob", "accepted")]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libptfnn.so (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise PtfnnError(E_STATE, "%s not found: build it with `python __graft_entry__.py` "
+                                  "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.ptfnn_build_info.restype = C.c_char_p
+    lib.ptfnn_last_error.restype = C.c_char_p
+    lib.ptfnn_last_error.argtypes = [C.c_void_p]
+    lib.ptfnn_default_config.restype = None
+    for name in SYMBOLS:
+        getattr(lib, name)          # AttributeError here = header / library mismatch
+    if lib.ptfnn_abi_version() != ABI_VERSION:
+        raise PtfnnError(E_INVALID, "ABI mismatch: library %d, binding %d" % (lib.ptfnn_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, handle=None):
+    if rc != OK:
+        msg = load().ptfnn_last_error(handle)
+        raise PtfnnError(rc, (msg or b"").decode("utf-8", "replace"))
+
+
+def build_info() -> str:
+    return load().ptfnn_build_info().decode()
+
+
+def device_count() -> int:
+    return int(load().ptfnn_device_count())
+
+
+def default_config() -> Config:
+    c = Config()
+    load().ptfnn_default_config(C.byref(c))
+    return c
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- single operations (stateless) -------------------------------------------------------------
+def op_evaluate_proposal(task, topology, data, w, device=0):
+    I, H, O = topology
+    data, w = f64(data), f64(w)
+    fx = np.zeros(data.shape[0])
+    prob = np.zeros((data.shape[0], O)) if task == TASK_CLASSIFICATION else None
+    check(load().ptfnn_op_evaluate_proposal(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
+                                            ptr(fx), ptr(prob)))
+    return (fx, prob) if task == TASK_CLASSIFICATION else fx
+
+
+def op_langevin_gradient(task, topology, data, w, learn_rate, depth=1, device=0):
+    I, H, O = topology
+    data, w = f64(data), f64(w)
+    out = np.zeros_like(w)
+    check(load().ptfnn_op_langevin_gradient(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
+                                            C.c_double(learn_rate), int(depth), ptr(out)))
+    return out
+
+
+def op_likelihood(task, topology, data, w, tau_sq=1.0, adapttemp=1.0, want_fx=True, device=0):
+    """-> (loglik/adapttemp, rmse, accuracy, fx)"""
+    I, H, O = topology
+    data, w = f64(data), f64(w)
+    out = np.zeros(3)
+    fx = np.zeros(data.shape[0]) if want_fx else None
+    check(load().ptfnn_op_likelihood(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
+                                     C.c_double(tau_sq), C.c_double(adapttemp), ptr(out), ptr(fx)))
+    return float(out[0]), float(out[1]), float(out[2]), fx
+
+
+def op_prior(task, topology, w, sigma_squared=25.0, nu_1=0.0, nu_2=0.0, tausq=1.0, device=0):
+    I, H, O = topology
+    w = f64(w)
+    out = C.c_double(0.0)
+    check(load().ptfnn_op_prior(device, task, I, H, O, ptr(w), C.c_double(sigma_squared), C.c_double(nu_1),
+                                C.c_double(nu_2), C.c_double(tausq), C.byref(out)))
+    return out.value
+
+
+def op_swap_sweep(lhood, u_row, device=0):
+    lhood, u_row = f64(lhood), f32(u_row)
+    n = lhood.shape[0]
+    src = np.zeros(n, dtype=np.int32)
+    sw = np.zeros(max(n - 1, 1), dtype=np.uint8)
+    check(load().ptfnn_op_swap_sweep(device, n, ptr(lhood), ptr(u_row), ptr(src), ptr(sw)))
+    return src, sw[:n - 1].astype(bool)

@@ -1,0 +1,857 @@
+// libptfnn.so -- host side of the C ABI declared in include/ptfnn.h.
+// Owns device memory, picks the kernel specialisation for the topology, launches the persistent
+// chain kernel (cooperatively, one CTA per temperature) and copies traces back.  No CPU compute
+// path exists: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptfnn.h"
+#include "ptfnn_kernels.cuh"
+#include "ptfnn_misc_kernels.cuh"
+
+using namespace ptfnn;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct ptfnn_sampler;
+static int fail(ptfnn_sampler *s, int code, const char *fmt, ...);
+
+#define CU_TRY(S, expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail((S), PTFNN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch table: one row per specialised topology
+// ------------------------------------------------------------------------------------------
+#include "ptfnn_registry.h"
+#include "ptfnn_topologies.h"
+typedef PtfnnKernelSet KernelSet;
+
+#define X(NAME, TASK, I, H, O, NT) const PtfnnKernelSet *ptfnn_kernelset_##NAME();
+PTFNN_TOPOLOGIES(X)
+#undef X
+
+static const std::vector<const KernelSet *> &kernel_sets() {
+    static const std::vector<const KernelSet *> v = {
+#define X(NAME, TASK, I, H, O, NT) ptfnn_kernelset_##NAME(),
+        PTFNN_TOPOLOGIES(X)
+#undef X
+    };
+    return v;
+}
+
+static const KernelSet *find_kernels(int task, int I, int H, int O) {
+    for (const KernelSet *k : kernel_sets())
+        if (k->task == task && k->I == I && k->H == H && k->O == O) return k;
+    return nullptr;
+}
+
+static std::string supported_list() {
+    std::string s;
+    char buf[64];
+    for (const KernelSet *k : kernel_sets()) {
+        snprintf(buf, sizeof buf, "%s[%d,%d,%d] ", k->task == kTaskReg ? "reg" : "cls", k->I, k->H, k->O);
+        s += buf;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct ptfnn_sampler {
+    ptfnn_config cfg;
+    const KernelSet *ks = nullptr;
+    int P = 0, IP = 0;
+    int swap_rule = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    std::string err;
+
+    bool have_data = false, have_state = false;
+    int n_train = 0, n_test = 0;
+    int step = 0, rounds_done = 0;
+    bool swap_pending = false, pending_final = false;
+    int64_t host_num_swap = 0, host_total_prop = 0;   // multi-GPU rounds are counted on the host
+    std::vector<uint8_t> host_swap_log;               // [rounds][Rg-1] for externally planned rounds
+    std::vector<int> host_swap_log_round;
+
+    DevBuf<float> train_x, train_y, test_x, test_y;
+    DevBuf<double> temperature;
+    DevBuf<float> w, last_w, gd_cache, pos_w, pub_rows;
+    DevBuf<double> eta, tau, lik, prior, last4, init_rmse, pub_lhood;
+    DevBuf<double> lik_prop, rmse_tr, rmse_te, acc_tr, acc_te, dbg_prior, dbg_diff, dbg_mh;
+    DevBuf<int> n_acc, init_count, gd_valid, accept_list;
+    DevBuf<uint8_t> dbg_acc, swap_log;
+    DevBuf<GridBarrier> barrier;
+    DevBuf<long long> swap_counters;
+    DevBuf<float> d_lx, d_z, d_zeta, d_u, d_uswap;   // replay staging
+    DevBuf<int> d_src;
+    DevBuf<uint8_t> d_swapped;
+    DevBuf<double> d_scratch;
+
+    void release_all() {
+        train_x.release(); train_y.release(); test_x.release(); test_y.release(); temperature.release();
+        w.release(); last_w.release(); gd_cache.release(); pos_w.release(); pub_rows.release();
+        eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
+        pub_lhood.release(); lik_prop.release(); rmse_tr.release(); rmse_te.release(); acc_tr.release();
+        acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
+        init_count.release(); gd_valid.release(); accept_list.release(); dbg_acc.release(); swap_log.release();
+        barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
+        d_u.release(); d_uswap.release(); d_src.release(); d_swapped.release(); d_scratch.release();
+    }
+};
+
+static int fail(ptfnn_sampler *s, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (s) s->err = buf;
+    return code;
+}
+
+// host mirrors of the cadence rules (R:427 | C:438, R:719)
+static bool h_swap_due(int rule, int s, int i) { return rule == 0 ? (i % s == 0 && i != 0) : ((i + 1) % s == 0); }
+static int h_inloop_rounds(const ptfnn_sampler *s, int upto_step_exclusive) {
+    int n = 0;
+    for (int i = 0; i < upto_step_exclusive; ++i) n += h_swap_due(s->swap_rule, s->cfg.swap_interval, i);
+    return n;
+}
+static int h_total_rounds(const ptfnn_sampler *s) {
+    const int n_r = h_inloop_rounds(s, s->cfg.samples - 1);
+    const int n_m = s->cfg.samples / s->cfg.swap_interval;
+    return n_r + (n_m > n_r ? 1 : 0);   // at most one left-over round on the exit vectors
+}
+
+// ------------------------------------------------------------------------------------------
+// library-level entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int ptfnn_abi_version(void) { return PTFNN_ABI_VERSION; }
+
+extern "C" const char *ptfnn_build_info(void) {
+    static std::string info;
+    if (info.empty()) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "libptfnn abi %d, sm_100a, nvcc %d.%d, tile_rows %d, topologies: ", PTFNN_ABI_VERSION,
+                 __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, kTileRows);
+        info = buf + supported_list();
+    }
+    return info.c_str();
+}
+
+extern "C" int ptfnn_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); cudaGetLastError(); return -1; }
+    return n;
+}
+
+extern "C" void ptfnn_default_config(ptfnn_config *c) {
+    memset(c, 0, sizeof *c);
+    c->abi_version = PTFNN_ABI_VERSION;
+    c->task = PTFNN_TASK_REGRESSION;
+    c->swap_rule = PTFNN_SWAP_RULE_AUTO;
+    c->use_langevin_gradients = 1;
+    c->common_random_numbers = 1;
+    c->memoize_gradient = 1;
+    c->l_prob = 0.5;
+    c->learn_rate = 0.1;
+    c->step_w = 0.025;        // R:258
+    c->step_eta = 0.2;        // R:260
+    c->sigma_squared = 25.0;  // R:273
+    c->nu_1 = 0.0; c->nu_2 = 0.0;
+    c->pt_fraction = 0.6;     // R:301
+}
+
+extern "C" const char *ptfnn_last_error(const ptfnn_sampler *s) { return s ? s->err.c_str() : g_last_error.c_str(); }
+
+static int require_device(ptfnn_sampler *s, int device) {
+    const int n = ptfnn_device_count();
+    if (n <= 0) return fail(s, PTFNN_E_CUDA, "no CUDA device available: libptfnn has no CPU path");
+    if (device < 0 || device >= n) return fail(s, PTFNN_E_INVALID, "device %d out of range (have %d)", device, n);
+    CU_TRY(s, cudaSetDevice(device));
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures, ptfnn_sampler **out) {
+    if (!cfg || !temperatures || !out) return fail(nullptr, PTFNN_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != PTFNN_ABI_VERSION) return fail(nullptr, PTFNN_E_INVALID, "abi_version %d != %d", cfg->abi_version, PTFNN_ABI_VERSION);
+    if (cfg->task != PTFNN_TASK_REGRESSION && cfg->task != PTFNN_TASK_CLASSIFICATION) return fail(nullptr, PTFNN_E_INVALID, "bad task %d", cfg->task);
+    if (cfg->n_in < 1 || cfg->n_hidden < 1 || cfg->n_out < 1) return fail(nullptr, PTFNN_E_INVALID, "bad topology [%d,%d,%d]", cfg->n_in, cfg->n_hidden, cfg->n_out);
+    if (cfg->task == PTFNN_TASK_REGRESSION && cfg->n_out != 1)
+        return fail(nullptr, PTFNN_E_UNSUPPORTED, "regression needs one output (the reference stores fx[i] = out, R:132)");
+    if (cfg->n_replicas < 1 || cfg->samples < 2 || cfg->swap_interval < 1) return fail(nullptr, PTFNN_E_INVALID, "need n_replicas >= 1, samples >= 2, swap_interval >= 1");
+    const int Rg = cfg->n_replicas_global > 0 ? cfg->n_replicas_global : cfg->n_replicas;
+    if (cfg->replica_offset < 0 || cfg->replica_offset + cfg->n_replicas > Rg) return fail(nullptr, PTFNN_E_INVALID, "replica_offset/n_replicas outside the ladder of %d", Rg);
+    const KernelSet *ks = find_kernels(cfg->task, cfg->n_in, cfg->n_hidden, cfg->n_out);
+    if (!ks) return fail(nullptr, PTFNN_E_UNSUPPORTED, "no sm_100a specialisation for %s topology [%d,%d,%d]; built: %s", cfg->task == kTaskReg ? "regression" : "classification", cfg->n_in, cfg->n_hidden, cfg->n_out, supported_list().c_str());
+    int rc = require_device(nullptr, cfg->device);
+    if (rc) return rc;
+
+    ptfnn_sampler *s = new (std::nothrow) ptfnn_sampler();
+    if (!s) return fail(nullptr, PTFNN_E_NOMEM, "out of host memory");
+    s->cfg = *cfg;
+    s->cfg.n_replicas_global = Rg;
+    s->ks = ks;
+    s->P = cfg->n_in * cfg->n_hidden + cfg->n_hidden * cfg->n_out + cfg->n_hidden + cfg->n_out;
+    s->IP = (cfg->n_in + 3) & ~3;
+    s->swap_rule = cfg->swap_rule == PTFNN_SWAP_RULE_AUTO ? (cfg->task == PTFNN_TASK_REGRESSION ? 0 : 1) : cfg->swap_rule;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { rc = fail(nullptr, PTFNN_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); delete s; return rc; }
+    s->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { rc = fail(nullptr, PTFNN_E_CUDA, "device lacks cooperative launch"); delete s; return rc; }
+
+    const size_t R = cfg->n_replicas, S = cfg->samples, P = s->P;
+    const int rounds = h_total_rounds(s) + 1;
+#define ALLOC(buf, count)                                                                     \
+    if ((e = s->buf.ensure(count)) != cudaSuccess) {                                          \
+        rc = fail(nullptr, PTFNN_E_NOMEM, "cudaMalloc(" #buf ", %zu elems): %s", (size_t)(count), cudaGetErrorString(e)); \
+        s->release_all(); delete s; cudaGetLastError(); return rc;                            \
+    }
+    ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(last_w, R * P); ALLOC(gd_cache, R * P);
+    ALLOC(pos_w, R * S * P); ALLOC(pub_rows, 2 * R * (P + 1)); ALLOC(pub_lhood, 2 * (size_t)Rg);
+    ALLOC(eta, R); ALLOC(tau, R); ALLOC(lik, R); ALLOC(prior, R); ALLOC(last4, R * 4); ALLOC(init_rmse, R * 2);
+    ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
+    ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
+    if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
+    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2);
+    ALLOC(d_src, (size_t)Rg); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
+#undef ALLOC
+    cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
+    cudaMemset(s->swap_counters.p, 0, 2 * sizeof(long long));
+    cudaMemset(s->swap_log.p, 0, s->swap_log.n);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = fail(nullptr, PTFNN_E_CUDA, "create: %s", cudaGetErrorString(e)); s->release_all(); delete s; return rc; }
+    *out = s;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_destroy(ptfnn_sampler *s) {
+    if (!s) return PTFNN_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->stream);
+    s->release_all();
+    delete s;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_set_stream(ptfnn_sampler *s, void *cuda_stream) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    s->stream = (cudaStream_t)cuda_stream;
+    return PTFNN_OK;
+}
+
+// row-major float64 [rows, n_cols] -> padded float32 X [rows][IP] + y [pad4(rows)]
+static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP, std::vector<float> &x,
+                         std::vector<float> &y) {
+    x.assign((size_t)rows * IP, 0.0f);
+    y.assign((size_t)((rows + 3) & ~3), 0.0f);
+    for (int r = 0; r < rows; ++r) {
+        for (int i = 0; i < I; ++i) x[(size_t)r * IP + i] = (float)data[(size_t)r * n_cols + i];
+        y[r] = (float)data[(size_t)r * n_cols + I];
+    }
+}
+
+extern "C" int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_train, const double *test,
+                              int32_t n_test, int32_t n_cols) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    if (!train || !test || n_train < 1 || n_test < 1) return fail(s, PTFNN_E_INVALID, "empty dataset");
+    if (n_cols < s->cfg.n_in + 1) return fail(s, PTFNN_E_INVALID, "n_cols %d < n_in + 1", n_cols);
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    std::vector<float> x, y;
+    pack_dataset(train, n_train, n_cols, s->cfg.n_in, s->IP, x, y);
+    CU_TRY(s, s->train_x.ensure(x.size())); CU_TRY(s, s->train_y.ensure(y.size()));
+    CU_TRY(s, cudaMemcpyAsync(s->train_x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->train_y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    pack_dataset(test, n_test, n_cols, s->cfg.n_in, s->IP, x, y);
+    CU_TRY(s, s->test_x.ensure(x.size())); CU_TRY(s, s->test_y.ensure(y.size()));
+    CU_TRY(s, cudaMemcpyAsync(s->test_x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->test_y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    s->n_train = n_train; s->n_test = n_test;
+    s->have_data = true;
+    return PTFNN_OK;
+}
+
+static DataView view(const DevBuf<float> &x, const DevBuf<float> &y, int n) { return DataView{x.p, y.p, n}; }
+
+static int upload_doubles_as_float(ptfnn_sampler *s, float *dst, const double *src, size_t n) {
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[i];
+    CU_TRY(s, cudaMemcpyAsync(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
+    if (!s || !w) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->have_data) return fail(s, PTFNN_E_STATE, "ptfnn_set_data must come first");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t R = s->cfg.n_replicas, S = s->cfg.samples, P = s->P;
+    int rc = upload_doubles_as_float(s, s->w.p, w, R * P);
+    if (rc) return rc;
+    // trace row 0 and carried rows: pos_w = 1, likelihood = -100, everything else 0
+    {
+        std::vector<float> ones(R * P, 1.0f);
+        CU_TRY(s, cudaMemcpyAsync(s->last_w.p, ones.data(), R * P * 4, cudaMemcpyHostToDevice, s->stream));
+        for (size_t r = 0; r < R; ++r)
+            CU_TRY(s, cudaMemcpyAsync(s->pos_w.p + r * S * P, ones.data(), P * 4, cudaMemcpyHostToDevice, s->stream));
+        std::vector<double> m100(R * S, 0.0);
+        for (size_t r = 0; r < R; ++r) m100[r * S] = -100.0;     // R:293
+        CU_TRY(s, cudaMemcpyAsync(s->lik_prop.p, m100.data(), R * S * 8, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(s, cudaStreamSynchronize(s->stream));
+    }
+    CU_TRY(s, cudaMemsetAsync(s->rmse_tr.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->rmse_te.p, 0, R * S * 8, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->acc_tr.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->acc_te.p, 0, R * S * 8, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->accept_list.p, 0, R * S * 4, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->last4.p, 0, R * 4 * 8, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->n_acc.p, 0, R * 4, s->stream)); CU_TRY(s, cudaMemsetAsync(s->init_count.p, 0, R * 4, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->gd_valid.p, 0, R * 4, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->swap_counters.p, 0, 16, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->swap_log.p, 0, s->swap_log.n, s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->barrier.p, 0, sizeof(GridBarrier), s->stream));
+    if (s->cfg.debug_traces) {
+        CU_TRY(s, cudaMemsetAsync(s->dbg_prior.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_diff.p, 0, R * S * 8, s->stream));
+        CU_TRY(s, cudaMemsetAsync(s->dbg_mh.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_acc.p, 0, R * S, s->stream));
+    }
+    InitParams ip;
+    ip.R = (int)R; ip.S = (int)S;
+    ip.sigma_sq = s->cfg.sigma_squared; ip.nu1 = s->cfg.nu_1; ip.nu2 = s->cfg.nu_2;
+    ip.temperature = s->temperature.p;
+    ip.train = view(s->train_x, s->train_y, s->n_train);
+    ip.test = view(s->test_x, s->test_y, s->n_test);
+    ip.w = s->w.p; ip.eta = s->eta.p; ip.tau = s->tau.p; ip.lik = s->lik.p; ip.prior = s->prior.p;
+    ip.init_rmse = s->init_rmse.p;
+    void *args[] = {&ip};
+    const size_t smem = ((P * 4 + 15) & ~(size_t)15) + 8 * (s->ks->NT / 32) * 8 + 64;
+    CU_TRY(s, cudaFuncSetAttribute(s->ks->init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(s, cudaLaunchKernel(s->ks->init, dim3((unsigned)R), dim3(s->ks->NT), args, smem, s->stream));
+    CU_TRY(s, cudaGetLastError());
+    s->step = 0; s->rounds_done = 0; s->swap_pending = false; s->pending_final = false;
+    s->host_num_swap = 0; s->host_total_prop = 0; s->host_swap_log.clear(); s->host_swap_log_round.clear();
+    s->have_state = true;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_set_state(ptfnn_sampler *s, const double *w, const double *eta, const double *lik,
+                               const double *prior, const double *tau) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t R = s->cfg.n_replicas, P = s->P;
+    if (w) {
+        int rc = upload_doubles_as_float(s, s->w.p, w, R * P);
+        if (rc) return rc;
+        CU_TRY(s, cudaMemsetAsync(s->gd_valid.p, 0, R * 4, s->stream));
+    }
+    if (eta) CU_TRY(s, cudaMemcpyAsync(s->eta.p, eta, R * 8, cudaMemcpyHostToDevice, s->stream));
+    if (lik) CU_TRY(s, cudaMemcpyAsync(s->lik.p, lik, R * 8, cudaMemcpyHostToDevice, s->stream));
+    if (prior) CU_TRY(s, cudaMemcpyAsync(s->prior.p, prior, R * 8, cudaMemcpyHostToDevice, s->stream));
+    if (tau) CU_TRY(s, cudaMemcpyAsync(s->tau.p, tau, R * 8, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_get_state(ptfnn_sampler *s, double *w, double *eta, double *lik, double *prior, double *tau,
+                               int32_t *num_accepted) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t R = s->cfg.n_replicas, P = s->P;
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (w) {
+        std::vector<float> tmp(R * P);
+        CU_TRY(s, cudaMemcpy(tmp.data(), s->w.p, R * P * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < R * P; ++i) w[i] = tmp[i];
+    }
+    if (eta) CU_TRY(s, cudaMemcpy(eta, s->eta.p, R * 8, cudaMemcpyDeviceToHost));
+    if (lik) CU_TRY(s, cudaMemcpy(lik, s->lik.p, R * 8, cudaMemcpyDeviceToHost));
+    if (prior) CU_TRY(s, cudaMemcpy(prior, s->prior.p, R * 8, cudaMemcpyDeviceToHost));
+    if (tau) CU_TRY(s, cudaMemcpy(tau, s->tau.p, R * 8, cudaMemcpyDeviceToHost));
+    if (num_accepted) CU_TRY(s, cudaMemcpy(num_accepted, s->n_acc.p, R * 4, cudaMemcpyDeviceToHost));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_get_step(const ptfnn_sampler *s, int32_t *step, int32_t *swap_rounds_done) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    if (step) *step = s->step;
+    if (swap_rounds_done) *swap_rounds_done = s->rounds_done;
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------
+static const size_t kStageLimitBytes = 96 * 1024;
+
+static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int32_t *steps_done) {
+    if (steps_done) *steps_done = 0;
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    if (s->swap_pending) return fail(s, PTFNN_E_STATE, "a swap round is pending: finish it with ptfnn_swap_plan/apply");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const ptfnn_config &c = s->cfg;
+    const int R = c.n_replicas, Rg = c.n_replicas_global, S = c.samples, P = s->P;
+    const bool external = Rg > R;
+    int n = std::min(n_steps, S - 1 - s->step);
+    if (n <= 0) return PTFNN_OK;
+    // multi-GPU: stop right after the first step at which a swap is due
+    if (external)
+        for (int k = 0; k < n; ++k)
+            if (h_swap_due(s->swap_rule, c.swap_interval, s->step + k)) { n = k + 1; break; }
+    const int begin = s->step, end = s->step + n;
+    int rounds_in_span = 0;
+    if (Rg > 1)
+        for (int i = begin; i < end; ++i) rounds_in_span += h_swap_due(s->swap_rule, c.swap_interval, i);
+    const bool chain_done = end == S - 1;
+    const bool final_round = Rg > 1 && chain_done && (h_total_rounds(s) > h_inloop_rounds(s, S - 1));
+
+    ChainParams p;
+    memset(&p, 0, sizeof p);
+    p.R = R; p.Rg = Rg; p.replica_offset = c.replica_offset;
+    p.S = S; p.swap_interval = c.swap_interval; p.swap_rule = s->swap_rule;
+    p.use_lg = c.use_langevin_gradients; p.crn = c.common_random_numbers; p.memo = c.memoize_gradient;
+    p.external_swap = external; p.debug = c.debug_traces;
+    p.step_begin = begin; p.step_end = end; p.round_begin = s->rounds_done;
+    p.final_round = final_round && !external;
+    p.l_prob = c.l_prob; p.pt_samples = (double)S * c.pt_fraction;   // R:301 `samples * 0.6` (a float)
+    p.sigma_sq = c.sigma_squared; p.nu1 = c.nu_1; p.nu2 = c.nu_2;
+    p.lr = (float)c.learn_rate; p.step_w = (float)c.step_w; p.step_eta = (float)c.step_eta;
+    p.seed = c.seed;
+    p.temperature = s->temperature.p;
+    p.train = view(s->train_x, s->train_y, s->n_train);
+    p.test = view(s->test_x, s->test_y, s->n_test);
+    p.w = s->w.p; p.eta = s->eta.p; p.tau = s->tau.p; p.lik = s->lik.p; p.prior = s->prior.p;
+    p.n_acc = s->n_acc.p; p.init_count = s->init_count.p; p.last_w = s->last_w.p; p.last4 = s->last4.p;
+    p.gd_cache = s->gd_cache.p; p.gd_valid = s->gd_valid.p;
+    p.pos_w = s->pos_w.p; p.lik_prop = s->lik_prop.p; p.rmse_tr = s->rmse_tr.p; p.rmse_te = s->rmse_te.p;
+    p.acc_tr = s->acc_tr.p; p.acc_te = s->acc_te.p; p.accept_list = s->accept_list.p;
+    p.dbg_prior = s->dbg_prior.p; p.dbg_diff = s->dbg_diff.p; p.dbg_mh = s->dbg_mh.p; p.dbg_acc = s->dbg_acc.p;
+    p.pub_rows = s->pub_rows.p; p.pub_lhood = s->pub_lhood.p; p.barrier = s->barrier.p;
+    p.swap_counters = s->swap_counters.p; p.swap_log = s->swap_log.p;
+    p.max_rounds = (int)(s->swap_log.n / std::max(Rg - 1, 1));
+
+    if (d) {
+        if (d->n < n) return fail(s, PTFNN_E_INVALID, "draws cover %d steps, need %d", d->n, n);
+        if (!d->lx || !d->z || !d->u) return fail(s, PTFNN_E_INVALID, "draws: lx, z and u are required");
+        const int need_rounds = external ? 0 : rounds_in_span + (p.final_round ? 1 : 0);
+        if (need_rounds > 0 && (!d->u_swap || d->n_swap_rounds < need_rounds))
+            return fail(s, PTFNN_E_INVALID, "draws: need %d swap rounds of uniforms, got %d", need_rounds, d->u_swap ? d->n_swap_rounds : 0);
+        const size_t rn = (size_t)R * d->n;
+        CU_TRY(s, s->d_lx.ensure(rn)); CU_TRY(s, s->d_u.ensure(rn)); CU_TRY(s, s->d_z.ensure(rn * P)); CU_TRY(s, s->d_zeta.ensure(rn));
+        CU_TRY(s, cudaMemcpyAsync(s->d_lx.p, d->lx, rn * 4, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(s->d_u.p, d->u, rn * 4, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(s, cudaMemcpyAsync(s->d_z.p, d->z, rn * P * 4, cudaMemcpyHostToDevice, s->stream));
+        if (d->z_eta) CU_TRY(s, cudaMemcpyAsync(s->d_zeta.p, d->z_eta, rn * 4, cudaMemcpyHostToDevice, s->stream));
+        if (need_rounds > 0) {
+            const size_t nu = (size_t)need_rounds * (Rg - 1);
+            CU_TRY(s, s->d_uswap.ensure(nu));
+            CU_TRY(s, cudaMemcpyAsync(s->d_uswap.p, d->u_swap, nu * 4, cudaMemcpyHostToDevice, s->stream));
+        }
+        p.replay = 1; p.replay_n = d->n;
+        p.lx = s->d_lx.p; p.z = s->d_z.p; p.z_eta = d->z_eta ? s->d_zeta.p : nullptr; p.u = s->d_u.p; p.u_swap = s->d_uswap.p;
+    }
+
+    const size_t stage_bytes = ((size_t)s->n_train * s->IP + ((s->n_train + 3) & ~3) + (size_t)s->n_test * s->IP + ((s->n_test + 3) & ~3)) * 4;
+    p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
+    const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, Rg, p.staged != 0, s->n_train, s->n_test);
+    if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB): ladder of %d too long for the in-kernel sweep", L.total, Rg);
+    CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int per_sm = 0;
+    CU_TRY(s, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->ks->chain, NT, L.total));
+    if (per_sm < 1) return fail(s, PTFNN_E_CUDA, "chain kernel does not fit on an SM (smem %zu)", L.total);
+    const int grid = std::min(R, per_sm * s->num_sms);
+    void *args[] = {&p};
+    CU_TRY(s, cudaLaunchCooperativeKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
+    CU_TRY(s, cudaGetLastError());
+    s->step = end;
+    if (external) {
+        if (rounds_in_span > 0) { s->swap_pending = true; s->pending_final = false; }
+        else if (final_round) { s->swap_pending = true; s->pending_final = true; }
+    } else {
+        s->rounds_done += rounds_in_span + (p.final_round ? 1 : 0);
+    }
+    if (steps_done) *steps_done = n;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_run(ptfnn_sampler *s, int32_t n_steps, int32_t *steps_done) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    return launch_chain(s, n_steps, nullptr, steps_done);
+}
+
+extern "C" int ptfnn_replay(ptfnn_sampler *s, const ptfnn_draws *d, int32_t *steps_done) {
+    if (!s || !d) return fail(s, PTFNN_E_INVALID, "null argument");
+    return launch_chain(s, d->n, d, steps_done);
+}
+
+extern "C" int ptfnn_sync(ptfnn_sampler *s) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_generate_draws(ptfnn_sampler *s, int32_t i0, int32_t n, float *lx, float *z, float *z_eta, float *u) {
+    if (!s || n < 1 || !lx || !z || !z_eta || !u) return fail(s, PTFNN_E_INVALID, "bad argument");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t rn = (size_t)s->cfg.n_replicas * n, P = s->P;
+    DevBuf<float> a, b, c, d;
+    CU_TRY(s, a.ensure(rn)); CU_TRY(s, b.ensure(rn * P)); CU_TRY(s, c.ensure(rn)); CU_TRY(s, d.ensure(rn));
+    draws_kernel<<<dim3(n, s->cfg.n_replicas), 64, 0, s->stream>>>(s->cfg.seed, s->cfg.common_random_numbers, s->cfg.replica_offset,
+                                                                  s->cfg.n_replicas, (int)P, i0, n, a.p, b.p, c.p, d.p);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    CU_TRY(s, cudaMemcpy(lx, a.p, rn * 4, cudaMemcpyDeviceToHost)); CU_TRY(s, cudaMemcpy(z, b.p, rn * P * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(s, cudaMemcpy(z_eta, c.p, rn * 4, cudaMemcpyDeviceToHost)); CU_TRY(s, cudaMemcpy(u, d.p, rn * 4, cudaMemcpyDeviceToHost));
+    a.release(); b.release(); c.release(); d.release();
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_swap_uniforms(const ptfnn_sampler *s, int32_t round, float *u_row) {
+    if (!s || !u_row) return fail(nullptr, PTFNN_E_INVALID, "null argument");
+    for (int k = 0; k + 1 < s->cfg.n_replicas_global; ++k) {
+        uint32_t c[4];
+        philox_draw(s->cfg.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
+        u_row[k] = u01_open_right(c[0]);
+    }
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// traces
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int fetch_rows(ptfnn_sampler *s, const T *dev, size_t row_elems, int first, int count, double *out) {
+    // dev is [R][S][row_elems]; copy rows [first, first+count) of every replica and widen to float64
+    const size_t R = s->cfg.n_replicas, S = s->cfg.samples;
+    std::vector<T> tmp(R * count * row_elems);
+    CU_TRY(s, cudaMemcpy2D(tmp.data(), count * row_elems * sizeof(T), dev + (size_t)first * row_elems,
+                           S * row_elems * sizeof(T), count * row_elems * sizeof(T), R, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, const ptfnn_traces *t) {
+    if (!s || !t) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    if (first < 0 || count < 1 || first + count > s->cfg.samples) return fail(s, PTFNN_E_INVALID, "rows [%d,%d) outside [0,%d)", first, first + count, s->cfg.samples);
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    int rc = 0;
+    if (t->pos_w && (rc = fetch_rows(s, s->pos_w.p, s->P, first, count, t->pos_w))) return rc;
+    if (t->lik_prop && (rc = fetch_rows(s, s->lik_prop.p, 1, first, count, t->lik_prop))) return rc;
+    if (t->rmse_train && (rc = fetch_rows(s, s->rmse_tr.p, 1, first, count, t->rmse_train))) return rc;
+    if (t->rmse_test && (rc = fetch_rows(s, s->rmse_te.p, 1, first, count, t->rmse_test))) return rc;
+    if (t->acc_train && (rc = fetch_rows(s, s->acc_tr.p, 1, first, count, t->acc_train))) return rc;
+    if (t->acc_test && (rc = fetch_rows(s, s->acc_te.p, 1, first, count, t->acc_test))) return rc;
+    if (t->accept_list && (rc = fetch_rows(s, s->accept_list.p, 1, first, count, t->accept_list))) return rc;
+    if (t->prior_prop || t->diff_prop || t->mh_prob || t->accepted) {
+        if (!s->cfg.debug_traces) return fail(s, PTFNN_E_STATE, "debug traces were not enabled in the config");
+        if (t->prior_prop && (rc = fetch_rows(s, s->dbg_prior.p, 1, first, count, t->prior_prop))) return rc;
+        if (t->diff_prop && (rc = fetch_rows(s, s->dbg_diff.p, 1, first, count, t->diff_prop))) return rc;
+        if (t->mh_prob && (rc = fetch_rows(s, s->dbg_mh.p, 1, first, count, t->mh_prob))) return rc;
+        if (t->accepted)
+            CU_TRY(s, cudaMemcpy2D(t->accepted, count, s->dbg_acc.p + first, s->cfg.samples, count, s->cfg.n_replicas, cudaMemcpyDeviceToHost));
+    }
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total, uint8_t *swapped, int32_t max_rounds) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    long long c[2] = {0, 0};
+    CU_TRY(s, cudaMemcpy(c, s->swap_counters.p, 16, cudaMemcpyDeviceToHost));
+    if (num_swap) *num_swap = c[0] + s->host_num_swap;
+    if (total) *total = c[1] + s->host_total_prop;
+    if (swapped && max_rounds > 0) {
+        const size_t w = std::max(s->cfg.n_replicas_global - 1, 1);
+        const size_t rounds = std::min<size_t>(max_rounds, s->swap_log.n / w);
+        CU_TRY(s, cudaMemcpy(swapped, s->swap_log.p, rounds * w, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < s->host_swap_log_round.size(); ++k) {
+            const size_t rd = s->host_swap_log_round[k];
+            if (rd < (size_t)max_rounds) memcpy(swapped + rd * w, s->host_swap_log.data() + k * w, w);
+        }
+    }
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU swap round
+// ------------------------------------------------------------------------------------------
+extern "C" int ptfnn_swap_pending(const ptfnn_sampler *s, int32_t *pending, int32_t *is_final_round) {
+    if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
+    if (pending) *pending = s->swap_pending;
+    if (is_final_round) *is_final_round = s->pending_final;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_swap_export(ptfnn_sampler *s, void *lhood_local_dev, void *rows_local_dev) {
+    if (!s || !lhood_local_dev) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->swap_pending) return fail(s, PTFNN_E_STATE, "no swap round pending");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const size_t R = s->cfg.n_replicas, P = s->P;
+    const int parity = s->rounds_done & 1;
+    if (s->pending_final) {
+        // exit vectors [w, eta, likelihood, ...]: the lhood field is the tempered likelihood (R:442)
+        CU_TRY(s, cudaMemcpyAsync(lhood_local_dev, s->lik.p, R * 8, cudaMemcpyDeviceToDevice, s->stream));
+    } else {
+        CU_TRY(s, cudaMemcpyAsync(lhood_local_dev, s->pub_lhood.p + (size_t)parity * s->cfg.n_replicas_global + s->cfg.replica_offset,
+                                  R * 8, cudaMemcpyDeviceToDevice, s->stream));
+        if (rows_local_dev)
+            CU_TRY(s, cudaMemcpyAsync(rows_local_dev, s->pub_rows.p + (size_t)parity * R * (P + 1), R * (P + 1) * 4, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    return PTFNN_OK;
+}
+
+static int run_sweep(ptfnn_sampler *s, cudaStream_t st, int n, const double *lhood_dev, const float *u_host, int *d_src,
+                     uint8_t *d_swapped, DevBuf<float> &d_u, int32_t *src, uint8_t *swapped, int *ns_out) {
+    CU_TRY(s, d_u.ensure(std::max(n - 1, 1)));
+    if (n > 1) CU_TRY(s, cudaMemcpyAsync(d_u.p, u_host, (size_t)(n - 1) * 4, cudaMemcpyHostToDevice, st));
+    DevBuf<int> d_ns;
+    CU_TRY(s, d_ns.ensure(1));
+    const size_t smem = (size_t)n * 12;
+    if (smem > 48 * 1024) CU_TRY(s, cudaFuncSetAttribute((const void *)op_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    op_sweep_kernel<<<1, 128, smem, st>>>(n, lhood_dev, d_u.p, d_src, d_swapped, d_ns.p);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaMemcpyAsync(src, d_src, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (n > 1 && swapped) CU_TRY(s, cudaMemcpyAsync(swapped, d_swapped, (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
+    int ns = 0;
+    CU_TRY(s, cudaMemcpyAsync(&ns, d_ns.p, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(s, cudaStreamSynchronize(st));
+    d_ns.release();
+    if (ns_out) *ns_out = ns;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_swap_plan(ptfnn_sampler *s, const void *lhood_global_dev, const float *u_row, int32_t *src, uint8_t *swapped) {
+    if (!s || !lhood_global_dev || !src) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->swap_pending) return fail(s, PTFNN_E_STATE, "no swap round pending");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const int Rg = s->cfg.n_replicas_global;
+    std::vector<float> u(std::max(Rg - 1, 1));
+    if (u_row) memcpy(u.data(), u_row, (size_t)(Rg - 1) * 4);
+    else ptfnn_swap_uniforms(s, s->rounds_done, u.data());
+    std::vector<uint8_t> sw(std::max(Rg - 1, 1));
+    int ns = 0;
+    int rc = run_sweep(s, s->stream, Rg, (const double *)lhood_global_dev, u.data(), s->d_src.p, s->d_swapped.p, s->d_uswap, src, sw.data(), &ns);
+    if (rc) return rc;
+    if (swapped) memcpy(swapped, sw.data(), (size_t)(Rg - 1));
+    s->host_num_swap += ns; s->host_total_prop += Rg - 1;
+    s->host_swap_log.insert(s->host_swap_log.end(), sw.begin(), sw.end());
+    s->host_swap_log_round.push_back(s->rounds_done);
+    s->rounds_done += 1;
+    if (s->pending_final) { s->swap_pending = false; s->pending_final = false; }   // stats only: nothing to install
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_swap_apply(ptfnn_sampler *s, const int32_t *src, const void *rows_local_dev, const void *rows_in_dev) {
+    if (!s || !src || !rows_local_dev) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->swap_pending) return PTFNN_OK;   // final round: already closed by ptfnn_swap_plan
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const int Rg = s->cfg.n_replicas_global;
+    CU_TRY(s, cudaMemcpyAsync(s->d_src.p, src, (size_t)Rg * 4, cudaMemcpyHostToDevice, s->stream));
+    swap_apply_kernel<<<s->cfg.n_replicas, 128, 0, s->stream>>>(s->cfg.n_replicas, s->P, s->cfg.replica_offset, s->d_src.p,
+                                                                (const float *)rows_local_dev, (const float *)rows_in_dev,
+                                                                s->w.p, s->eta.p, s->gd_valid.p);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    s->swap_pending = false;
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single operations
+// ------------------------------------------------------------------------------------------
+struct OpData {
+    DevBuf<float> x, y, w;
+    int rows = 0;
+    void release() { x.release(); y.release(); w.release(); }
+};
+
+static int op_prepare(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
+                      const double *w, const KernelSet **ks, OpData &od) {
+    int rc = require_device(nullptr, device);
+    if (rc) return rc;
+    *ks = find_kernels(task, I, H, O);
+    if (!*ks) return fail(nullptr, PTFNN_E_UNSUPPORTED, "no sm_100a specialisation for task %d topology [%d,%d,%d]; built: %s", task, I, H, O, supported_list().c_str());
+    if (!w) return fail(nullptr, PTFNN_E_INVALID, "null weights");
+    const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
+    if (data) {
+        if (rows < 1 || n_cols < I + 1) return fail(nullptr, PTFNN_E_INVALID, "bad data shape [%d,%d]", rows, n_cols);
+        std::vector<float> x, y;
+        pack_dataset(data, rows, n_cols, I, IP, x, y);
+        CU_TRY(nullptr, od.x.ensure(x.size())); CU_TRY(nullptr, od.y.ensure(y.size()));
+        CU_TRY(nullptr, cudaMemcpy(od.x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+        CU_TRY(nullptr, cudaMemcpy(od.y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice));
+        od.rows = rows;
+    }
+    std::vector<float> wf(P);
+    for (int j = 0; j < P; ++j) wf[j] = (float)w[j];
+    CU_TRY(nullptr, od.w.ensure(P));
+    CU_TRY(nullptr, cudaMemcpy(od.w.p, wf.data(), (size_t)P * 4, cudaMemcpyHostToDevice));
+    return PTFNN_OK;
+}
+
+static int op_forward(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
+                      const double *w, double *fx, double *prob, double sums[3]) {
+    const KernelSet *ks;
+    OpData od;
+    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od);
+    if (rc) { od.release(); return rc; }
+    const int P = I * H + H * O + H + O;
+    DevBuf<float> d_fx, d_prob;
+    DevBuf<double> d_sums;
+    CU_TRY(nullptr, d_fx.ensure(rows)); CU_TRY(nullptr, d_sums.ensure(3));
+    if (prob) CU_TRY(nullptr, d_prob.ensure((size_t)rows * O));
+    DataView v{od.x.p, od.y.p, rows};
+    const float *wp = od.w.p; float *fxp = d_fx.p; float *pp = prob ? d_prob.p : nullptr; double *sp = d_sums.p;
+    void *args[] = {&wp, &v, &fxp, &pp, &sp};
+    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
+    CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(nullptr, cudaLaunchKernel(ks->fwd, dim3(1), dim3(ks->NT), args, smem, 0));
+    CU_TRY(nullptr, cudaDeviceSynchronize());
+    if (fx) {
+        std::vector<float> t(rows);
+        CU_TRY(nullptr, cudaMemcpy(t.data(), d_fx.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < rows; ++r) fx[r] = t[r];
+    }
+    if (prob) {
+        std::vector<float> t((size_t)rows * O);
+        CU_TRY(nullptr, cudaMemcpy(t.data(), d_prob.p, t.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < t.size(); ++k) prob[k] = t[k];
+    }
+    if (sums) CU_TRY(nullptr, cudaMemcpy(sums, d_sums.p, 24, cudaMemcpyDeviceToHost));
+    od.release(); d_fx.release(); d_prob.release(); d_sums.release();
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_op_evaluate_proposal(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                                          int32_t rows, int32_t n_cols, const double *w, double *fx, double *prob) {
+    if (!data || !fx) return fail(nullptr, PTFNN_E_INVALID, "null argument");
+    return op_forward(device, task, I, H, O, data, rows, n_cols, w, fx, task == kTaskCls ? prob : nullptr, nullptr);
+}
+
+// The scalar epilogue of likelihood_func (R:204-205 / C:222) on the device sums.
+__global__ void op_lik_epilogue_kernel(int task, int rows, const double *sums, double tau_sq, double adapt, double *out3) {
+    if (task == kTaskReg) {
+        out3[0] = (-0.5 * rows * log(2.0 * 3.14159265358979323846 * tau_sq) - 0.5 * sums[0] / tau_sq) / adapt;
+        out3[1] = sqrt(sums[0] / rows);
+        out3[2] = 0.0;
+    } else {
+        out3[0] = sums[0] / adapt;
+        out3[1] = sqrt(sums[1] / rows);
+        out3[2] = 100.0 * (sums[2] / rows);
+    }
+}
+
+extern "C" int ptfnn_op_likelihood(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data, int32_t rows,
+                                   int32_t n_cols, const double *w, double tau_sq, double adapttemp, double *out3, double *fx) {
+    if (!data || !out3) return fail(nullptr, PTFNN_E_INVALID, "null argument");
+    double sums[3];
+    int rc = op_forward(device, task, I, H, O, data, rows, n_cols, w, fx, nullptr, sums);
+    if (rc) return rc;
+    DevBuf<double> d;
+    CU_TRY(nullptr, d.ensure(6));
+    CU_TRY(nullptr, cudaMemcpy(d.p, sums, 24, cudaMemcpyHostToDevice));
+    op_lik_epilogue_kernel<<<1, 1>>>(task, rows, d.p, tau_sq, adapttemp, d.p + 3);
+    CU_TRY(nullptr, cudaGetLastError());
+    CU_TRY(nullptr, cudaMemcpy(out3, d.p + 3, 24, cudaMemcpyDeviceToHost));
+    d.release();
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_op_langevin_gradient(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                                          int32_t rows, int32_t n_cols, const double *w, double learn_rate, int32_t depth,
+                                          double *w_out) {
+    if (!data || !w_out || depth < 0) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    const KernelSet *ks;
+    OpData od;
+    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od);
+    if (rc) { od.release(); return rc; }
+    const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
+    DevBuf<float> d_out;
+    CU_TRY(nullptr, d_out.ensure(P));
+    DataView v{od.x.p, od.y.p, rows};
+    const float *wp = od.w.p; float *op = d_out.p; float lr = (float)learn_rate; int dep = depth;
+    void *args[] = {&wp, &op, &v, &lr, &dep};
+    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 16 + (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4);
+    CU_TRY(nullptr, cudaFuncSetAttribute(ks->sgd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(nullptr, cudaLaunchKernel(ks->sgd, dim3(1), dim3(32), args, smem, 0));
+    CU_TRY(nullptr, cudaDeviceSynchronize());
+    std::vector<float> t(P);
+    CU_TRY(nullptr, cudaMemcpy(t.data(), d_out.p, (size_t)P * 4, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < P; ++j) w_out[j] = t[j];
+    od.release(); d_out.release();
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_op_prior(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *w, double sigma_squared,
+                              double nu_1, double nu_2, double tausq, double *out) {
+    if (!w || !out) return fail(nullptr, PTFNN_E_INVALID, "null argument");
+    int rc = require_device(nullptr, device);
+    if (rc) return rc;
+    const int P = I * H + H * O + H + O;
+    std::vector<float> wf(P);
+    for (int j = 0; j < P; ++j) wf[j] = (float)w[j];
+    DevBuf<float> dw; DevBuf<double> d;
+    CU_TRY(nullptr, dw.ensure(P)); CU_TRY(nullptr, d.ensure(1));
+    CU_TRY(nullptr, cudaMemcpy(dw.p, wf.data(), (size_t)P * 4, cudaMemcpyHostToDevice));
+    op_prior_kernel<<<1, 128>>>(task, I, H, O, dw.p, sigma_squared, nu_1, nu_2, tausq, d.p);
+    CU_TRY(nullptr, cudaGetLastError());
+    CU_TRY(nullptr, cudaMemcpy(out, d.p, 8, cudaMemcpyDeviceToHost));
+    dw.release(); d.release();
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t *src, uint8_t *swapped) {
+    if (n < 1 || !lhood || !src || (n > 1 && !u_row)) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    int rc = require_device(nullptr, device);
+    if (rc) return rc;
+    DevBuf<double> dl; DevBuf<int> ds; DevBuf<uint8_t> dsw; DevBuf<float> du;
+    CU_TRY(nullptr, dl.ensure(n)); CU_TRY(nullptr, ds.ensure(n)); CU_TRY(nullptr, dsw.ensure(std::max(n - 1, 1)));
+    CU_TRY(nullptr, cudaMemcpy(dl.p, lhood, (size_t)n * 8, cudaMemcpyHostToDevice));
+    rc = run_sweep(nullptr, 0, n, dl.p, u_row, ds.p, dsw.p, du, src, swapped, nullptr);
+    dl.release(); ds.release(); dsw.release(); du.release();
+    return rc;
+}

@@ -1,0 +1,231 @@
+// Device-side building blocks of the sm_100a parallel-tempering FNN sampler.
+// Nothing here is derived from reference code (the reference has no native code at all);
+// file:line citations point at the reference behaviour each piece has to reproduce.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptfnn {
+
+constexpr int kTaskReg = 0;
+constexpr int kTaskCls = 1;
+constexpr int kWarp = 32;
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (free-running mode).  __host__ __device__ so that the
+// host can reproduce the integer stream bit-for-bit (swap uniforms on the multi-GPU path).
+// Counter layout: {step | round, block, stream, tag}; key = 64-bit seed.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kTagProposal = 0x50524f50u;  // lx, eta noise, proposal normals  (R:327-355)
+constexpr uint32_t kTagAccept = 0x41434350u;    // MH uniform                        (R:387)
+constexpr uint32_t kTagSwap = 0x53574150u;      // coordinator swap uniforms         (R:677)
+constexpr uint32_t kStreamCommon = 0xffffffffu; // common-random-numbers stream      
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__host__ __device__ __forceinline__ void philox_draw(uint64_t seed, uint32_t a, uint32_t b, uint32_t s,
+                                                     uint32_t tag, uint32_t (&out)[4]) {
+    out[0] = a; out[1] = b; out[2] = s; out[3] = tag;
+    philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 24-bit uniforms: exactly representable in float32, so host and device agree bit-for-bit.
+__host__ __device__ __forceinline__ float u01_open_right(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }      // [0,1)
+__host__ __device__ __forceinline__ float u01_open_left(uint32_t x) { return (float)((x >> 8) + 1u) * (1.0f / 16777216.0f); } // (0,1]
+
+#ifdef __CUDACC__
+// Box-Muller; two uniforms -> two standard normals.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, float &z1) {
+    const float r = sqrtf(-2.0f * logf(u01_open_left(a)));
+    float s, c;
+    sincospif(2.0f * u01_open_right(b), &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// The draws of one replica-step, shared by the chain kernel and ptfnn_generate_draws so that the
+// verification dump is the same code path.
+struct StepDraws {
+    float lx, z_eta, u;
+};
+__device__ __forceinline__ StepDraws philox_step_scalars(uint64_t seed, uint32_t step, uint32_t stream,
+                                                         uint32_t replica) {
+    uint32_t c[4];
+    StepDraws d;
+    philox_draw(seed, step, 0u, stream, kTagProposal, c);
+    d.lx = u01_open_right(c[0]);
+    float z1;
+    box_muller(c[2], c[3], d.z_eta, z1);
+    philox_draw(seed, step, 0u, replica, kTagAccept, c);
+    d.u = u01_open_right(c[0]);
+    return d;
+}
+// normals z[4*blk .. 4*blk+3] of the proposal noise vector
+__device__ __forceinline__ void philox_step_normals4(uint64_t seed, uint32_t step, uint32_t stream, uint32_t blk,
+                                                     float (&z)[4]) {
+    uint32_t c[4];
+    philox_draw(seed, step, 1u + blk, stream, kTagProposal, c);
+    box_muller(c[0], c[1], z[0], z[1]);
+    box_muller(c[2], c[3], z[2], z[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// math
+// ------------------------------------------------------------------------------------------
+// Latency-critical sigmoid of the serial SGD recurrence: MUFU.EX2 + MUFU.RCP (R:43-44).
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// Sigmoid of the row-parallel likelihood pass: full-precision expf and IEEE division.
+__device__ __forceinline__ float sigmoid_precise(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+template <bool PRECISE>
+__device__ __forceinline__ float sigmoid_sel(float z) {
+    if constexpr (PRECISE) return sigmoid_precise(z);
+    else return sigmoid_fast(z);
+}
+
+__device__ __forceinline__ float warp_sum(float v, int levels) {
+    // xor butterfly over the lowest 2^levels lanes (callers with H <= 16 need fewer levels)
+    if (levels >= 5) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (levels >= 4) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (levels >= 3) v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (levels >= 2) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (levels >= 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of K doubles.  `scratch` holds K * (NT/32) doubles.  Result valid in ALL threads.
+template <int K, int NT>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *scratch) {
+    constexpr int NW = NT / kWarp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum_d(v[k]);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[k * NW + warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += scratch[k * NW + w];  // fixed order: deterministic
+        v[k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier: stage the training/test sets into shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// grid-wide barrier for the swap round (cooperative launch guarantees co-residency).
+// Replaces the reference's per-replica Event pair (R:432-434, R:730-752).
+// ------------------------------------------------------------------------------------------
+struct GridBarrier {
+    unsigned int count;
+    unsigned int generation;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int gen = ld_acquire_u32(&b->generation);
+        __threadfence();
+        if (atomicAdd(&b->count, 1u) == nblocks - 1u) {
+            b->count = 0u;
+            __threadfence();
+            atomicAdd(&b->generation, 1u);
+        } else {
+            while (ld_acquire_u32(&b->generation) == gen) __nanosleep(32);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// swap rule (R:674): min(1, 0.5 * exp(min(709, l2 - l1))); sequential sweep (R:741-748).
+// One thread; lh/src live in shared memory.  Returns the number of accepted swaps.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double swap_probability(double l1, double l2) {
+    double d = l2 - l1;
+    if (d > 709.0) d = 709.0;
+    const double p = 0.5 * exp(d);
+    return p < 1.0 ? p : 1.0;  // NaN -> 1, like Python's min(1, nan)
+}
+
+template <class UFn>
+__device__ __forceinline__ int swap_sweep_serial(int n, double *lh, int *src, uint8_t *swapped_out, UFn u_of) {
+    int ns = 0;
+    for (int k = 0; k + 1 < n; ++k) {
+        const bool s = (double)u_of(k) < swap_probability(lh[k], lh[k + 1]);
+        if (s) {
+            const double t = lh[k]; lh[k] = lh[k + 1]; lh[k + 1] = t;
+            const int ti = src[k]; src[k] = src[k + 1]; src[k + 1] = ti;
+            ++ns;
+        }
+        if (swapped_out) swapped_out[k] = (uint8_t)s;
+    }
+    return ns;
+}
+#endif  // __CUDACC__
+
+}  // namespace ptfnn

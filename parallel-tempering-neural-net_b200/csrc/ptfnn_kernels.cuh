@@ -1,0 +1,800 @@
+// Kernels of the sm_100a parallel-tempering FNN sampler (templated on the topology [I,H,O] and task).
+//
+//   K1  lik_rows      row-parallel forward + Gaussian / softmax-of-sigmoid reduction
+//                     (Network.evaluate_proposal R:120-134 / C:134-153, likelihood_func R:200-205 / C:209-222)
+//   K2  SgdWarp       the serial online-SGD recurrence ("Langevin gradient", R:99-118 + R:51-78 / C:72-82)
+//   K3  chain_kernel  persistent per-temperature MCMC loop (ptReplica.run R:313-437 / C:313-448)
+//   K4  swap round    grid barrier + sequential sweep + row exchange (R:427-437, R:659-690, R:741-752)
+//
+// One CTA per temperature.  Warp 0 owns the serial recurrence (hidden units live in its lanes'
+// registers); the remaining warps run the row-parallel likelihood of the proposal at the same time.
+#pragma once
+#include "ptfnn_device.cuh"
+
+namespace ptfnn {
+
+template <int I>
+struct IPad {
+    static constexpr int value = (I + 3) & ~3;
+};
+
+struct DataView {
+    const float *x;  // [n][IP] row-major, zero padded to a multiple of 4 floats (16-byte rows for TMA / LDS.128)
+    const float *y;  // [n]     regression target (R:201) or class label as float (C:210)
+    int n;
+};
+
+constexpr int kTileRows = 128;  // rows per TMA tile when the training set is streamed instead of staged
+
+// ==========================================================================================
+// K2: serial SGD recurrence, one warp.  Lane l owns hidden units l, l+32, ... in registers.
+// ==========================================================================================
+template <int I, int H, int O, int TASK>
+struct SgdWarp {
+    static constexpr int HPL = (H + 31) / 32;
+    static constexpr int IP = IPad<I>::value;
+    static constexpr int LEVELS = H > 16 ? 5 : H > 8 ? 4 : H > 4 ? 3 : H > 2 ? 2 : H > 1 ? 1 : 0;
+    float w1[HPL][I], b1[HPL], w2[HPL][O], b2[O];
+
+    // weight vector layout a1 (R:80-90): [W1 (I x H), W2 (H x O), B1 (H), B2 (O)]
+    __device__ __forceinline__ void load(const float *w, int lane) {
+#pragma unroll
+        for (int k = 0; k < HPL; ++k) {
+            const int h = lane + 32 * k;
+            const bool a = h < H;
+#pragma unroll
+            for (int i = 0; i < I; ++i) w1[k][i] = a ? w[i * H + h] : 0.0f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) w2[k][o] = a ? w[I * H + h * O + o] : 0.0f;
+            b1[k] = a ? w[I * H + H * O + h] : 0.0f;
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) b2[o] = w[I * H + H * O + H + o];
+    }
+    __device__ __forceinline__ void store(float *w, int lane) const {
+#pragma unroll
+        for (int k = 0; k < HPL; ++k) {
+            const int h = lane + 32 * k;
+            if (h < H) {
+#pragma unroll
+                for (int i = 0; i < I; ++i) w[i * H + h] = w1[k][i];
+#pragma unroll
+                for (int o = 0; o < O; ++o) w[I * H + h * O + o] = w2[k][o];
+                w[I * H + H * O + h] = b1[k];
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int o = 0; o < O; ++o) w[I * H + H * O + H + o] = b2[o];
+        }
+    }
+
+    // One row: ForwardPass (R:51-55) then BackwardPass (R:57-78 / C:72-82).  xrow is warp-uniform.
+    __device__ __forceinline__ void row(const float *xrow, float yv, float lr, int lane) {
+        float x[IP];
+#pragma unroll
+        for (int q = 0; q < IP / 4; ++q) {
+            const float4 v = reinterpret_cast<const float4 *>(xrow)[q];
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+        float hid[HPL];
+        float p[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) p[o] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < HPL; ++k) {
+            float z = -b1[k];                                   // bias is SUBTRACTED (R:52)
+#pragma unroll
+            for (int i = 0; i < I; ++i) z = fmaf(x[i], w1[k][i], z);
+            hid[k] = (lane + 32 * k < H) ? sigmoid_fast(z) : 0.0f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) p[o] = fmaf(hid[k], w2[k][o], p[o]);
+        }
+        float od[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            const float out = sigmoid_fast(warp_sum(p[o], LEVELS) - b2[o]);       // R:54-55
+            float d;
+            if constexpr (TASK == kTaskCls) d = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75 one-hot
+            else d = yv;                                                          // O == 1 (R:132)
+            od[o] = (d - out) * (out * (1.0f - out));                             // R:58
+        }
+#pragma unroll
+        for (int k = 0; k < HPL; ++k) {
+            float s = 0.0f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) s = fmaf(od[o], w2[k][o], s);             // pre-update W2 (R:59)
+            const float hd = s * (hid[k] * (1.0f - hid[k]));
+#pragma unroll
+            for (int o = 0; o < O; ++o) w2[k][o] = fmaf(lr * od[o], hid[k], w2[k][o]);   // R:67-69
+            const float lh = lr * hd;
+#pragma unroll
+            for (int i = 0; i < I; ++i) w1[k][i] = fmaf(lh, x[i], w1[k][i]);      // R:74-76
+            b1[k] -= lh;                                                          // R:77-78
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) b2[o] -= lr * od[o];                          // R:70-71
+    }
+};
+
+// Streaming state of the SGD warp when the training set does not fit in shared memory:
+// two TMA tiles, one mbarrier each.
+struct SgdStream {
+    float *tile_x[2];
+    float *tile_y[2];
+    uint64_t *bar[2];
+    uint32_t parity[2];
+};
+
+// One epoch of online SGD over the training rows in order.  Called by warp 0 only.
+template <int I, int H, int O, int TASK>
+__device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const DataView &d, bool staged,
+                                         float lr, SgdStream &st) {
+    constexpr int IP = IPad<I>::value;
+    const int lane = threadIdx.x & 31;
+    SgdWarp<I, H, O, TASK> net;
+    net.load(w_in, lane);
+    if (staged) {
+        for (int r = 0; r < d.n; ++r) net.row(d.x + (size_t)r * IP, d.y[r], lr, lane);
+    } else {
+        const int ntiles = (d.n + kTileRows - 1) / kTileRows;
+        auto issue = [&](int t) {
+            const int b = t & 1;
+            const int rows = min(kTileRows, d.n - t * kTileRows);
+            const uint32_t bx = (uint32_t)rows * IP * 4u;
+            const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;   // y is allocated padded to 4 floats
+            if (lane == 0) {
+                mbar_arrive_expect_tx(st.bar[b], bx + by);
+                tma_load_1d(st.tile_x[b], d.x + (size_t)t * kTileRows * IP, bx, st.bar[b]);
+                tma_load_1d(st.tile_y[b], d.y + (size_t)t * kTileRows, by, st.bar[b]);
+            }
+        };
+        issue(0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1;
+            __syncwarp();                      // every lane is done reading the buffer about to be refilled
+            if (t + 1 < ntiles) issue(t + 1);
+            mbar_wait(st.bar[b], st.parity[b]);
+            st.parity[b] ^= 1u;
+            const int rows = min(kTileRows, d.n - t * kTileRows);
+            const float *xs = st.tile_x[b];
+            const float *ys = st.tile_y[b];
+            for (int r = 0; r < rows; ++r) net.row(xs + r * IP, ys[r], lr, lane);
+        }
+    }
+    net.store(w_out, lane);
+}
+
+// ==========================================================================================
+// K1: row-parallel forward + likelihood partial sums.  Thread t of a team of nt threads takes
+// rows t, t+nt, ...  (RB rows at a time so each broadcast weight load is reused RB times).
+//   regression:      s0 += (y - fx)^2
+//   classification:  s0 += log softmax(out)[label] (C:215-219), s1 += (argmax - y)^2 (C:212),
+//                    correct += (argmax == y) (C:200-207)
+// ==========================================================================================
+template <int I, int H, int O, int TASK, int RB, bool PRECISE, bool WRITE>
+__device__ __forceinline__ void lik_rows_impl(const float *__restrict__ w, const DataView &d, int t, int nt,
+                                              double &s0, double &s1, int &correct, float *fx_out,
+                                              float *prob_out) {
+    constexpr int IP = IPad<I>::value;
+    constexpr int oW2 = I * H, oB1 = I * H + H * O, oB2 = I * H + H * O + H;
+    constexpr int HU = (H <= 16) ? H : 4;
+    for (int r0 = t * RB; r0 < d.n; r0 += nt * RB) {
+        float x[RB][IP];
+        float acc[RB][O];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            const int r = min(r0 + b, d.n - 1);
+            const float4 *xr = reinterpret_cast<const float4 *>(d.x + (size_t)r * IP);
+#pragma unroll
+            for (int q = 0; q < IP / 4; ++q) {
+                const float4 v = xr[q];
+                x[b][4 * q] = v.x; x[b][4 * q + 1] = v.y; x[b][4 * q + 2] = v.z; x[b][4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int o = 0; o < O; ++o) acc[b][o] = -w[oB2 + o];
+        }
+#pragma unroll HU
+        for (int h = 0; h < H; ++h) {
+            float w1h[I], w2h[O];
+#pragma unroll
+            for (int i = 0; i < I; ++i) w1h[i] = w[i * H + h];
+#pragma unroll
+            for (int o = 0; o < O; ++o) w2h[o] = w[oW2 + h * O + o];
+            const float nb = -w[oB1 + h];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                float z = nb;
+#pragma unroll
+                for (int i = 0; i < I; ++i) z = fmaf(x[b][i], w1h[i], z);
+                const float hid = sigmoid_sel<PRECISE>(z);
+#pragma unroll
+                for (int o = 0; o < O; ++o) acc[b][o] = fmaf(hid, w2h[o], acc[b][o]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            const int r = r0 + b;
+            if (r < d.n) {
+                const float yv = d.y[r];
+                if constexpr (TASK == kTaskReg) {
+                    const float fx = sigmoid_sel<PRECISE>(acc[b][0]);             // R:55, R:132
+                    const float e = yv - fx;
+                    s0 += (double)(e * e);
+                    if constexpr (WRITE) fx_out[r] = fx;
+                } else {
+                    float out[O];
+                    int am = 0;
+                    float se = 0.0f;
+#pragma unroll
+                    for (int o = 0; o < O; ++o) {
+                        out[o] = sigmoid_sel<PRECISE>(acc[b][o]);
+                        se += PRECISE ? expf(out[o]) : __expf(out[o]);            // C:108-110
+                    }
+#pragma unroll
+                    for (int o = 1; o < O; ++o) am = (out[o] > out[am]) ? o : am; // np.argmax: first max
+                    const int lab = (int)yv;
+                    float ol = out[0];
+#pragma unroll
+                    for (int o = 1; o < O; ++o) ol = (o == lab) ? out[o] : ol;
+                    s0 += (double)(ol - (PRECISE ? logf(se) : __logf(se)));
+                    const float e = (float)am - yv;
+                    s1 += (double)(e * e);
+                    correct += ((float)am == yv) ? 1 : 0;
+                    if constexpr (WRITE) {
+                        fx_out[r] = (float)am;
+                        if (prob_out) {
+#pragma unroll
+                            for (int o = 0; o < O; ++o) prob_out[(size_t)r * O + o] = expf(out[o]) / se;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int I, int H, int O, int TASK, bool PRECISE, bool WRITE>
+__device__ __forceinline__ void lik_rows(const float *__restrict__ w, const DataView &d, int t, int nt, double &s0,
+                                         double &s1, int &correct, float *fx_out = nullptr,
+                                         float *prob_out = nullptr) {
+    constexpr int IP = IPad<I>::value;
+    // row blocking only pays when every thread has several rows and the registers allow it
+    constexpr int RBMAX = (IP * 4 + O * 4 <= 96) ? 4 : ((IP * 2 + O * 2 <= 96) ? 2 : 1);
+    if (RBMAX >= 4 && d.n >= 8 * nt) lik_rows_impl<I, H, O, TASK, RBMAX, PRECISE, WRITE>(w, d, t, nt, s0, s1, correct, fx_out, prob_out);
+    else if (RBMAX >= 2 && d.n >= 4 * nt) lik_rows_impl<I, H, O, TASK, 2, PRECISE, WRITE>(w, d, t, nt, s0, s1, correct, fx_out, prob_out);
+    else lik_rows_impl<I, H, O, TASK, 1, PRECISE, WRITE>(w, d, t, nt, s0, s1, correct, fx_out, prob_out);
+}
+
+// ==========================================================================================
+// K3 + K4: the persistent chain kernel
+// ==========================================================================================
+struct ChainParams {
+    // ---- configuration
+    int R, Rg, replica_offset;     // local replicas, whole ladder, ladder index of local replica 0
+    int S, swap_interval, swap_rule;
+    int use_lg, crn, memo, external_swap, debug;
+    int step_begin, step_end;      // steps [begin, end) this launch
+    int round_begin;               // swap rounds completed before this launch
+    int final_round;               // 1: after the last step run the left-over coordinator round
+    int replay, replay_n;          // draws come from HBM arrays covering steps [step_begin, step_begin+replay_n)
+    int staged;                    // datasets fit in shared memory
+    double l_prob, pt_samples, sigma_sq, nu1, nu2;
+    float lr, step_w, step_eta;
+    uint64_t seed;
+    const double *temperature;     // [R]
+    // ---- data
+    DataView train, test;
+    // ---- chain state (global, one row per local replica)
+    float *w;                      // [R][P]
+    double *eta, *tau, *lik, *prior;
+    int *n_acc, *init_count;
+    float *last_w;                 // [R][P]  last recorded pos_w row (R:417)
+    double *last4;                 // [R][4]  rmse_train, rmse_test, acc_train, acc_test carried rows (R:420-423)
+    float *gd_cache;               // [R][P]  langevin_gradient(w) memo
+    int *gd_valid;                 // [R]
+    // ---- traces
+    float *pos_w;                  // [R][S][P]
+    double *lik_prop, *rmse_tr, *rmse_te, *acc_tr, *acc_te;   // [R][S]
+    int *accept_list;              // [R][S]
+    double *dbg_prior, *dbg_diff, *dbg_mh;                    // [R][S] (debug)
+    uint8_t *dbg_acc;
+    // ---- replay draws
+    const float *lx, *z, *z_eta, *u, *u_swap;
+    // ---- swap round
+    float *pub_rows;               // [2][R][P+1]   (w, eta) published at the hand-shake (R:430-431)
+    double *pub_lhood;             // [2][Rg]       lhood field (R:430 / C:439)
+    GridBarrier *barrier;
+    long long *swap_counters;      // {num_swap, total_swap_proposals}  (R:680-688)
+    uint8_t *swap_log;             // [rounds][Rg-1]
+    int max_rounds;
+};
+
+__device__ __forceinline__ bool swap_due(int rule, int s, int i) {
+    return rule == 0 ? (i % s == 0 && i != 0) : ((i + 1) % s == 0);                // R:427 | C:438
+}
+__device__ __forceinline__ int next_swap_step(int rule, int s, int i) {
+    if (rule == 0) { const int k = (i + s - 1) / s; return (k < 1 ? 1 : k) * s; }
+    return ((i + s) / s) * s - 1;
+}
+
+template <int I, int H, int O>
+struct NetSizes {
+    static constexpr int P = I * H + H * O + H + O;
+    static constexpr int IP = IPad<I>::value;
+};
+
+// dynamic shared memory layout (floats unless noted); host computes the same with chain_smem_bytes()
+struct ChainSmem {
+    int P4;          // P rounded up to 4
+    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep_l, off_sweep_s,
+        off_stage, total;
+};
+__host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
+                                                       int n_test) {
+    ChainSmem L;
+    L.P4 = (P + 3) & ~3;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+    L.off_w = take(L.P4 * 4); L.off_prop = take(L.P4 * 4); L.off_gd = take(L.P4 * 4);
+    L.off_pgd = take(L.P4 * 4); L.off_last = take(L.P4 * 4);
+    L.off_red = take((size_t)8 * (nt / 32) * 8);
+    L.off_bar = take(8 * 4);
+    L.off_tiles = take(staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4));
+    L.off_sweep_l = take((size_t)Rg * 8);
+    L.off_sweep_s = take((size_t)Rg * 4);
+    auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
+    L.off_stage = take(staged ? ((size_t)n_train * IP + pad4(n_train) + (size_t)n_test * IP + pad4(n_test)) * 4 : 0);
+    L.total = o;
+    return L;
+}
+
+template <int I, int H, int O, int TASK, int NT>
+__global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
+    constexpr int P = NetSizes<I, H, O>::P;
+    constexpr int IP = NetSizes<I, H, O>::IP;
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ChainSmem L = chain_smem_layout(P, IP, NT, p.Rg, p.staged != 0, p.train.n, p.test.n);
+    float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
+    float *s_prop = reinterpret_cast<float *>(smem_raw + L.off_prop);
+    float *s_gd = reinterpret_cast<float *>(smem_raw + L.off_gd);
+    float *s_pgd = reinterpret_cast<float *>(smem_raw + L.off_pgd);
+    float *s_last = reinterpret_cast<float *>(smem_raw + L.off_last);
+    double *s_red = reinterpret_cast<double *>(smem_raw + L.off_red);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + L.off_bar);
+    double *s_sweep_l = reinterpret_cast<double *>(smem_raw + L.off_sweep_l);
+    int *s_sweep_src = reinterpret_cast<int *>(smem_raw + L.off_sweep_s);
+    __shared__ int s_flag[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time setup: mbarriers; stage both datasets into shared memory with TMA bulk copies
+    DataView train = p.train, test = p.test;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    SgdStream stream;
+    if (p.staged) {
+        auto pad4 = [](int n) { return (n + 3) & ~3; };
+        float *sx_tr = reinterpret_cast<float *>(smem_raw + L.off_stage);
+        float *sy_tr = sx_tr + (size_t)train.n * IP;
+        float *sx_te = sy_tr + pad4(train.n);
+        float *sy_te = sx_te + (size_t)test.n * IP;
+        if (tid == 0) {
+            const uint32_t b0 = (uint32_t)train.n * IP * 4u, b1 = (uint32_t)pad4(train.n) * 4u;
+            const uint32_t b2 = (uint32_t)test.n * IP * 4u, b3 = (uint32_t)pad4(test.n) * 4u;
+            mbar_arrive_expect_tx(&s_bar[2], b0 + b1 + b2 + b3);
+            tma_load_1d(sx_tr, train.x, b0, &s_bar[2]);
+            tma_load_1d(sy_tr, train.y, b1, &s_bar[2]);
+            tma_load_1d(sx_te, test.x, b2, &s_bar[2]);
+            tma_load_1d(sy_te, test.y, b3, &s_bar[2]);
+        }
+        mbar_wait(&s_bar[2], 0);
+        train.x = sx_tr; train.y = sy_tr; test.x = sx_te; test.y = sy_te;
+    } else {
+        float *tiles = reinterpret_cast<float *>(smem_raw + L.off_tiles);
+        stream.tile_x[0] = tiles;
+        stream.tile_x[1] = tiles + kTileRows * IP;
+        stream.tile_y[0] = tiles + 2 * kTileRows * IP;
+        stream.tile_y[1] = tiles + 2 * kTileRows * IP + kTileRows;
+        stream.bar[0] = &s_bar[0]; stream.bar[1] = &s_bar[1];
+    }
+    stream.parity[0] = stream.parity[1] = 0u;
+
+    const int nblocks = gridDim.x;
+    int step = p.step_begin;
+    int round = p.round_begin;
+    const double inv_sig2 = 1.0 / ((double)p.step_w * (double)p.step_w);
+
+    while (step < p.step_end) {
+        int seg_last = p.Rg > 1 ? next_swap_step(p.swap_rule, p.swap_interval, step) : p.step_end - 1;
+        bool swap_at_end = p.Rg > 1;
+        if (seg_last > p.step_end - 1) { seg_last = p.step_end - 1; swap_at_end = false; }
+        const int parity = round & 1;
+
+        for (int r = blockIdx.x; r < p.R; r += nblocks) {
+            // ---------------- load this replica's state ----------------
+            for (int j = tid; j < P; j += NT) {
+                s_w[j] = p.w[(size_t)r * P + j];
+                s_last[j] = p.last_w[(size_t)r * P + j];
+                s_gd[j] = p.gd_cache[(size_t)r * P + j];
+            }
+            double eta = p.eta[r], tau = p.tau[r], lik = p.lik[r], prior_cur = p.prior[r];
+            int n_acc = p.n_acc[r], init_count = p.init_count[r];
+            int gd_valid = p.memo ? p.gd_valid[r] : 0;
+            double last_rtr = p.last4[r * 4 + 0], last_rte = p.last4[r * 4 + 1];
+            double last_atr = p.last4[r * 4 + 2], last_ate = p.last4[r * 4 + 3];
+            const double temperature = p.temperature[r];
+            const uint32_t gr = (uint32_t)(p.replica_offset + r);
+            const uint32_t rng_stream = p.crn ? kStreamCommon : gr;
+            __syncthreads();
+
+            for (int i = step; i <= seg_last; ++i) {
+                // ---- a11: temperature schedule inside the chain (R:317-324)
+                double adapt = init_count ? 1.0 : temperature;
+                if ((double)i == p.pt_samples && init_count == 0) {
+                    adapt = 1.0;
+                    init_count = 1;
+                    double s[2] = {0.0, 0.0};
+                    double dummy = 0.0;
+                    int c0 = 0;
+                    lik_rows<I, H, O, TASK, true, false>(s_w, train, tid, NT, s[0], dummy, c0);
+                    block_sum<2, NT>(s, s_red);
+                    if constexpr (TASK == kTaskReg)
+                        lik = (-0.5 * train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / adapt;
+                    else
+                        lik = s[0] / adapt;
+                }
+                // ---- draws (a9): lx, proposal noise, eta noise, MH uniform
+                float lx, z_eta, u;
+                const int di = i - p.step_begin;
+                if (p.replay) {
+                    const size_t q = (size_t)r * p.replay_n + di;
+                    lx = p.lx[q];
+                    z_eta = (TASK == kTaskReg && p.z_eta) ? p.z_eta[q] : 0.0f;
+                    u = p.u[q];
+                } else {
+                    const StepDraws sd = philox_step_scalars(p.seed, (uint32_t)i, rng_stream, gr);
+                    lx = sd.lx; z_eta = sd.z_eta; u = sd.u;
+                }
+                const bool lg = p.use_lg && ((double)lx < p.l_prob);              // R:329
+                // ---- Langevin branch, first SGD epoch: w_gd = langevin_gradient(w)   (R:330)
+                if (lg && !gd_valid) {
+                    if (warp == 0) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
+                    __syncthreads();
+                    gd_valid = p.memo;
+                }
+                // ---- proposal: w_prop = (w_gd | w) + step_w * z                     (R:331 | R:353)
+                {
+                    const float *base = lg ? s_gd : s_w;
+                    if (p.replay) {
+                        const float *zz = p.z + ((size_t)r * p.replay_n + di) * P;
+                        for (int j = tid; j < P; j += NT) s_prop[j] = fmaf(p.step_w, zz[j], base[j]);
+                    } else {
+                        for (int b = tid; b < (P + 3) / 4; b += NT) {
+                            float z4[4];
+                            philox_step_normals4(p.seed, (uint32_t)i, rng_stream, (uint32_t)b, z4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int j = 4 * b + k;
+                                if (j < P) s_prop[j] = fmaf(p.step_w, z4[k], base[j]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- second SGD epoch on warp 0 (R:332) WHILE the other warps evaluate the
+                //      proposal's likelihood on train and test (R:360-362)
+                double s[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[k] = 0.0;
+                int c_tr = 0, c_te = 0;
+                if (lg && NW > 1) {
+                    if (warp == 0) {
+                        sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
+                    } else {
+                        lik_rows<I, H, O, TASK, true, false>(s_prop, train, tid - 32, NT - 32, s[0], s[1], c_tr);
+                        lik_rows<I, H, O, TASK, true, false>(s_prop, test, tid - 32, NT - 32, s[2], s[3], c_te);
+                    }
+                } else {
+                    if (lg) {
+                        if (warp == 0) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
+                        __syncthreads();
+                    }
+                    lik_rows<I, H, O, TASK, true, false>(s_prop, train, tid, NT, s[0], s[1], c_tr);
+                    lik_rows<I, H, O, TASK, true, false>(s_prop, test, tid, NT, s[2], s[3], c_te);
+                }
+                __syncthreads();
+                // ---- reductions: likelihood sums, |w_prop|^2 (prior), Langevin asymmetry norms
+                s[4] = (double)c_tr; s[5] = (double)c_te;
+                {
+                    double sq = 0.0, first = 0.0, second = 0.0;
+                    for (int j = tid; j < P; j += NT) {
+                        const float wp = s_prop[j];
+                        sq += (double)wp * (double)wp;
+                        if (lg) {
+                            const double a = (double)s_w[j] - (double)s_pgd[j];     // wc_delta (R:336)
+                            const double b = (double)wp - (double)s_gd[j];          // wp_delta (R:337)
+                            first += a * a; second += b * b;
+                        }
+                    }
+                    s[6] = sq;
+                    s[7] = second - first;   // -> diff_prop = 0.5*(second-first)/sigma^2 / adapttemp
+                }
+                block_sum<8, NT>(s, s_red);
+                // ---- scalars (every thread computes the same values; thread 0 records them)
+                double eta_pro = eta;
+                if constexpr (TASK == kTaskReg) {
+                    eta_pro = eta + (double)p.step_eta * (double)z_eta;             // R:355
+                    tau = exp(eta_pro);                                             // R:356
+                }
+                double lik_prop, rmse_tr, rmse_te, acc_tr = 0.0, acc_te = 0.0, prior_prop;
+                if constexpr (TASK == kTaskReg) {
+                    lik_prop = (-0.5 * train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / adapt;  // R:204-205
+                    rmse_tr = sqrt(s[0] / train.n);
+                    rmse_te = sqrt(s[2] / test.n);
+                    prior_prop = -((I * H + H + 2) / 2.0) * log(p.sigma_sq) - s[6] / (2.0 * p.sigma_sq) -
+                                 (1.0 + p.nu1) * log(tau) - p.nu2 / tau;           // R:218-220
+                } else {
+                    lik_prop = s[0] / adapt;                                        // C:222
+                    rmse_tr = sqrt(s[1] / train.n);
+                    rmse_te = sqrt(s[3] / test.n);
+                    acc_tr = 100.0 * (s[4] / train.n);
+                    acc_te = 100.0 * (s[5] / test.n);
+                    prior_prop = -((I * H + H + O + H * O) / 2.0) * log(p.sigma_sq) - s[6] / (2.0 * p.sigma_sq);  // C:227-229
+                }
+                const double diff_prop = lg ? (0.5 * s[7] * inv_sig2) / adapt : 0.0;   // R:341-346 (Q4)
+                const double a = (lik_prop - lik) + (prior_prop - prior_cur) + diff_prop;   // R:365-373
+                double mh = exp(a);
+                if (!(mh < 1.0)) mh = 1.0;     // min(1, .): overflow -> 1 (R:375); NaN -> 1 (Python min)
+                const bool accept = (double)u < mh;                                   // R:395
+                // ---- traces of row i+1
+                const size_t ti = (size_t)r * p.S + (i + 1);
+                if (tid == 0) {
+                    p.accept_list[ti] = n_acc;                                        // R:380 (count BEFORE)
+                    p.lik_prop[ti] = (TASK == kTaskReg) ? lik_prop : lik_prop * adapt;    // R:391 / C:404
+                    if (p.debug) {
+                        p.dbg_prior[ti] = prior_prop; p.dbg_diff[ti] = diff_prop; p.dbg_mh[ti] = mh;
+                        p.dbg_acc[ti] = accept ? 1 : 0;
+                    }
+                }
+                if (accept) {
+                    n_acc += 1; lik = lik_prop; prior_cur = prior_prop; eta = eta_pro;
+                    last_rtr = rmse_tr; last_rte = rmse_te;
+                    if constexpr (TASK == kTaskCls) { last_atr = acc_tr; last_ate = acc_te; }   // C:414-415 (Q13)
+                    else { last_atr = 0.0; last_ate = 0.0; }                                   // R:403-404
+                    for (int j = tid; j < P; j += NT) {
+                        const float v = s_prop[j];
+                        s_w[j] = v; s_last[j] = v;
+                        if (lg && p.memo) s_gd[j] = s_pgd[j];   // langevin_gradient(new w) is already known
+                    }
+                    gd_valid = (lg && p.memo) ? 1 : 0;
+                }
+                if (tid == 0) {
+                    p.rmse_tr[ti] = last_rtr; p.rmse_te[ti] = last_rte;
+                    p.acc_tr[ti] = last_atr; p.acc_te[ti] = last_ate;
+                }
+                __syncthreads();
+                float *pw = p.pos_w + ti * P;
+                for (int j = tid; j < P; j += NT) pw[j] = s_last[j];                  // R:408 | R:417
+            }
+
+            // ---------------- publish for the hand-shake (R:427-431 / C:438-440) ----------------
+            if (swap_at_end) {
+                float *row = p.pub_rows + ((size_t)parity * p.R + r) * (P + 1);
+                for (int j = tid; j < P; j += NT) row[j] = s_w[j];
+                if (tid == 0) {
+                    row[P] = (float)eta;
+                    p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] =
+                        (TASK == kTaskReg) ? lik * temperature : lik;                 // R:430 (Q8) | C:439
+                }
+            }
+            // ---------------- store state ----------------
+            for (int j = tid; j < P; j += NT) {
+                p.w[(size_t)r * P + j] = s_w[j];
+                p.last_w[(size_t)r * P + j] = s_last[j];
+                if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j];
+            }
+            if (tid == 0) {
+                p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior_cur;
+                p.n_acc[r] = n_acc; p.init_count[r] = init_count; p.gd_valid[r] = gd_valid;
+                p.last4[r * 4 + 0] = last_rtr; p.last4[r * 4 + 1] = last_rte;
+                p.last4[r * 4 + 2] = last_atr; p.last4[r * 4 + 3] = last_ate;
+            }
+            __syncthreads();
+        }
+        step = seg_last + 1;
+
+        if (swap_at_end) {
+            if (p.external_swap) break;   // multi-GPU: the host completes the round (ptfnn_swap_*)
+            // ---------------- K4: swap round ----------------
+            grid_barrier(p.barrier, nblocks);
+            for (int k = tid; k < p.Rg; k += NT) {
+                s_sweep_l[k] = __ldcg(&p.pub_lhood[(size_t)parity * p.Rg + k]);
+                s_sweep_src[k] = k;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const bool log_it = blockIdx.x == 0 && round < p.max_rounds;
+                uint8_t *lg_out = log_it ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
+                int ns;
+                if (p.replay) {
+                    const float *ur = p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1);
+                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) { return ur[k]; });
+                } else {
+                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) {
+                        uint32_t c[4];
+                        philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
+                        return u01_open_right(c[0]);
+                    });
+                }
+                if (blockIdx.x == 0) { p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1; }
+            }
+            __syncthreads();
+            // take back ONLY w and eta (R:435-437); likelihood / prior stay stale
+            for (int r = blockIdx.x; r < p.R; r += nblocks) {
+                const int src = s_sweep_src[p.replica_offset + r] - p.replica_offset;
+                if (src != r) {
+                    const float *row = p.pub_rows + ((size_t)parity * p.R + src) * (P + 1);
+                    for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
+                    if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
+                }
+            }
+            __syncthreads();
+            ++round;
+        }
+    }
+
+    // ---------------- left-over coordinator round on the exit vectors (R:442-444) -------------
+    if (p.final_round && !p.external_swap && step >= p.step_end) {
+        const int parity = round & 1;
+        for (int r = blockIdx.x; r < p.R; r += nblocks)
+            if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = p.lik[r];
+        grid_barrier(p.barrier, nblocks);
+        if (blockIdx.x == 0) {
+            for (int k = tid; k < p.Rg; k += NT) {
+                s_sweep_l[k] = __ldcg(&p.pub_lhood[(size_t)parity * p.Rg + k]);
+                s_sweep_src[k] = k;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint8_t *lg_out = round < p.max_rounds ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
+                int ns;
+                if (p.replay) {
+                    const float *ur = p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1);
+                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) { return ur[k]; });
+                } else {
+                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) {
+                        uint32_t c[4];
+                        philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
+                        return u01_open_right(c[0]);
+                    });
+                }
+                p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1;
+            }
+        }
+    }
+    (void)s_flag;
+}
+
+// ==========================================================================================
+// pre-loop part of ptReplica.run (R:266-285 / C:271-284): eta = log var(fx - y), tau, prior,
+// current likelihood; also resets the carried trace rows.  One CTA per replica.
+// ==========================================================================================
+struct InitParams {
+    int R, S;
+    double sigma_sq, nu1, nu2;
+    const double *temperature;
+    DataView train, test;
+    const float *w;
+    double *eta, *tau, *lik, *prior;
+    double *init_rmse;   // [R][2] (train, test) -- informational
+};
+
+template <int I, int H, int O, int TASK, int NT>
+__global__ void __launch_bounds__(NT) init_kernel(const InitParams p) {
+    constexpr int P = NetSizes<I, H, O>::P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_w = reinterpret_cast<float *>(smem_raw);
+    double *s_red = reinterpret_cast<double *>(smem_raw + (((size_t)P * 4 + 15) & ~(size_t)15));
+    const int r = blockIdx.x, tid = threadIdx.x;
+    for (int j = tid; j < P; j += NT) s_w[j] = p.w[(size_t)r * P + j];
+    __syncthreads();
+    double eta = 0.0, tau = 1.0;                                                  // C:263 junk variable
+    if constexpr (TASK == kTaskReg) {
+        // np.var(pred_train - y_train): two-pass population variance (R:270)
+        constexpr int IP = IPad<I>::value;
+        auto residual = [&](int row) {
+            DataView one{p.train.x + (size_t)row * IP, p.train.y + row, 1};
+            float fx = 0.0f;
+            double sse = 0.0, d1 = 0.0;
+            int c = 0;
+            lik_rows_impl<I, H, O, TASK, 1, true, true>(s_w, one, 0, 1, sse, d1, c, &fx, nullptr);
+            return (double)fx - (double)p.train.y[row];
+        };
+        double sd[1] = {0.0};
+        for (int row = tid; row < p.train.n; row += NT) sd[0] += residual(row);
+        block_sum<1, NT>(sd, s_red);
+        const double mean = sd[0] / p.train.n;
+        double sv[1] = {0.0};
+        for (int row = tid; row < p.train.n; row += NT) {
+            const double dv = residual(row) - mean;
+            sv[0] += dv * dv;
+        }
+        block_sum<1, NT>(sv, s_red);
+        eta = log(sv[0] / p.train.n);
+        tau = exp(eta);                                                           // R:271
+    }
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int c0 = 0, c1 = 0;
+    lik_rows<I, H, O, TASK, true, false>(s_w, p.train, tid, NT, s[0], s[1], c0);
+    lik_rows<I, H, O, TASK, true, false>(s_w, p.test, tid, NT, s[2], s[3], c1);
+    for (int j = tid; j < P; j += NT) s[4] += (double)s_w[j] * (double)s_w[j];
+    block_sum<5, NT>(s, s_red);
+    if (tid == 0) {
+        const double T = p.temperature[r];
+        double lik, prior;
+        if constexpr (TASK == kTaskReg) {
+            lik = (-0.5 * p.train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / T;   // R:284
+            prior = -((I * H + H + 2) / 2.0) * log(p.sigma_sq) - s[4] / (2.0 * p.sigma_sq) -
+                    (1.0 + p.nu1) * log(tau) - p.nu2 / tau;                                              // R:280
+            p.init_rmse[r * 2 + 0] = sqrt(s[0] / p.train.n);
+            p.init_rmse[r * 2 + 1] = sqrt(s[2] / p.test.n);
+        } else {
+            lik = s[0] / T;                                                                              // C:283
+            prior = -((I * H + H + O + H * O) / 2.0) * log(p.sigma_sq) - s[4] / (2.0 * p.sigma_sq);      // C:281
+            p.init_rmse[r * 2 + 0] = sqrt(s[1] / p.train.n);
+            p.init_rmse[r * 2 + 1] = sqrt(s[3] / p.test.n);
+        }
+        p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior;
+    }
+}
+
+// ==========================================================================================
+// single-operation kernels (one CTA)
+// ==========================================================================================
+template <int I, int H, int O, int TASK, int NT>
+__global__ void __launch_bounds__(NT) op_forward_kernel(const float *w, DataView d, float *fx, float *prob,
+                                                        double *sums /* s0, s1, correct */) {
+    constexpr int P = NetSizes<I, H, O>::P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_w = reinterpret_cast<float *>(smem_raw);
+    double *s_red = reinterpret_cast<double *>(smem_raw + (((size_t)P * 4 + 15) & ~(size_t)15));
+    for (int j = threadIdx.x; j < P; j += NT) s_w[j] = w[j];
+    __syncthreads();
+    double s[3] = {0.0, 0.0, 0.0};
+    int c = 0;
+    lik_rows<I, H, O, TASK, true, true>(s_w, d, threadIdx.x, NT, s[0], s[1], c, fx, prob);
+    s[2] = (double)c;
+    block_sum<3, NT>(s, s_red);
+    if (threadIdx.x == 0) { sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2]; }
+}
+
+template <int I, int H, int O, int TASK>
+__global__ void __launch_bounds__(32) op_sgd_kernel(const float *w_in, float *w_out, DataView d, float lr, int depth) {
+    constexpr int P = NetSizes<I, H, O>::P;
+    constexpr int IP = IPad<I>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_w = reinterpret_cast<float *>(smem_raw);
+    const size_t wbytes = ((size_t)P * 4 + 15) & ~(size_t)15;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + wbytes);
+    float *tiles = reinterpret_cast<float *>(smem_raw + wbytes + 16);
+    for (int j = threadIdx.x; j < P; j += 32) s_w[j] = w_in[j];
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    SgdStream st;
+    st.tile_x[0] = tiles; st.tile_x[1] = tiles + kTileRows * IP;
+    st.tile_y[0] = tiles + 2 * kTileRows * IP; st.tile_y[1] = tiles + 2 * kTileRows * IP + kTileRows;
+    st.bar[0] = &s_bar[0]; st.bar[1] = &s_bar[1];
+    st.parity[0] = st.parity[1] = 0u;
+    for (int e = 0; e < depth; ++e) {                       // R:108 `depth` epochs (sgd_depth is always 1, R:170)
+        sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
+        __syncwarp();
+    }
+    for (int j = threadIdx.x; j < P; j += 32) w_out[j] = s_w[j];
+}
+
+}  // namespace ptfnn

@@ -1,0 +1,125 @@
+"""GPU parity, per function: the CUDA path (through the C ABI) against the reference's known
+answers (tests/golden/known_answers.npz, recorded from the unmodified reference) and the oracle.
+Tolerance: 1e-4 relative (BASELINE north_star, fp32 device arithmetic vs the float64 reference)."""
+import numpy as np
+import pytest
+
+from oracle import ptfnn_c as oc
+from oracle import ptfnn_numpy as on
+from ptnn_b200 import capi
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.mark.parametrize("ds", cm.REG_DATASETS)
+@pytest.mark.parametrize("H", [5, 10])
+def test_regression_ops_match_reference(ds, H):
+    ka = cm.npz("known_answers")
+    tr, te = cm.dataset(on.REGRESSION, ds)
+    key = "reg_%s_h%d_" % (ds, H)
+    topo, w, tau = (4, H, 1), ka[key + "w"], float(ka[key + "tau"])
+    fx = capi.op_evaluate_proposal(capi.TASK_REGRESSION, topo, tr, w)                    # R:120-134
+    assert cm.relerr(fx, ka[key + "fx"]) < RTOL
+    lik, rm, _, fx2 = capi.op_likelihood(capi.TASK_REGRESSION, topo, tr, w, tau, 1.25)    # R:200-205
+    lik_te, rm_te, _, _ = capi.op_likelihood(capi.TASK_REGRESSION, topo, te, w, tau, 1.25)
+    assert np.allclose([lik, rm, lik_te, rm_te], ka[key + "lik"], rtol=RTOL, atol=0)
+    assert np.array_equal(fx, fx2)
+    assert capi.op_prior(capi.TASK_REGRESSION, topo, w, tausq=tau) == pytest.approx(float(ka[key + "prior"]), rel=RTOL)
+    w_gd = capi.op_langevin_gradient(capi.TASK_REGRESSION, topo, tr, w, 0.1)             # R:99-118
+    assert cm.relerr(w_gd, ka[key + "w_gd"]) < RTOL
+
+
+@pytest.mark.parametrize("ds", cm.CLS_DATASETS)
+def test_classification_ops_match_reference(ds):
+    ka = cm.npz("known_answers")
+    tr, te = cm.dataset(on.CLASSIFICATION, ds)
+    topo = cm.cls_topology(ds)
+    key = "cls_%s_" % ds
+    w = ka[key + "w"]
+    fx, prob = capi.op_evaluate_proposal(capi.TASK_CLASSIFICATION, topo, tr, w)          # C:134-153
+    # argmax may legitimately differ only where two sigmoid outputs tie to within fp32 round-off
+    ref_prob = ka[key + "prob"]
+    top2 = np.sort(ref_prob, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5
+    assert np.array_equal(fx[clear], ka[key + "fx"][clear])
+    assert cm.relerr(prob, ref_prob) < RTOL
+    lik, rm, acc, _ = capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, tr, w, 1.0, 2.5)   # C:209-222
+    lik_te, rm_te, acc_te, _ = capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, te, w, 1.0, 2.5)
+    assert np.allclose([lik, lik_te], ka[key + "lik"][[0, 2]], rtol=RTOL, atol=0)
+    if clear.all():
+        assert np.allclose([rm, rm_te], ka[key + "lik"][[1, 3]], rtol=RTOL, atol=0)
+        assert np.allclose([acc, acc_te], ka[key + "acc"], rtol=RTOL, atol=0)
+    assert capi.op_prior(capi.TASK_CLASSIFICATION, topo, w) == pytest.approx(float(ka[key + "prior"]), rel=RTOL)
+    w_gd = capi.op_langevin_gradient(capi.TASK_CLASSIFICATION, topo, tr, w, 0.01)        # C:114-132
+    assert cm.relerr(w_gd, ka[key + "w_gd"]) < RTOL
+
+
+def test_langevin_gradient_depth_and_golden_calls():
+    """langevin_gradient inputs/outputs recorded inside real reference runs (first two calls of chain 0)."""
+    for name in ("reg_sunspot_lg", "reg_mackey_h10", "cls_iris_lg", "cls_cancer_lg", "cls_ions_lg"):
+        fx, cfg, tr, te, _ = cm.case(name)
+        for k in range(fx["ref_lg_in"].shape[0]):
+            out = capi.op_langevin_gradient(cfg.task, cfg.topology, tr, fx["ref_lg_in"][k], cfg.learn_rate)
+            assert cm.relerr(out, fx["ref_lg_out"][k]) < RTOL, (name, k)
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    w = np.random.RandomState(1).randn(31)
+    two = capi.op_langevin_gradient(capi.TASK_REGRESSION, (4, 5, 1), tr, w, 0.1, depth=2)   # R:108 epochs
+    ref = oc.langevin_gradient(on.REGRESSION, (4, 5, 1), tr, oc.langevin_gradient(on.REGRESSION, (4, 5, 1), tr, w, 0.1), 0.1)
+    assert cm.relerr(two, ref) < RTOL
+    assert np.array_equal(capi.op_langevin_gradient(capi.TASK_REGRESSION, (4, 5, 1), tr, w, 0.1, depth=0), w.astype(np.float32).astype(np.float64))
+
+
+def test_ragged_and_tiny_inputs():
+    """Row counts that are not multiples of the TMA tile (128), the row block or 4 (y padding)."""
+    rs = np.random.RandomState(5)
+    for n in (1, 2, 3, 5, 127, 128, 129, 257, 1000):
+        data = rs.rand(n, 5)
+        w = rs.randn(385) * 0.5
+        fx = capi.op_evaluate_proposal(capi.TASK_REGRESSION, (4, 64, 1), data, w)
+        assert cm.relerr(fx, oc.evaluate(on.REGRESSION, (4, 64, 1), data, w)) < RTOL
+        lik, rm, _, _ = capi.op_likelihood(capi.TASK_REGRESSION, (4, 64, 1), data, w, 0.3, 1.7)
+        l2, r2, _ = oc.likelihood(on.REGRESSION, (4, 64, 1), data, w, 0.3, 1.7)
+        assert np.allclose([lik, rm], [l2, r2], rtol=RTOL)
+        w_gd = capi.op_langevin_gradient(capi.TASK_REGRESSION, (4, 64, 1), data, w, 0.05)
+        assert cm.relerr(w_gd, oc.langevin_gradient(on.REGRESSION, (4, 64, 1), data, w, 0.05)) < RTOL
+    for n in (1, 7, 130):
+        data = np.hstack([rs.randn(n, 16), rs.randint(0, 10, size=(n, 1)).astype(float)])
+        w = rs.randn(on.num_params((16, 30, 10))) * 0.3
+        fx, prob = capi.op_evaluate_proposal(capi.TASK_CLASSIFICATION, (16, 30, 10), data, w)
+        _, prob_ref = oc.evaluate(on.CLASSIFICATION, (16, 30, 10), data, w)
+        assert cm.relerr(prob, prob_ref) < RTOL
+        w_gd = capi.op_langevin_gradient(capi.TASK_CLASSIFICATION, (16, 30, 10), data, w, 0.01)
+        assert cm.relerr(w_gd, oc.langevin_gradient(on.CLASSIFICATION, (16, 30, 10), data, w, 0.01)) < RTOL
+
+
+def test_wide_hidden_topology_ops():
+    """[16,256,10] (BASELINE configs[4] shape), 300 rows."""
+    rs = np.random.RandomState(9)
+    topo = (16, 256, 10)
+    data = np.hstack([rs.randn(300, 16), rs.randint(0, 10, size=(300, 1)).astype(float)])
+    w = rs.randn(on.num_params(topo)) * 0.2
+    lik, rm, acc, _ = capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, data, w, 1.0, 3.0)
+    l2, r2, a2 = oc.likelihood(on.CLASSIFICATION, topo, data, w, 1.0, 3.0)
+    assert lik == pytest.approx(l2, rel=RTOL)
+    w_gd = capi.op_langevin_gradient(capi.TASK_CLASSIFICATION, topo, data, w, 0.01)
+    assert cm.relerr(w_gd, oc.langevin_gradient(on.CLASSIFICATION, topo, data, w, 0.01)) < RTOL
+
+
+def test_swap_sweep_matches_reference_rule():
+    rs = np.random.RandomState(3)
+    lh = [0.0, 10.0, 20.0, 30.0]
+    src, sw = capi.op_swap_sweep(lh, [0.99, 0.99, 0.99])                                 # R:674, R:741-748 bubble
+    assert src.tolist() == [1, 2, 3, 0] and sw.all()
+    for n in (2, 3, 10, 257, 1024):
+        lh = rs.randn(n) * 2
+        u = rs.randint(0, 1 << 24, size=n - 1).astype(np.float64) / (1 << 24)
+        a, b = on.swap_sweep(lh, u)
+        c, d = capi.op_swap_sweep(lh, u)
+        assert a == c.tolist() and b == d.tolist(), n
+    # the 709 clamp (R:674): a huge gap must not overflow into NaN / no-swap
+    src, sw = capi.op_swap_sweep([-1e6, 1e6], [0.999])
+    assert sw.all() and src.tolist() == [1, 0]
+    src, sw = capi.op_swap_sweep([1e6, -1e6], [0.0])
+    assert not sw.any()

@@ -1,0 +1,141 @@
+"""GPU parity of the whole hot path in replay mode: the reference's recorded draws are fed to the
+persistent chain kernel and its traces are compared with what the UNMODIFIED reference produced
+(tests/golden/*.npz) and with the float64 oracle.
+
+  teacher-forced: the device state is reset to the oracle's pre-step state before every step, so
+                  every step's proposed log-likelihood / prior / MH probability is checked
+                  independently (1e-4 relative);
+  free replay:    only the initial state is shared; accept / swap decisions must be identical
+                  up to a documented near-tie (u between the two MH probabilities).
+"""
+import numpy as np
+import pytest
+
+from oracle import ptfnn_c as oc
+from oracle import ptfnn_numpy as on
+from ptnn_b200.sampler import Sampler
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _sampler(cfg, temps, **kw):
+    kw.setdefault("debug_traces", True)
+    return Sampler.from_oracle_config(cfg, temps, **kw)
+
+
+@pytest.mark.parametrize("name", cm.CASES)
+def test_init_chains_matches_reference(name):
+    fx, cfg, tr, te, draws = cm.case(name)
+    with _sampler(cfg, fx["temperatures"]) as s:
+        s.set_data(tr, te)
+        s.init_chains(fx["w0"])
+        st = s.get_state()
+    assert cm.relerr(st["lik"], fx["ref_init_lik"]) < RTOL          # R:284 / C:283
+    assert cm.relerr(st["prior"], fx["ref_init_prior"]) < RTOL      # R:280 / C:281
+    assert np.array_equal(st["w"], fx["w0"].astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize("name", cm.CASES)
+def test_teacher_forced_replay(name):
+    fx, cfg, tr, te, draws = cm.case(name)
+    ref = oc.run_pt(cfg, tr, te, fx["temperatures"], fx["w0"], draws)
+    S = cfg.samples
+    with _sampler(cfg, fx["temperatures"]) as s:
+        s.set_data(tr, te)
+        s.init_chains(fx["w0"])
+        for i in range(S - 1):
+            s.set_state(w=ref.state_w[:, i], eta=ref.state_eta[:, i], lik=ref.state_lik[:, i],
+                        prior=ref.state_prior[:, i], tau=ref.state_tau[:, i])
+            assert s.replay(draws, n_steps=1) == 1
+        t = s.traces()
+    # the reference's own numbers (golden) and the oracle's
+    assert cm.relerr(t["lik_prop"][:, 1:], ref.lik_prop[:, 1:]) < RTOL
+    scale = 1.0 if cfg.task == on.REGRESSION else None
+    if scale:
+        assert cm.relerr(t["lik_prop"][:, 1:], fx["ref_lik_prop"][:, 1:]) < RTOL
+    assert cm.relerr(t["prior_prop"][:, 1:], fx["ref_prior_prop"][:, 1:]) < RTOL
+    # diff_prop is a difference of two O(P/2..1000) terms: compare on the scale of the terms
+    assert np.max(np.abs(t["diff_prop"] - ref.diff_prop)) < RTOL * max(1.0, np.max(np.abs(ref.diff_prop)), cfg.P)
+    # decisions: identical except where u falls between the two MH probabilities (near-tie)
+    diff = t["accepted"] != ref.accepted
+    lo = np.minimum(t["mh_prob"], ref.mh_prob) - 1e-7
+    hi = np.maximum(t["mh_prob"], ref.mh_prob) + 1e-7
+    u = np.concatenate([np.zeros((ref.accepted.shape[0], 1)), draws.u], axis=1)
+    assert np.all((u[diff] >= lo[diff]) & (u[diff] <= hi[diff]))
+    assert diff.mean() < 0.02
+    # rows written on acceptance carry the proposal (pos_w) and its rmse / accuracy
+    acc = t["accepted"] & ref.accepted
+    w_prop_ref = np.where(ref.accepted[..., None], ref.pos_w, 0.0)
+    assert cm.relerr(np.where(acc[..., None], t["pos_w"], 0.0), np.where(acc[..., None], w_prop_ref, 0.0)) < RTOL
+    assert cm.relerr(t["rmse_train"] * acc, fx["ref_rmse_train"] * acc) < (RTOL if cfg.task == on.REGRESSION else 0.2)
+    assert cm.relerr(t["rmse_test"] * acc, fx["ref_rmse_test"] * acc) < (RTOL if cfg.task == on.REGRESSION else 0.2)
+
+
+def _first_divergence(t, ref, sw_dev, cfg):
+    """First step index at which any accept decision or any swap decision differs (S-1 if none)."""
+    S = cfg.samples
+    bad = np.argwhere(t["accepted"] != ref.accepted)
+    i_acc = int(bad[:, 1].min()) - 1 if bad.size else S - 1          # row i+1 holds step i
+    n = min(len(sw_dev), len(ref.swapped))
+    i_sw = S - 1
+    rnd = 0
+    for i in range(S - 1):
+        if cfg.swap_due(i):
+            if rnd < n and not np.array_equal(sw_dev[rnd], ref.swapped[rnd]):
+                i_sw = i
+                break
+            rnd += 1
+    return min(i_acc, i_sw), i_acc, i_sw
+
+
+@pytest.mark.parametrize("name", cm.CASES)
+def test_free_replay_decisions_and_traces(name):
+    fx, cfg, tr, te, draws = cm.case(name)
+    ref = oc.run_pt(cfg, tr, te, fx["temperatures"], fx["w0"], draws)
+    S = cfg.samples
+    with _sampler(cfg, fx["temperatures"]) as s:
+        s.set_data(tr, te)
+        s.init_chains(fx["w0"])
+        assert s.replay(draws) == S - 1
+        t = s.traces()
+        ns, tot, sw = s.swap_stats()
+    assert tot == int(fx["ref_total_swap_proposals"])                 # rounds incl. the left-over one (Q9)
+    i_star, i_acc, i_sw = _first_divergence(t, ref, sw, cfg)
+    if i_star < S - 1:
+        # documented near-tie: at the first divergent step u lies between the two MH probabilities
+        if i_acc <= i_sw:
+            r = int(np.argwhere(t["accepted"][:, i_acc + 1] != ref.accepted[:, i_acc + 1])[0, 0])
+            u = draws.u[r, i_acc]
+            lo, hi = sorted([t["mh_prob"][r, i_acc + 1], ref.mh_prob[r, i_acc + 1]])
+            assert lo - 1e-7 <= u <= hi + 1e-7 and (hi - lo) <= 1e-3 * max(hi, 1e-30) + 1e-7, (name, i_acc, r, u, lo, hi)
+    rows = slice(0, i_star + 1)     # rows 0..i_star were written by steps < i_star
+    assert cm.relerr(t["lik_prop"][:, rows][:, 1:], ref.lik_prop[:, rows][:, 1:]) < RTOL
+    assert cm.relerr(t["pos_w"][:, rows], fx["ref_pos_w"][:, rows]) < RTOL          # the reference's own file
+    assert np.array_equal(t["accept_list"][:, rows], fx["ref_accept_list"][:, rows])
+    if cfg.task == on.REGRESSION:
+        assert cm.relerr(t["rmse_train"][:, rows], ref.rmse_train[:, rows]) < RTOL
+        assert cm.relerr(t["rmse_test"][:, rows], ref.rmse_test[:, rows]) < RTOL
+    if i_star == S - 1:
+        assert ns == int(fx["ref_num_swap"]) and np.array_equal(sw, fx["ref_swapped"])
+        assert np.array_equal(t["accepted"], ref.accepted)
+    # most of every golden case must replay before any near-tie
+    assert i_star >= (S - 1) // 2, (name, i_star)
+
+
+def test_trace_row_zero_and_carried_rows():
+    """pos_w row 0 = ones and stays ones until the first acceptance; likelihood row 0
+    = -100; rmse rows 0 until the first acceptance; accept_list[i+1] = count BEFORE step i."""
+    fx, cfg, tr, te, draws = cm.case("reg_lazer_rw")
+    with _sampler(cfg, fx["temperatures"]) as s:
+        s.set_data(tr, te)
+        s.init_chains(fx["w0"])
+        s.replay(draws)
+        t = s.traces()
+    assert np.all(t["pos_w"][:, 0] == 1.0) and np.all(t["lik_prop"][:, 0] == -100.0)
+    for r in range(t["accepted"].shape[0]):
+        first = int(np.argmax(t["accepted"][r])) if t["accepted"][r].any() else cfg.samples
+        assert np.all(t["pos_w"][r, :first] == 1.0) and np.all(t["rmse_train"][r, :first] == 0.0)
+        assert np.array_equal(t["accept_list"][r, 1:], np.cumsum(t["accepted"][r])[:-1])
+    assert np.all(t["acc_train"] == 0.0)                                              # R:403-404
