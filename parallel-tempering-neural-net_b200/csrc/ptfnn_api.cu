@@ -697,6 +697,8 @@ extern "C" int ptfnn_swap_apply(ptfnn_sampler *s, const int32_t *src, const void
     CU_TRY(s, cudaGetLastError());
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     s->swap_pending = false;
+    // the chain may have ended on a swap step: the coordinator's left-over round is still due (Q9)
+    if (s->step == s->cfg.samples - 1 && s->rounds_done < h_total_rounds(s)) { s->swap_pending = true; s->pending_final = true; }
     return PTFNN_OK;
 }
 
