@@ -195,10 +195,10 @@ def run_reference_arm(args, w):
 # ------------------------------------------------------------------------------------------
 def measure_peaks(device):
     lib = ctypes.CDLL(os.path.join(ROOT, "parallel-tempering-neural-net_b200", "csrc", "libptfnn_peaks.so"))
-    out = (ctypes.c_double * 3)()
+    out = (ctypes.c_double * 4)()
     if lib.ptfnn_measure_peaks(int(device), out) != 0:
         return None
-    return {"fp32_tflops": out[0], "mufu_gops": out[1], "smem_gbs": out[2]}
+    return {"fp32_tflops": out[0], "mufu_gops": out[1], "smem_gbs": out[2], "fp32_3reg_tflops": out[3]}
 
 
 def run_b200_arm(args, w, rank, world, local_rank):

@@ -40,13 +40,13 @@ static int fail(ptfnn_sampler *s, int code, const char *fmt, ...);
 #include "ptfnn_topologies.h"
 typedef PtfnnKernelSet KernelSet;
 
-#define X(NAME, TASK, I, H, O, NT) const PtfnnKernelSet *ptfnn_kernelset_##NAME();
+#define X(NAME, TASK, I, H, O, NT, MINB) const PtfnnKernelSet *ptfnn_kernelset_##NAME();
 PTFNN_TOPOLOGIES(X)
 #undef X
 
 static const std::vector<const KernelSet *> &kernel_sets() {
     static const std::vector<const KernelSet *> v = {
-#define X(NAME, TASK, I, H, O, NT) ptfnn_kernelset_##NAME(),
+#define X(NAME, TASK, I, H, O, NT, MINB) ptfnn_kernelset_##NAME(),
         PTFNN_TOPOLOGIES(X)
 #undef X
     };
@@ -114,7 +114,7 @@ struct ptfnn_sampler {
     DevBuf<GridBarrier> barrier;
     DevBuf<long long> swap_counters;
     DevBuf<float> d_lx, d_z, d_zeta, d_u, d_uswap;   // replay staging
-    DevBuf<int> d_src;
+    DevBuf<int> d_src, smsp_load;
     DevBuf<uint8_t> d_swapped;
     DevBuf<double> d_scratch;
 
@@ -126,7 +126,7 @@ struct ptfnn_sampler {
         acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
         init_count.release(); gd_valid.release(); accept_list.release(); dbg_acc.release(); swap_log.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
-        d_u.release(); d_uswap.release(); d_src.release(); d_swapped.release(); d_scratch.release();
+        d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); d_swapped.release(); d_scratch.release();
     }
 };
 
@@ -252,10 +252,11 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
     ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2);
-    ALLOC(d_src, (size_t)Rg); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
+    ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
+    cudaMemset(s->smsp_load.p, 0, s->smsp_load.n * sizeof(int));
     cudaMemset(s->swap_counters.p, 0, 2 * sizeof(long long));
     cudaMemset(s->swap_log.p, 0, s->swap_log.n);
     e = cudaGetLastError();
@@ -468,6 +469,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.pub_rows = s->pub_rows.p; p.pub_lhood = s->pub_lhood.p; p.barrier = s->barrier.p;
     p.swap_counters = s->swap_counters.p; p.swap_log = s->swap_log.p;
     p.max_rounds = (int)(s->swap_log.n / std::max(Rg - 1, 1));
+    p.smsp_load = s->smsp_load.p;
 
     if (d) {
         if (d->n < n) return fail(s, PTFNN_E_INVALID, "draws cover %d steps, need %d", d->n, n);

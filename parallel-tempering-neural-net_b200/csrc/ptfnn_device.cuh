@@ -85,7 +85,11 @@ __device__ __forceinline__ void philox_step_normals4(uint64_t seed, uint32_t ste
 // math
 // ------------------------------------------------------------------------------------------
 // Latency-critical sigmoid of the serial SGD recurrence: MUFU.EX2 + MUFU.RCP (R:43-44).
-__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// ex2.approx.ftz / rcp.approx.ftz directly: no denormal-range fix-up code on the dependent chain
+// (ftz only flushes results below 2^-126, where the sigmoid is 1 or 0 to fp32 precision anyway).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float z) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * z)); }
 // Sigmoid of the row-parallel likelihood pass: full-precision expf and IEEE division.
 __device__ __forceinline__ float sigmoid_precise(float z) { return 1.0f / (1.0f + expf(-z)); }
 
@@ -95,7 +99,7 @@ __device__ __forceinline__ float sigmoid_sel(float z) {
     else return sigmoid_fast(z);
 }
 
-__device__ __forceinline__ float warp_sum(float v, int levels) {
+__device__ __forceinline__ float warp_sum_shfl(float v, int levels) {
     // xor butterfly over the lowest 2^levels lanes (callers with H <= 16 need fewer levels)
     if (levels >= 5) v += __shfl_xor_sync(0xffffffffu, v, 16);
     if (levels >= 4) v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -104,6 +108,26 @@ __device__ __forceinline__ float warp_sum(float v, int levels) {
     if (levels >= 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
 }
+
+// All-lane sum on the critical path of the SGD recurrence.  Measured on B200 (tools/latency_probe.cu):
+// one SHFL.BFLY+FADD level costs ~36 cycles, so a 5-level butterfly is ~180 cycles per row, while
+// FMUL + F2I + REDUX.SUM.S32 + I2F + FMUL is ~75.  The sum is therefore taken in 2^-22 fixed point
+// with the integer REDUX unit (exact and order-independent once quantised; quantisation error
+// <= 32 * 2^-23 ~ 4e-6 worst case, ~4e-7 rms, i.e. at the level of fp32 summation error).  A second,
+// concurrent REDUX.MAX on the magnitudes guards the range: if any lane holds |v| >= 15.9 the
+// butterfly is used instead (warp-uniform branch; needs |weight| ~ 16, far outside the prior's bulk).
+__device__ __forceinline__ float warp_sum(float v, int levels) {
+    if (levels <= 1) return warp_sum_shfl(v, levels);
+    const unsigned int mag = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);
+    const int q = __float2int_rn(v * 4194304.0f);
+    const int s = __reduce_add_sync(0xffffffffu, q);
+    if (mag < 0x417e6666u)   // 15.9f
+        return (float)s * (1.0f / 4194304.0f);
+    return warp_sum_shfl(v, 5);
+}
+
+__device__ __forceinline__ unsigned int hw_smid() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned int hw_warpid() { unsigned int r; asm volatile("mov.u32 %0, %%warpid;" : "=r"(r)); return r; }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll

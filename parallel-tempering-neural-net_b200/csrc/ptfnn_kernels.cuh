@@ -24,7 +24,10 @@ struct DataView {
     int n;
 };
 
-constexpr int kTileRows = 128;  // rows per TMA tile when the training set is streamed instead of staged
+constexpr int kTileRows = 128;
+// Likelihood-pass sigmoids: MUFU ex2 + rcp (relative error ~4e-7, well inside the 1e-4 parity bar);
+// log / exp of the softmax epilogue stay full precision.
+constexpr bool kPreciseLik = false;  // rows per TMA tile when the training set is streamed instead of staged
 
 // ==========================================================================================
 // K2: serial SGD recurrence, one warp.  Lane l owns hidden units l, l+32, ... in registers.
@@ -69,27 +72,42 @@ struct SgdWarp {
         }
     }
 
-    // One row: ForwardPass (R:51-55) then BackwardPass (R:57-78 / C:72-82).  xrow is warp-uniform.
-    __device__ __forceinline__ void row(const float *xrow, float yv, float lr, int lane) {
-        float x[IP];
+    // Pre-activation of the hidden units for row x with the CURRENT weights: z = x.W1 - B1 (R:52).
+    __device__ __forceinline__ void preact(const float (&x)[IP], float (&z)[HPL]) const {
 #pragma unroll
-        for (int q = 0; q < IP / 4; ++q) {
-            const float4 v = reinterpret_cast<const float4 *>(xrow)[q];
-            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        for (int k = 0; k < HPL; ++k) {
+            float t = -b1[k];                                   // bias is SUBTRACTED (R:52)
+#pragma unroll
+            for (int i = 0; i < I; ++i) t = fmaf(x[i], w1[k][i], t);
+            z[k] = t;
         }
+    }
+
+    // One row: ForwardPass (R:51-55) then BackwardPass (R:57-78 / C:72-82).
+    //   z      in:  pre-activations of THIS row (all earlier updates included)
+    //          out: pre-activations of the NEXT row xn, obtained off the critical path as
+    //               xn.W1_old - B1_old (computed while the output-layer reduction is in flight)
+    //               + lr*hid_delta * (xn.x + 1)   (the rank-1 update W1 += lr*hd (x) x, B1 -= lr*hd)
+    //   so the dependent chain from hid_delta to the next row's sigmoid is one FFMA instead of
+    //   an update FFMA plus an I-long dot product.
+    __device__ __forceinline__ void row(const float (&x)[IP], float yv, const float (&xn)[IP], float (&z)[HPL],
+                                        float lr, int lane) {
         float hid[HPL];
         float p[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) p[o] = 0.0f;
 #pragma unroll
         for (int k = 0; k < HPL; ++k) {
-            float z = -b1[k];                                   // bias is SUBTRACTED (R:52)
-#pragma unroll
-            for (int i = 0; i < I; ++i) z = fmaf(x[i], w1[k][i], z);
-            hid[k] = (lane + 32 * k < H) ? sigmoid_fast(z) : 0.0f;
+            hid[k] = (lane + 32 * k < H) ? sigmoid_fast(z[k]) : 0.0f;
 #pragma unroll
             for (int o = 0; o < O; ++o) p[o] = fmaf(hid[k], w2[k][o], p[o]);
         }
+        // independent of the reduction below: stale pre-activation of the next row and xn.x + 1
+        float zn[HPL];
+        preact(xn, zn);
+        float c = 1.0f;
+#pragma unroll
+        for (int i = 0; i < I; ++i) c = fmaf(xn[i], x[i], c);
         float od[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
@@ -104,10 +122,10 @@ struct SgdWarp {
             float s = 0.0f;
 #pragma unroll
             for (int o = 0; o < O; ++o) s = fmaf(od[o], w2[k][o], s);             // pre-update W2 (R:59)
-            const float hd = s * (hid[k] * (1.0f - hid[k]));
+            const float lh = lr * (s * (hid[k] * (1.0f - hid[k])));
+            z[k] = fmaf(lh, c, zn[k]);
 #pragma unroll
             for (int o = 0; o < O; ++o) w2[k][o] = fmaf(lr * od[o], hid[k], w2[k][o]);   // R:67-69
-            const float lh = lr * hd;
 #pragma unroll
             for (int i = 0; i < I; ++i) w1[k][i] = fmaf(lh, x[i], w1[k][i]);      // R:74-76
             b1[k] -= lh;                                                          // R:77-78
@@ -117,14 +135,46 @@ struct SgdWarp {
     }
 };
 
+// shared-memory row fetch (the SGD warp always reads rows from shared memory: the staged copy or a TMA tile)
+template <int IP>
+__device__ __forceinline__ void lds_row(uint32_t xaddr, float (&x)[IP]) {
+#pragma unroll
+    for (int q = 0; q < IP / 4; ++q)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x[4 * q]), "=f"(x[4 * q + 1]), "=f"(x[4 * q + 2]), "=f"(x[4 * q + 3])
+                     : "r"(xaddr + 16u * q));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 // Streaming state of the SGD warp when the training set does not fit in shared memory:
 // two TMA tiles, one mbarrier each.
 struct SgdStream {
-    float *tile_x[2];
-    float *tile_y[2];
-    uint64_t *bar[2];
-    uint32_t parity[2];
+    float *tile_x0, *tile_x1, *tile_y0, *tile_y1;
+    uint64_t *bar0, *bar1;
+    uint32_t parity0, parity1;
 };
+
+// Rows [0, count) of a shared-memory tile whose look-ahead row (r+1) lies in the same tile.
+// (xc, yc) = the row about to be processed (already in registers), z = its pre-activations.
+template <int I, int H, int O, int TASK>
+__device__ __forceinline__ void sgd_rows(SgdWarp<I, H, O, TASK> &net, uint32_t xa, uint32_t ya, int count,
+                                         float (&xc)[IPad<I>::value], float &yc,
+                                         float (&z)[SgdWarp<I, H, O, TASK>::HPL], float lr, int lane) {
+    constexpr int IP = IPad<I>::value;
+    for (int r = 0; r < count; ++r) {
+        float xn[IP];
+        lds_row<IP>(xa + (uint32_t)(r + 1) * IP * 4u, xn);
+        const float yn = lds_f32(ya + (uint32_t)(r + 1) * 4u);
+        net.row(xc, yc, xn, z, lr, lane);
+#pragma unroll
+        for (int i = 0; i < IP; ++i) xc[i] = xn[i];
+        yc = yn;
+    }
+}
 
 // One epoch of online SGD over the training rows in order.  Called by warp 0 only.
 template <int I, int H, int O, int TASK>
@@ -134,32 +184,60 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
     const int lane = threadIdx.x & 31;
     SgdWarp<I, H, O, TASK> net;
     net.load(w_in, lane);
+    float xc[IP], yc, xz[IP];
+    float z[SgdWarp<I, H, O, TASK>::HPL];
+#pragma unroll
+    for (int i = 0; i < IP; ++i) xz[i] = 0.0f;
     if (staged) {
-        for (int r = 0; r < d.n; ++r) net.row(d.x + (size_t)r * IP, d.y[r], lr, lane);
+        const uint32_t xa = smem_u32(d.x), ya = smem_u32(d.y);
+        lds_row<IP>(xa, xc);
+        yc = lds_f32(ya);
+        net.preact(xc, z);
+        sgd_rows<I, H, O, TASK>(net, xa, ya, d.n - 1, xc, yc, z, lr, lane);
+        net.row(xc, yc, xz, z, lr, lane);                       // last row: nothing to look ahead to
     } else {
         const int ntiles = (d.n + kTileRows - 1) / kTileRows;
         auto issue = [&](int t) {
-            const int b = t & 1;
             const int rows = min(kTileRows, d.n - t * kTileRows);
             const uint32_t bx = (uint32_t)rows * IP * 4u;
             const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;   // y is allocated padded to 4 floats
             if (lane == 0) {
-                mbar_arrive_expect_tx(st.bar[b], bx + by);
-                tma_load_1d(st.tile_x[b], d.x + (size_t)t * kTileRows * IP, bx, st.bar[b]);
-                tma_load_1d(st.tile_y[b], d.y + (size_t)t * kTileRows, by, st.bar[b]);
+                uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
+                mbar_arrive_expect_tx(bar, bx + by);
+                tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
+                tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
             }
         };
+        auto wait = [&](int t) {
+            if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
+            else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
+        };
         issue(0);
+        wait(0);
+        lds_row<IP>(smem_u32(st.tile_x0), xc);
+        yc = lds_f32(smem_u32(st.tile_y0));
+        net.preact(xc, z);
         for (int t = 0; t < ntiles; ++t) {
-            const int b = t & 1;
-            __syncwarp();                      // every lane is done reading the buffer about to be refilled
-            if (t + 1 < ntiles) issue(t + 1);
-            mbar_wait(st.bar[b], st.parity[b]);
-            st.parity[b] ^= 1u;
+            // tile t is resident; tile t+1 streams into the other buffer (free: all lanes are past
+            // tile t-1 and past the look-ahead read of this tile's first row) while tile t is consumed
+            __syncwarp();
+            const bool more = t + 1 < ntiles;
+            if (more) issue(t + 1);
             const int rows = min(kTileRows, d.n - t * kTileRows);
-            const float *xs = st.tile_x[b];
-            const float *ys = st.tile_y[b];
-            for (int r = 0; r < rows; ++r) net.row(xs + r * IP, ys[r], lr, lane);
+            sgd_rows<I, H, O, TASK>(net, smem_u32((t & 1) ? st.tile_x1 : st.tile_x0),
+                                    smem_u32((t & 1) ? st.tile_y1 : st.tile_y0), rows - 1, xc, yc, z, lr, lane);
+            if (more) {                                          // the tile's last row looks ahead into tile t+1
+                wait(t + 1);
+                float xn[IP];
+                lds_row<IP>(smem_u32((t & 1) ? st.tile_x0 : st.tile_x1), xn);
+                const float yn = lds_f32(smem_u32((t & 1) ? st.tile_y0 : st.tile_y1));
+                net.row(xc, yc, xn, z, lr, lane);
+#pragma unroll
+                for (int i = 0; i < IP; ++i) xc[i] = xn[i];
+                yc = yn;
+            } else {
+                net.row(xc, yc, xz, z, lr, lane);
+            }
         }
     }
     net.store(w_out, lane);
@@ -229,7 +307,7 @@ __device__ __forceinline__ void lik_rows_impl(const float *__restrict__ w, const
 #pragma unroll
                     for (int o = 0; o < O; ++o) {
                         out[o] = sigmoid_sel<PRECISE>(acc[b][o]);
-                        se += PRECISE ? expf(out[o]) : __expf(out[o]);            // C:108-110
+                        se += expf(out[o]);            // C:108-110
                     }
 #pragma unroll
                     for (int o = 1; o < O; ++o) am = (out[o] > out[am]) ? o : am; // np.argmax: first max
@@ -237,7 +315,7 @@ __device__ __forceinline__ void lik_rows_impl(const float *__restrict__ w, const
                     float ol = out[0];
 #pragma unroll
                     for (int o = 1; o < O; ++o) ol = (o == lab) ? out[o] : ol;
-                    s0 += (double)(ol - (PRECISE ? logf(se) : __logf(se)));
+                    s0 += (double)(ol - logf(se));
                     const float e = (float)am - yv;
                     s1 += (double)(e * e);
                     correct += ((float)am == yv) ? 1 : 0;
@@ -308,6 +386,7 @@ struct ChainParams {
     long long *swap_counters;      // {num_swap, total_swap_proposals}  (R:680-688)
     uint8_t *swap_log;             // [rounds][Rg-1]
     int max_rounds;
+    int *smsp_load;                // [num_SMs][4] serial (SGD) warps currently placed on each SM sub-partition
 };
 
 __device__ __forceinline__ bool swap_due(int rule, int s, int i) {
@@ -349,8 +428,8 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
     return L;
 }
 
-template <int I, int H, int O, int TASK, int NT>
-__global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
+template <int I, int H, int O, int TASK, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int P = NetSizes<I, H, O>::P;
     constexpr int IP = NetSizes<I, H, O>::IP;
     constexpr int NW = NT / 32;
@@ -396,13 +475,35 @@ __global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
         train.x = sx_tr; train.y = sy_tr; test.x = sx_te; test.y = sy_te;
     } else {
         float *tiles = reinterpret_cast<float *>(smem_raw + L.off_tiles);
-        stream.tile_x[0] = tiles;
-        stream.tile_x[1] = tiles + kTileRows * IP;
-        stream.tile_y[0] = tiles + 2 * kTileRows * IP;
-        stream.tile_y[1] = tiles + 2 * kTileRows * IP + kTileRows;
-        stream.bar[0] = &s_bar[0]; stream.bar[1] = &s_bar[1];
+        stream.tile_x0 = tiles;
+        stream.tile_x1 = tiles + kTileRows * IP;
+        stream.tile_y0 = tiles + 2 * kTileRows * IP;
+        stream.tile_y1 = tiles + 2 * kTileRows * IP + kTileRows;
+        stream.bar0 = &s_bar[0]; stream.bar1 = &s_bar[1];
     }
-    stream.parity[0] = stream.parity[1] = 0u;
+    stream.parity0 = stream.parity1 = 0u;
+
+    // ---- which warp runs the serial recurrence.  Warps are bound to one of the SM's four
+    // sub-partitions (hardware warp slot % 4); co-resident CTAs would otherwise all put their
+    // serial warp on the same sub-partition and queue for its issue port.  Greedy balance through a
+    // per-SM counter table (released at kernel exit).
+    __shared__ unsigned int s_hw[NW];
+    if (lane == 0) s_hw[warp] = hw_warpid() & 3u;
+    __syncthreads();
+    const unsigned int smid = hw_smid();
+    if (tid == 0) {
+        int best = 0, best_load = 1 << 30;
+        for (int w = 0; w < NW; ++w) {
+            const int load = *(volatile int *)&p.smsp_load[smid * 4 + s_hw[w]];
+            if (load < best_load) { best_load = load; best = w; }
+        }
+        atomicAdd(&p.smsp_load[smid * 4 + s_hw[best]], 1);
+        s_flag[0] = best;
+    }
+    __syncthreads();
+    const int sgd_warp = s_flag[0];
+    const bool is_sgd_warp = warp == sgd_warp;
+    const int lik_tid = (warp < sgd_warp ? tid : tid - 32);     // index inside the team of the other warps
 
     const int nblocks = gridDim.x;
     int step = p.step_begin;
@@ -441,7 +542,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
                     double s[2] = {0.0, 0.0};
                     double dummy = 0.0;
                     int c0 = 0;
-                    lik_rows<I, H, O, TASK, true, false>(s_w, train, tid, NT, s[0], dummy, c0);
+                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_w, train, tid, NT, s[0], dummy, c0);
                     block_sum<2, NT>(s, s_red);
                     if constexpr (TASK == kTaskReg)
                         lik = (-0.5 * train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / adapt;
@@ -463,7 +564,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
                 const bool lg = p.use_lg && ((double)lx < p.l_prob);              // R:329
                 // ---- Langevin branch, first SGD epoch: w_gd = langevin_gradient(w)   (R:330)
                 if (lg && !gd_valid) {
-                    if (warp == 0) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
+                    if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
                     __syncthreads();
                     gd_valid = p.memo;
                 }
@@ -493,19 +594,19 @@ __global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
                 for (int k = 0; k < 8; ++k) s[k] = 0.0;
                 int c_tr = 0, c_te = 0;
                 if (lg && NW > 1) {
-                    if (warp == 0) {
+                    if (is_sgd_warp) {
                         sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                     } else {
-                        lik_rows<I, H, O, TASK, true, false>(s_prop, train, tid - 32, NT - 32, s[0], s[1], c_tr);
-                        lik_rows<I, H, O, TASK, true, false>(s_prop, test, tid - 32, NT - 32, s[2], s[3], c_te);
+                        lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, train, lik_tid, NT - 32, s[0], s[1], c_tr);
+                        lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, test, lik_tid, NT - 32, s[2], s[3], c_te);
                     }
                 } else {
                     if (lg) {
-                        if (warp == 0) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
+                        if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
-                    lik_rows<I, H, O, TASK, true, false>(s_prop, train, tid, NT, s[0], s[1], c_tr);
-                    lik_rows<I, H, O, TASK, true, false>(s_prop, test, tid, NT, s[2], s[3], c_te);
+                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, train, tid, NT, s[0], s[1], c_tr);
+                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, test, tid, NT, s[2], s[3], c_te);
                 }
                 __syncthreads();
                 // ---- reductions: likelihood sums, |w_prop|^2 (prior), Langevin asymmetry norms
@@ -677,7 +778,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(const ChainParams p) {
             }
         }
     }
-    (void)s_flag;
+    if (tid == 0) atomicSub(&p.smsp_load[smid * 4 + s_hw[sgd_warp]], 1);
 }
 
 // ==========================================================================================
@@ -786,10 +887,10 @@ __global__ void __launch_bounds__(32) op_sgd_kernel(const float *w_in, float *w_
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     SgdStream st;
-    st.tile_x[0] = tiles; st.tile_x[1] = tiles + kTileRows * IP;
-    st.tile_y[0] = tiles + 2 * kTileRows * IP; st.tile_y[1] = tiles + 2 * kTileRows * IP + kTileRows;
-    st.bar[0] = &s_bar[0]; st.bar[1] = &s_bar[1];
-    st.parity[0] = st.parity[1] = 0u;
+    st.tile_x0 = tiles; st.tile_x1 = tiles + kTileRows * IP;
+    st.tile_y0 = tiles + 2 * kTileRows * IP; st.tile_y1 = tiles + 2 * kTileRows * IP + kTileRows;
+    st.bar0 = &s_bar[0]; st.bar1 = &s_bar[1];
+    st.parity0 = st.parity1 = 0u;
     for (int e = 0; e < depth; ++e) {                       // R:108 `depth` epochs (sgd_depth is always 1, R:170)
         sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
         __syncwarp();

@@ -20,6 +20,9 @@ __global__ void fma_kernel(float *out, int iters, float a, float b) {
     if (s == 12345.678f) out[0] = s;
 }
 
+// ex2 -> +1 -> rcp chains (the sigmoid core).  The FADD between the two MUFU ops keeps ptxas from
+// folding rcp(ex2(x)) into ex2(-x), which an earlier version of this probe suffered from (it read
+// 2x the real rate); tools/contention_probe.cu confirms 16 MUFU lanes/clk/SM on B200.
 template <int ILP>
 __global__ void mufu_kernel(float *out, int iters) {
     float v[ILP];
@@ -30,8 +33,25 @@ __global__ void mufu_kernel(float *out, int iters) {
         for (int k = 0; k < ILP; ++k) {
             float e;
             asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k]));
+            e += 1.0f;
             asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(e));
         }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += v[k];
+    if (s == 12345.678f) out[0] = s;
+}
+
+// three-register FFMA (no immediate / constant operand), the form real kernels issue
+template <int ILP>
+__global__ void fma3_kernel(float *out, int iters, const float *ab) {
+    float v[ILP], a[ILP], b[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) { v[k] = threadIdx.x * 1e-3f + k; a[k] = ab[k] + threadIdx.x * 1e-9f; b[k] = ab[ILP + k]; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) v[k] = fmaf(v[k], a[k], b[k]);
     }
     float s = 0.f;
 #pragma unroll
@@ -79,8 +99,11 @@ static const int kIters = 4096, kThreads = 256, kBlocksPerSm = 8;
 static void launch_fma(int sms, float *d) { fma_kernel<8><<<sms * kBlocksPerSm, kThreads>>>(d, kIters, 1.0001f, 0.5f); }
 static void launch_mufu(int sms, float *d) { mufu_kernel<8><<<sms * kBlocksPerSm, kThreads>>>(d, kIters / 4); }
 static void launch_smem(int sms, float *d) { smem_kernel<<<sms * kBlocksPerSm, kThreads>>>(d, kIters / 4); }
+static float *g_ab = nullptr;
+static void launch_fma3(int sms, float *d) { fma3_kernel<8><<<sms * kBlocksPerSm, kThreads>>>(d, kIters, g_ab); }
 
-// out[0] = FP32 FMA TFLOP/s, out[1] = MUFU Gop/s (ex2+rcp counted as 2 ops), out[2] = shared-memory GB/s
+// out[0] = FP32 FMA TFLOP/s (constant-operand form), out[1] = MUFU Gop/s (ex2+rcp counted as 2 ops),
+// out[2] = shared-memory GB/s, out[3] = FP32 FMA TFLOP/s (three-register form)
 extern "C" int ptfnn_measure_peaks(int device, double *out) {
     if (cudaSetDevice(device) != cudaSuccess) return -2;
     cudaDeviceProp p;
@@ -95,6 +118,13 @@ extern "C" int ptfnn_measure_peaks(int device, double *out) {
     out[1] = threads * (kIters / 4) * 8 * 2.0 / (ms * 1e-3) / 1e9;
     ms = time_ms(launch_smem, sms, d);
     out[2] = threads * (kIters / 4) * 8 * 16.0 / (ms * 1e-3) / 1e9;
+    float hab[16];
+    for (int k = 0; k < 16; ++k) hab[k] = k < 8 ? 1.0001f : 0.5f;
+    cudaMalloc(&g_ab, sizeof hab);
+    cudaMemcpy(g_ab, hab, sizeof hab, cudaMemcpyHostToDevice);
+    ms = time_ms(launch_fma3, sms, d);
+    out[3] = threads * kIters * 8 * 2.0 / (ms * 1e-3) / 1e12;
+    cudaFree(g_ab);
     cudaFree(d);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

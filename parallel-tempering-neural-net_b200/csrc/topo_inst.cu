@@ -1,5 +1,5 @@
 // One translation unit per topology: instantiates the templated kernels of ptfnn_kernels.cuh for
-// -DPTFNN_T_NAME / _TASK / _I / _H / _O / _NT and exports their addresses.
+// -DPTFNN_T_NAME / _TASK / _I / _H / _O / _NT / _MINB and exports their addresses.
 #include "ptfnn_kernels.cuh"
 #include "ptfnn_registry.h"
 
@@ -13,7 +13,7 @@ using namespace ptfnn;
 const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
     static const PtfnnKernelSet ks = {
         PTFNN_STR(PTFNN_T_NAME), PTFNN_T_TASK, PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_NT,
-        (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
+        (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT, PTFNN_T_MINB>,
         (const void *)init_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_forward_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK>,

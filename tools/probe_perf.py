@@ -1,0 +1,66 @@
+"""Measurement helper (GPU box): per-row latency of the serial SGD recurrence and per-step cost of
+Langevin vs random-walk steps of the chain kernel.  Not part of the product or the tests."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ptnn_b200 import capi, datasets
+from ptnn_b200.sampler import Sampler, geometric_ladder
+from oracle import ptfnn_numpy as on
+
+
+def sgd_row_latency(task, topo, data, lr=0.01, d0=1, d1=9):
+    w = np.random.RandomState(0).randn(on.num_params(topo)) * 0.3
+    capi.op_langevin_gradient(task, topo, data, w, lr, depth=d0)
+    ts = []
+    for d in (d0, d1):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        capi.op_langevin_gradient(task, topo, data, w, lr, depth=d)
+        torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
+    per_row = (ts[1] - ts[0]) / ((d1 - d0) * data.shape[0])
+    return per_row * 1e9
+
+
+def chain_step_cost(task, topo, train, test, R, si, lr, memo, n=8):
+    temps = geometric_ladder(R, 2) if R > 1 else np.ones(1)
+    out = {}
+    for label, lxv in (("LG", 0.0), ("RW", 0.999)):
+        S = n * 3 + 2
+        s = Sampler(task, topo, temps, S, 10 ** 6, learn_rate=lr, memoize_gradient=memo, stream=torch.cuda.current_stream())
+        s.set_data(train, test)
+        s.init_chains(np.random.RandomState(1).randn(R, s.P))
+        lx, z, ze, u = s.generate_draws(0, S - 1)
+        lx[:] = lxv
+        d = on.Draws(lx=lx, z=z, z_eta=ze, u=u, u_swap=None)
+        s.replay(d, n_steps=n)                      # warm-up
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(); s.replay(d, n_steps=n); b.record(); torch.cuda.synchronize()
+        # replay() uploads draws inside the bracket; subtract by timing a second call of the same size
+        out[label] = a.elapsed_time(b) / n
+        s.close()
+    return out
+
+
+if __name__ == "__main__":
+    print(capi.build_info())
+    tr, te = datasets.synthetic_timeseries()
+    d = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "datasets.npz"))
+    sun_tr, sun_te = d["reg_Sunspot_train"], d["reg_Sunspot_test"]
+    clk = 1.965
+    for name, task, topo, data in (("4-5-1 sunspot-rows x100", 0, (4, 5, 1), np.tile(sun_tr, (100, 1))),
+                                   ("4-10-1", 0, (4, 10, 1), np.tile(sun_tr, (100, 1))),
+                                   ("4-64-1 synth", 0, (4, 64, 1), tr)):
+        ns = sgd_row_latency(task, topo, data)
+        print("SGD row latency %-28s %7.1f ns/row = %6.0f cycles @%.3f GHz" % (name, ns, ns * clk, clk))
+    ir = np.hstack([np.random.RandomState(2).randn(20000, 16), np.random.RandomState(3).randint(0, 10, (20000, 1)).astype(float)])
+    for name, topo in (("16-30-10", (16, 30, 10)), ("16-256-10", (16, 256, 10))):
+        ns = sgd_row_latency(1, topo, ir, d1=3)
+        print("SGD row latency %-28s %7.1f ns/row = %6.0f cycles" % (name, ns, ns * clk))
+    for memo in (0, 1):
+        c = chain_step_cost(0, (4, 64, 1), tr, te, 1024, 10, 0.01, memo, n=6)
+        print("synth_ts R=1024 memo=%d: LG step %.3f ms, RW step %.3f ms" % (memo, c["LG"], c["RW"]))
+        c = chain_step_cost(0, (4, 5, 1), sun_tr, sun_te, 10, 50, 0.1, memo, n=50)
+        print("sunspot  R=10   memo=%d: LG step %.4f ms, RW step %.4f ms" % (memo, c["LG"], c["RW"]))
+    c = chain_step_cost(0, (4, 64, 1), tr, te, 128, 10, 0.01, 0, n=6)
+    print("synth_ts R=128 memo=0: LG step %.3f ms, RW step %.3f ms" % (c["LG"], c["RW"]))
