@@ -177,6 +177,9 @@ int ptfnn_swap_apply(ptfnn_sampler *s, const int32_t *src /* host [n_replicas_gl
 
 /* ---- single operations (stateless; each replaces one reference method for drop-in use and for
  * per-function parity tests).  data: row-major [rows, n_cols] float64 host array. ---- */
+/* Network.ForwardPass on one input row, any topology (R:51-55 / C:49-55): hidout [H], out [O] */
+int ptfnn_op_forward_pass(int32_t device, int32_t n_in, int32_t n_hidden, int32_t n_out, const double *x,
+                          const double *w, double *hidout, double *out);
 /* Network.evaluate_proposal (R:120-134 -> fx; C:134-153 -> fx = argmax, prob = softmax(out)) */
 int ptfnn_op_evaluate_proposal(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
                                const double *data, int32_t rows, int32_t n_cols, const double *w,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
     "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
-    "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
+    "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
     "ptfnn_op_swap_sweep",
 ]
 
@@ -113,6 +113,15 @@ def ptr(a):
 
 
 # ---- single operations (stateless) -------------------------------------------------------------
+def op_forward_pass(topology, x, w, device=0):
+    """Network.ForwardPass on one row -> (hidout[H], out[O])."""
+    I, H, O = topology
+    x, w = f64(x).reshape(-1), f64(w)
+    hid, out = np.zeros(H), np.zeros(O)
+    check(load().ptfnn_op_forward_pass(device, I, H, O, ptr(x), ptr(w), ptr(hid), ptr(out)))
+    return hid, out
+
+
 def op_evaluate_proposal(task, topology, data, w, device=0):
     I, H, O = topology
     data, w = f64(data), f64(w)

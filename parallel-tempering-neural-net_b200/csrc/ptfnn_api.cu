@@ -848,6 +848,29 @@ extern "C" int ptfnn_op_prior(int32_t device, int32_t task, int32_t I, int32_t H
     return PTFNN_OK;
 }
 
+extern "C" int ptfnn_op_forward_pass(int32_t device, int32_t I, int32_t H, int32_t O, const double *x, const double *w,
+                                     double *hidout, double *out) {
+    if (!x || !w || !hidout || !out || I < 1 || H < 1 || O < 1) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    int rc = require_device(nullptr, device);
+    if (rc) return rc;
+    const int P = I * H + H * O + H + O;
+    std::vector<float> buf((size_t)I + P);
+    for (int i = 0; i < I; ++i) buf[i] = (float)x[i];
+    for (int j = 0; j < P; ++j) buf[I + j] = (float)w[j];
+    DevBuf<float> d;
+    CU_TRY(nullptr, d.ensure((size_t)I + P + H + O));
+    CU_TRY(nullptr, cudaMemcpy(d.p, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+    if ((size_t)H * 4 > 48 * 1024) CU_TRY(nullptr, cudaFuncSetAttribute((const void *)op_forward_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4));
+    op_forward_row_kernel<<<1, 128, (size_t)H * 4>>>(I, H, O, d.p, d.p + I, d.p + I + P, d.p + I + P + H);
+    CU_TRY(nullptr, cudaGetLastError());
+    std::vector<float> r((size_t)H + O);
+    CU_TRY(nullptr, cudaMemcpy(r.data(), d.p + I + P, r.size() * 4, cudaMemcpyDeviceToHost));
+    for (int h = 0; h < H; ++h) hidout[h] = r[h];
+    for (int o = 0; o < O; ++o) out[o] = r[H + o];
+    d.release();
+    return PTFNN_OK;
+}
+
 extern "C" int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t *src, uint8_t *swapped) {
     if (n < 1 || !lhood || !src || (n > 1 && !u_row)) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
     int rc = require_device(nullptr, device);

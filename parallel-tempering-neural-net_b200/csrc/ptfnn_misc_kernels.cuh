@@ -58,6 +58,24 @@ __global__ void draws_kernel(uint64_t seed, int crn, int replica_offset, int R, 
     }
 }
 
+// Network.ForwardPass on ONE row with runtime dimensions (R:51-55): hid = sigmoid(x.W1 - B1),
+// out = sigmoid(hid.W2 - B2).  One block; hidden units strided over threads.
+__global__ void op_forward_row_kernel(int I, int H, int O, const float *x, const float *w, float *hid, float *out) {
+    extern __shared__ float s_hid[];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float z = -w[I * H + H * O + h];
+        for (int i = 0; i < I; ++i) z = fmaf(x[i], w[i * H + h], z);
+        s_hid[h] = sigmoid_precise(z);
+        hid[h] = s_hid[h];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        float z = -w[I * H + H * O + H + o];
+        for (int h = 0; h < H; ++h) z = fmaf(s_hid[h], w[I * H + h * O + o], z);
+        out[o] = sigmoid_precise(z);
+    }
+}
+
 // multi-GPU: install the rows selected by the sweep (R:435-437)
 __global__ void swap_apply_kernel(int R, int P, int replica_offset, const int *src, const float *rows_local,
                                   const float *rows_in, float *w, double *eta, int *gd_valid) {

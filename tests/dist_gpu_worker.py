@@ -1,0 +1,78 @@
+"""Worker for tests/test_gpu_distributed.py (torch.distributed.run, NCCL, one rank per GPU):
+the ladder split over ranks must give traces bit-identical to the single-GPU run of the same
+replay (tier 4)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ptfnn_numpy as on                      # noqa: E402
+from ptnn_b200.distributed import make_gpu_ladder, partition    # noqa: E402
+from ptnn_b200.sampler import Sampler, geometric_ladder    # noqa: E402
+from tests import common as cm                            # noqa: E402
+
+
+def main():
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mode = os.environ.get("PT_TEST_MODE", "replay")
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    Rg, S, si = 8 * world, 62, 5
+    cfg = on.PTConfig(task=on.REGRESSION, topology=(4, 5, 1), samples=S, swap_interval=si,
+                      use_langevin_gradients=True, l_prob=0.5, learn_rate=0.1)
+    temps = geometric_ladder(Rg, 2)
+    w0 = np.random.RandomState(11).randn(Rg, cfg.P)
+    draws = on.random_draws(cfg, Rg, seed=5, common_random_numbers=False)
+    draws.u_swap[:] = draws.u_swap * 0.3                  # frequent swaps: rows really cross rank boundaries
+    lo, n = partition(Rg, world, rank)
+    kw = dict(use_langevin_gradients=True, l_prob=0.5, learn_rate=0.1, seed=77, common_random_numbers=False)
+    ladder, smp = make_gpu_ladder(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, **kw)
+    smp.set_data(tr, te)
+    smp.init_chains(w0[lo:lo + n])
+    if mode == "replay":
+        local = on.Draws(lx=draws.lx[lo:lo + n], z=draws.z[lo:lo + n], z_eta=draws.z_eta[lo:lo + n],
+                         u=draws.u[lo:lo + n], u_swap=None)
+        ladder.run(None, local, draws.u_swap)
+    else:
+        ladder.run(None)
+    t = smp.traces()
+    ns, tot, sw = smp.swap_stats()
+    st = smp.get_state()
+    pack = np.concatenate([t["pos_w"].reshape(n, -1), t["lik_prop"], t["accept_list"], st["w"], st["eta"][:, None]], axis=1)
+    mine = torch.from_numpy(pack).cuda()
+    allp = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allp, mine)
+    moved = torch.tensor([ladder.rows_moved], dtype=torch.int64, device="cuda")
+    dist.all_reduce(moved)
+    ok = True
+    if rank == 0:
+        with Sampler(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, **kw) as one:
+            one.set_data(tr, te)
+            one.init_chains(w0)
+            if mode == "replay":
+                one.replay(draws)
+            else:
+                one.run()
+            t1 = one.traces()
+            ns1, tot1, sw1 = one.swap_stats()
+            st1 = one.get_state()
+        ref = np.concatenate([t1["pos_w"].reshape(Rg, -1), t1["lik_prop"], t1["accept_list"], st1["w"], st1["eta"][:, None]], axis=1)
+        got = torch.cat(allp).cpu().numpy()
+        ok &= np.array_equal(got, ref)
+        ok &= (ns, tot) == (ns1, tot1) and np.array_equal(sw, sw1)
+        ok &= int(moved.item()) > 0
+        print("DIST_GPU_RESULT mode=%s ok=%s world=%d swaps=%d/%d rows_moved=%d" % (mode, ok, world, ns, tot, int(moved.item())))
+    smp.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
