@@ -114,7 +114,7 @@ struct ptfnn_sampler {
     DevBuf<GridBarrier> barrier;
     DevBuf<long long> swap_counters;
     DevBuf<float> d_lx, d_z, d_zeta, d_u, d_uswap;   // replay staging
-    DevBuf<int> d_src, smsp_load;
+    DevBuf<int> d_src, smsp_load, swap_src;
     DevBuf<uint8_t> d_swapped;
     DevBuf<double> d_scratch;
 
@@ -126,7 +126,7 @@ struct ptfnn_sampler {
         acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
         init_count.release(); gd_valid.release(); accept_list.release(); dbg_acc.release(); swap_log.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
-        d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); d_swapped.release(); d_scratch.release();
+        d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release();
     }
 };
 
@@ -252,7 +252,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
     ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2);
-    ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
+    ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(swap_src, R); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
@@ -470,6 +470,8 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.swap_counters = s->swap_counters.p; p.swap_log = s->swap_log.p;
     p.max_rounds = (int)(s->swap_log.n / std::max(Rg - 1, 1));
     p.smsp_load = s->smsp_load.p;
+    p.swap_src = s->swap_src.p;
+    p.P = P;
 
     if (d) {
         if (d->n < n) return fail(s, PTFNN_E_INVALID, "draws cover %d steps, need %d", d->n, n);
@@ -495,8 +497,8 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     const size_t stage_bytes = ((size_t)s->n_train * s->IP + ((s->n_train + 3) & ~3) + (size_t)s->n_test * s->IP + ((s->n_test + 3) & ~3)) * 4;
     p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
     const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
-    const ChainSmem L = chain_smem_layout(P, s->IP, NT, Rg, p.staged != 0, s->n_train, s->n_test);
-    if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB): ladder of %d too long for the in-kernel sweep", L.total, Rg);
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test);
+    if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
     CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int per_sm = 0;
     CU_TRY(s, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->ks->chain, NT, L.total));

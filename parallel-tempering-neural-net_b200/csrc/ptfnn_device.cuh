@@ -250,6 +250,22 @@ __device__ __forceinline__ int swap_sweep_serial(int n, double *lh, int *src, ui
     }
     return ns;
 }
+
+// Streaming form of the same sweep with O(1) state: when pair k is decided, slot k's final content
+// is known (either the original vector of slot k+1, or the vector that has been bubbling up), so
+// nothing but the bubbling vector's (lhood, origin) needs to be carried.  `lh_chunk(k)` returns the
+// ORIGINAL lhood of slot k; emit(slot, origin) reports final contents, decided(k, swapped) every pair.
+template <class LFn, class UFn, class Emit, class Decided>
+__device__ __forceinline__ void swap_sweep_stream(int k_begin, int k_end, int n, double &cur_l, int &cur_src, int &ns,
+                                                  LFn lh_of, UFn u_of, Emit emit, Decided decided) {
+    for (int k = k_begin; k < k_end && k + 1 < n; ++k) {
+        const double nxt = lh_of(k + 1);
+        const bool s = (double)u_of(k) < swap_probability(cur_l, nxt);
+        if (s) { emit(k, k + 1); ++ns; }
+        else { emit(k, cur_src); cur_l = nxt; cur_src = k + 1; }
+        decided(k, s);
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace ptfnn

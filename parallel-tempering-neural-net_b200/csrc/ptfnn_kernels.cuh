@@ -25,6 +25,7 @@ struct DataView {
 };
 
 constexpr int kTileRows = 128;
+constexpr int kSweepChunk = 128; // lhood fields staged per chunk by the in-kernel swap sweep
 // Likelihood-pass sigmoids: MUFU ex2 + rcp (relative error ~4e-7, well inside the 1e-4 parity bar);
 // log / exp of the softmax epilogue stay full precision.
 constexpr bool kPreciseLik = false;  // rows per TMA tile when the training set is streamed instead of staged
@@ -386,6 +387,8 @@ struct ChainParams {
     long long *swap_counters;      // {num_swap, total_swap_proposals}  (R:680-688)
     uint8_t *swap_log;             // [rounds][Rg-1]
     int max_rounds;
+    int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
+    int P;
     int *smsp_load;                // [num_SMs][4] serial (SGD) warps currently placed on each SM sub-partition
 };
 
@@ -406,8 +409,7 @@ struct NetSizes {
 // dynamic shared memory layout (floats unless noted); host computes the same with chain_smem_bytes()
 struct ChainSmem {
     int P4;          // P rounded up to 4
-    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep_l, off_sweep_s,
-        off_stage, total;
+    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep, off_stage, total;
 };
 __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
                                                        int n_test) {
@@ -420,12 +422,74 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
     L.off_red = take((size_t)8 * (nt / 32) * 8);
     L.off_bar = take(8 * 4);
     L.off_tiles = take(staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4));
-    L.off_sweep_l = take((size_t)Rg * 8);
-    L.off_sweep_s = take((size_t)Rg * 4);
+    L.off_sweep = take(Rg > 1 ? (size_t)kSweepChunk * 8 : 0);   // one chunk of lhood fields for the streaming sweep
     auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
     L.off_stage = take(staged ? ((size_t)n_train * IP + pad4(n_train) + (size_t)n_test * IP + pad4(n_test)) * 4 : 0);
     L.total = o;
     return L;
+}
+
+// K4: the coordinator's swap round (R:741-752) inside the chain kernel, after the grid barrier.
+// Every CTA runs the same sequential sweep (thread 0; lhood fields staged chunk-wise), notes the
+// origin of the vectors that end in ITS slots, then pulls (w, eta) of those from the published rows
+// (R:435-437: only w and eta are taken back, likelihood / prior stay stale -- SURVEY Q7).
+template <int NT>
+__device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int parity, bool apply, double *s_chunk,
+                                            int nblocks) {
+    const int tid = threadIdx.x;
+    const int P = p.P;
+    const double *L = p.pub_lhood + (size_t)parity * p.Rg;
+    const bool log_it = blockIdx.x == 0 && round < p.max_rounds;
+    uint8_t *lg_out = log_it ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
+    const float *ur = p.replay ? p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1) : nullptr;
+    double cur_l = 0.0;
+    int cur_src = 0, ns = 0;
+    // highest slot this CTA owns: no need to scan past it (block 0 scans everything for the log)
+    int last_needed = p.Rg - 1;
+    if (blockIdx.x != 0 && apply) {
+        int r_hi = blockIdx.x;
+        while (r_hi + nblocks < p.R) r_hi += nblocks;
+        last_needed = p.replica_offset + r_hi;
+    }
+    auto mine = [&](int slot) {
+        const int r = slot - p.replica_offset;
+        return apply && r >= 0 && r < p.R && (r % nblocks) == (int)blockIdx.x;
+    };
+    for (int base = 0; base <= last_needed; base += kSweepChunk - 1) {
+        // chunk holds original lhood of slots [base, base + kSweepChunk)
+        __syncthreads();
+        for (int k = tid; k < kSweepChunk && base + k < p.Rg; k += NT) s_chunk[k] = __ldcg(&L[base + k]);
+        __syncthreads();
+        if (tid == 0) {
+            if (base == 0) { cur_l = s_chunk[0]; cur_src = 0; }
+            const int k_end = min(base + kSweepChunk - 1, last_needed + 1);
+            swap_sweep_stream(
+                base, k_end, p.Rg, cur_l, cur_src, ns, [&](int k) { return s_chunk[k - base]; },
+                [&](int k) {
+                    if (ur) return ur[k];
+                    uint32_t c[4];
+                    philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
+                    return u01_open_right(c[0]);
+                },
+                [&](int slot, int origin) { if (mine(slot)) p.swap_src[slot - p.replica_offset] = origin; },
+                [&](int k, bool sw) { if (lg_out) lg_out[k] = (uint8_t)sw; });
+        }
+    }
+    if (tid == 0) {
+        if (last_needed == p.Rg - 1 && mine(p.Rg - 1)) p.swap_src[p.Rg - 1 - p.replica_offset] = cur_src;
+        if (blockIdx.x == 0) { p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1; }
+    }
+    __syncthreads();
+    if (!apply) return;
+    for (int r = blockIdx.x; r < p.R; r += nblocks) {
+        const int src = p.swap_src[r] - p.replica_offset;
+        if (src != r) {
+            const float *row = p.pub_rows + ((size_t)parity * p.R + src) * (P + 1);
+            for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
+            if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
+        }
+    }
+    __syncthreads();
 }
 
 template <int I, int H, int O, int TASK, int NT, int MINB>
@@ -434,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int IP = NetSizes<I, H, O>::IP;
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ChainSmem L = chain_smem_layout(P, IP, NT, p.Rg, p.staged != 0, p.train.n, p.test.n);
+    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n);
     float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
     float *s_prop = reinterpret_cast<float *>(smem_raw + L.off_prop);
     float *s_gd = reinterpret_cast<float *>(smem_raw + L.off_gd);
@@ -442,8 +506,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     float *s_last = reinterpret_cast<float *>(smem_raw + L.off_last);
     double *s_red = reinterpret_cast<double *>(smem_raw + L.off_red);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + L.off_bar);
-    double *s_sweep_l = reinterpret_cast<double *>(smem_raw + L.off_sweep_l);
-    int *s_sweep_src = reinterpret_cast<int *>(smem_raw + L.off_sweep_s);
+    double *s_sweep = reinterpret_cast<double *>(smem_raw + L.off_sweep);
     __shared__ int s_flag[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -713,37 +776,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             if (p.external_swap) break;   // multi-GPU: the host completes the round (ptfnn_swap_*)
             // ---------------- K4: swap round ----------------
             grid_barrier(p.barrier, nblocks);
-            for (int k = tid; k < p.Rg; k += NT) {
-                s_sweep_l[k] = __ldcg(&p.pub_lhood[(size_t)parity * p.Rg + k]);
-                s_sweep_src[k] = k;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const bool log_it = blockIdx.x == 0 && round < p.max_rounds;
-                uint8_t *lg_out = log_it ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
-                int ns;
-                if (p.replay) {
-                    const float *ur = p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1);
-                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) { return ur[k]; });
-                } else {
-                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) {
-                        uint32_t c[4];
-                        philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
-                        return u01_open_right(c[0]);
-                    });
-                }
-                if (blockIdx.x == 0) { p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1; }
-            }
-            __syncthreads();
-            // take back ONLY w and eta (R:435-437); likelihood / prior stay stale
-            for (int r = blockIdx.x; r < p.R; r += nblocks) {
-                const int src = s_sweep_src[p.replica_offset + r] - p.replica_offset;
-                if (src != r) {
-                    const float *row = p.pub_rows + ((size_t)parity * p.R + src) * (P + 1);
-                    for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
-                    if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
-                }
-            }
+            chain_sweep<NT>(p, round, parity, /*apply=*/true, s_sweep, nblocks);
             __syncthreads();
             ++round;
         }
@@ -755,28 +788,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         for (int r = blockIdx.x; r < p.R; r += nblocks)
             if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = p.lik[r];
         grid_barrier(p.barrier, nblocks);
-        if (blockIdx.x == 0) {
-            for (int k = tid; k < p.Rg; k += NT) {
-                s_sweep_l[k] = __ldcg(&p.pub_lhood[(size_t)parity * p.Rg + k]);
-                s_sweep_src[k] = k;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                uint8_t *lg_out = round < p.max_rounds ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
-                int ns;
-                if (p.replay) {
-                    const float *ur = p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1);
-                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) { return ur[k]; });
-                } else {
-                    ns = swap_sweep_serial(p.Rg, s_sweep_l, s_sweep_src, lg_out, [&](int k) {
-                        uint32_t c[4];
-                        philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
-                        return u01_open_right(c[0]);
-                    });
-                }
-                p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1;
-            }
-        }
+        if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nblocks);
     }
     if (tid == 0) atomicSub(&p.smsp_load[smid * 4 + s_hw[sgd_warp]], 1);
 }
