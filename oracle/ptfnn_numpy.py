@@ -70,10 +70,25 @@ class Network:
         out_delta = (desired - self.out) * (self.out * (1 - self.out))
         hid_delta = out_delta.dot(self.W2.T) * (self.hidout * (1 - self.hidout))   # pre-update W2
         lr = self.lrate
-        self.W2 += np.outer(self.hidout, lr * out_delta)      # R:67-69: W2[x,y] += lr*od[y]*hid[x]
-        self.B2 += -1 * lr * out_delta                          # R:70-71
-        self.W1 += np.outer(x, lr * hid_delta)                # R:74-76: W1[x,y] += lr*hd[y]*in[x]
-        self.B1 += -1 * lr * hid_delta                          # R:77-78
+        if self.task == REGRESSION:
+            # R:66-78 updates element by element in Python loops; kept that way so that this port
+            # has the reference's cost profile when it serves as the CPU baseline (same values).
+            I, H, O = self.Top
+            for a in range(H):
+                for b in range(O):
+                    self.W2[a, b] += lr * out_delta[b] * self.hidout[a]
+            for b in range(O):
+                self.B2[b] += -1 * lr * out_delta[b]
+            for a in range(I):
+                for b in range(H):
+                    self.W1[a, b] += lr * hid_delta[b] * x[a]
+            for b in range(H):
+                self.B1[b] += -1 * lr * hid_delta[b]
+        else:                                                   # C:78-82 is vectorised in the reference too
+            self.W2 += np.outer(self.hidout, lr * out_delta)
+            self.B2 += -1 * lr * out_delta
+            self.W1 += np.outer(x, lr * hid_delta)
+            self.B1 += -1 * lr * hid_delta
 
     def langevin_gradient(self, data, w, depth=1):             # R:99-118 / C:114-132
         w = np.array(w, dtype=np.float64, copy=True)
