@@ -93,6 +93,32 @@ __device__ __forceinline__ float sigmoid_fast(float z) { return rcp_ftz(1.0f + e
 // Sigmoid of the row-parallel likelihood pass: full-precision expf and IEEE division.
 __device__ __forceinline__ float sigmoid_precise(float z) { return 1.0f / (1.0f + expf(-z)); }
 
+// RB sigmoids with ONE reciprocal.  The row-parallel likelihood pass is bound by the XU (MUFU) pipe
+// (16 lanes/clk/SM on B200; ncu: 66 % XU, mio_throttle the top stall with 2 MUFU per sigmoid), so
+// the RB denominators d_b = 1 + 2^(-z_b log2 e) share a single MUFU.RCP of their product and each
+// 1/d_b is recovered with FMULs: 1.25 MUFU per sigmoid for RB = 4 instead of 2.  The exponent is
+// clamped so that the product cannot overflow (sigmoid(z < -20.8) is returned as 2^-30 ~ 9e-10:
+// absolute error < 1e-9, below fp32 resolution of the activations).
+template <int RB>
+__device__ __forceinline__ void sigmoid_group(const float (&z)[RB], float (&s)[RB]) {
+    constexpr float kClamp = RB >= 4 ? 30.0f : 60.0f;
+    float d[RB];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) d[b] = 1.0f + ex2_ftz(fminf(-1.4426950408889634f * z[b], kClamp));
+    if constexpr (RB == 4) {
+        const float p01 = d[0] * d[1], p23 = d[2] * d[3];
+        const float r = rcp_ftz(p01 * p23);
+        const float r01 = r * p23, r23 = r * p01;
+        s[0] = r01 * d[1]; s[1] = r01 * d[0]; s[2] = r23 * d[3]; s[3] = r23 * d[2];
+    } else if constexpr (RB == 2) {
+        const float r = rcp_ftz(d[0] * d[1]);
+        s[0] = r * d[1]; s[1] = r * d[0];
+    } else {
+#pragma unroll
+        for (int b = 0; b < RB; ++b) s[b] = rcp_ftz(d[b]);
+    }
+}
+
 template <bool PRECISE>
 __device__ __forceinline__ float sigmoid_sel(float z) {
     if constexpr (PRECISE) return sigmoid_precise(z);

@@ -38,7 +38,14 @@ struct SgdWarp {
     static constexpr int HPL = (H + 31) / 32;
     static constexpr int IP = IPad<I>::value;
     static constexpr int LEVELS = H > 16 ? 5 : H > 8 ? 4 : H > 4 ? 3 : H > 2 ? 2 : H > 1 ? 1 : 0;
+    // Small H: the output layer is evaluated from an ALL-GATHER of the hidden activations -- H
+    // independent SHFLs (pipelined: ~40 cycles for H = 5, ~60 for H = 12, measured) + a local dot
+    // product with a replicated copy of W2 -- instead of a dependent log-depth reduction
+    // (3 butterfly levels = 107 cycles, REDUX path = 78).
+    static constexpr bool GATHER = H <= 8;    // measured: H = 10 is faster on the REDUX path (201 vs 218 cycles/row)
+    static constexpr int HG = GATHER ? H : 1;
     float w1[HPL][I], b1[HPL], w2[HPL][O], b2[O];
+    float w2f[HG][O];   // GATHER only: full W2, identical in every lane
 
     // weight vector layout a1 (R:80-90): [W1 (I x H), W2 (H x O), B1 (H), B2 (O)]
     __device__ __forceinline__ void load(const float *w, int lane) {
@@ -54,6 +61,12 @@ struct SgdWarp {
         }
 #pragma unroll
         for (int o = 0; o < O; ++o) b2[o] = w[I * H + H * O + H + o];
+        if constexpr (GATHER) {
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int o = 0; o < O; ++o) w2f[h][o] = w[I * H + h * O + o];
+        }
     }
     __device__ __forceinline__ void store(float *w, int lane) const {
 #pragma unroll
@@ -100,8 +113,10 @@ struct SgdWarp {
 #pragma unroll
         for (int k = 0; k < HPL; ++k) {
             hid[k] = (lane + 32 * k < H) ? sigmoid_fast(z[k]) : 0.0f;
+            if constexpr (!GATHER) {
 #pragma unroll
-            for (int o = 0; o < O; ++o) p[o] = fmaf(hid[k], w2[k][o], p[o]);
+                for (int o = 0; o < O; ++o) p[o] = fmaf(hid[k], w2[k][o], p[o]);
+            }
         }
         // independent of the reduction below: stale pre-activation of the next row and xn.x + 1
         float zn[HPL];
@@ -109,14 +124,34 @@ struct SgdWarp {
         float c = 1.0f;
 #pragma unroll
         for (int i = 0; i < I; ++i) c = fmaf(xn[i], x[i], c);
+        float g[HG];
+        if constexpr (GATHER) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) g[h] = __shfl_sync(0xffffffffu, hid[0], h);
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                float a0 = 0.0f, a1 = 0.0f;                  // two partial sums: shorter dependent chain
+#pragma unroll
+                for (int h = 0; h + 1 < H; h += 2) { a0 = fmaf(g[h], w2f[h][o], a0); a1 = fmaf(g[h + 1], w2f[h + 1][o], a1); }
+                if (H & 1) a0 = fmaf(g[H - 1], w2f[H - 1][o], a0);
+                p[o] = a0 + a1;
+            }
+        }
         float od[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
-            const float out = sigmoid_fast(warp_sum(p[o], LEVELS) - b2[o]);       // R:54-55
+            const float zo = (GATHER ? p[o] : warp_sum(p[o], LEVELS)) - b2[o];
+            const float out = sigmoid_fast(zo);                                   // R:54-55
             float d;
             if constexpr (TASK == kTaskCls) d = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75 one-hot
             else d = yv;                                                          // O == 1 (R:132)
             od[o] = (d - out) * (out * (1.0f - out));                             // R:58
+        }
+        if constexpr (GATHER) {                                                   // replicated W2 follows R:67-69 too
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int o = 0; o < O; ++o) w2f[h][o] = fmaf(lr * od[o], g[h], w2f[h][o]);
         }
 #pragma unroll
         for (int k = 0; k < HPL; ++k) {
@@ -281,14 +316,24 @@ __device__ __forceinline__ void lik_rows_impl(const float *__restrict__ w, const
 #pragma unroll
             for (int o = 0; o < O; ++o) w2h[o] = w[oW2 + h * O + o];
             const float nb = -w[oB1 + h];
+            float zz[RB], hid[RB];
 #pragma unroll
             for (int b = 0; b < RB; ++b) {
                 float z = nb;
 #pragma unroll
                 for (int i = 0; i < I; ++i) z = fmaf(x[b][i], w1h[i], z);
-                const float hid = sigmoid_sel<PRECISE>(z);
+                zz[b] = z;
+            }
+            if constexpr (PRECISE) {
 #pragma unroll
-                for (int o = 0; o < O; ++o) acc[b][o] = fmaf(hid, w2h[o], acc[b][o]);
+                for (int b = 0; b < RB; ++b) hid[b] = sigmoid_precise(zz[b]);
+            } else {
+                sigmoid_group<RB>(zz, hid);
+            }
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+#pragma unroll
+                for (int o = 0; o < O; ++o) acc[b][o] = fmaf(hid[b], w2h[o], acc[b][o]);
             }
         }
 #pragma unroll
@@ -389,7 +434,7 @@ struct ChainParams {
     int max_rounds;
     int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
     int P;
-    int *smsp_load;                // [num_SMs][4] serial (SGD) warps currently placed on each SM sub-partition
+    int *smsp_load;                // [num_SMs] ticket counter used to spread serial (SGD) warps over the SM sub-partitions
 };
 
 __device__ __forceinline__ bool swap_due(int rule, int s, int i) {
@@ -548,19 +593,17 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 
     // ---- which warp runs the serial recurrence.  Warps are bound to one of the SM's four
     // sub-partitions (hardware warp slot % 4); co-resident CTAs would otherwise all put their
-    // serial warp on the same sub-partition and queue for its issue port.  Greedy balance through a
-    // per-SM counter table (released at kernel exit).
+    // serial warp on the same sub-partition and queue for its issue port (measured: 2x slower rows).
     __shared__ unsigned int s_hw[NW];
     if (lane == 0) s_hw[warp] = hw_warpid() & 3u;
     __syncthreads();
     const unsigned int smid = hw_smid();
     if (tid == 0) {
-        int best = 0, best_load = 1 << 30;
-        for (int w = 0; w < NW; ++w) {
-            const int load = *(volatile int *)&p.smsp_load[smid * 4 + s_hw[w]];
-            if (load < best_load) { best_load = load; best = w; }
-        }
-        atomicAdd(&p.smsp_load[smid * 4 + s_hw[best]], 1);
+        // race-free: a per-SM ticket; ticket % 4 is the sub-partition this CTA's serial warp should use
+        const unsigned int target = (unsigned int)atomicAdd(&p.smsp_load[smid], 1) & 3u;
+        int best = 0;
+        for (int w = NW - 1; w >= 0; --w)
+            if (s_hw[w] == target) best = w;
         s_flag[0] = best;
     }
     __syncthreads();
@@ -790,7 +833,6 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         grid_barrier(p.barrier, nblocks);
         if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nblocks);
     }
-    if (tid == 0) atomicSub(&p.smsp_load[smid * 4 + s_hw[sgd_warp]], 1);
 }
 
 // ==========================================================================================

@@ -9,7 +9,7 @@
 #define PTFNN_TOPOLOGIES(X)                                                                          \
     X(reg_4_5_1, 0, 4, 5, 1, 128, 4)      /* Data_OneStepAhead suite, paper / drafts (hidden = 5) */  \
     X(reg_4_10_1, 0, 4, 10, 1, 128, 4)    /* checked-in driver, R:915 (hidden = 10) */                \
-    X(reg_4_64_1, 0, 4, 64, 1, 64, 8)     /* synthetic time series, BASELINE configs[3]: 1024 temperatures = 7 per SM */ \
+    X(reg_4_64_1, 0, 4, 64, 1, 128, 7)    /* synthetic time series, BASELINE configs[3]: 1024 temperatures = 7 per SM */ \
     X(cls_4_12_3, 1, 4, 12, 3, 128, 4)    /* Iris, C:920-930 */                                       \
     X(cls_9_12_2, 1, 9, 12, 2, 128, 2)    /* Cancer, C:950-957 */                                     \
     X(cls_34_50_2, 1, 34, 50, 2, 128, 2)  /* Ionosphere, C:942-949 */                                 \
