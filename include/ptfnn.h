@@ -188,6 +188,10 @@ int ptfnn_op_evaluate_proposal(int32_t device, int32_t task, int32_t n_in, int32
 int ptfnn_op_langevin_gradient(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
                                const double *data, int32_t rows, int32_t n_cols, const double *w,
                                double learn_rate, int32_t depth, double *w_out /* [P] */);
+/* measurement helper: best-of-`repeats` device time (CUDA events) of the langevin_gradient kernel alone */
+int ptfnn_time_langevin_gradient(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                                 const double *data, int32_t rows, int32_t n_cols, const double *w,
+                                 double learn_rate, int32_t depth, int32_t repeats, double *kernel_ms);
 /* ptReplica.likelihood_func (R:200-205 / C:209-222): out = {loglik/adapttemp, rmse, accuracy} */
 int ptfnn_op_likelihood(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
                         const double *data, int32_t rows, int32_t n_cols, const double *w, double tau_sq,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
     "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
-    "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
+    "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
     "ptfnn_op_swap_sweep",
 ]
 
@@ -139,6 +139,16 @@ def op_langevin_gradient(task, topology, data, w, learn_rate, depth=1, device=0)
     check(load().ptfnn_op_langevin_gradient(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
                                             C.c_double(learn_rate), int(depth), ptr(out)))
     return out
+
+
+def time_langevin_gradient(task, topology, data, w, learn_rate, depth=1, repeats=3, device=0):
+    """Device time (ms, CUDA events, best of ``repeats``) of the langevin_gradient kernel alone."""
+    I, H, O = topology
+    data, w = f64(data), f64(w)
+    ms = C.c_double(0.0)
+    check(load().ptfnn_time_langevin_gradient(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
+                                              C.c_double(learn_rate), int(depth), int(repeats), C.byref(ms)))
+    return ms.value
 
 
 def op_likelihood(task, topology, data, w, tau_sq=1.0, adapttemp=1.0, want_fx=True, device=0):

@@ -497,7 +497,8 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     const size_t stage_bytes = ((size_t)s->n_train * s->IP + ((s->n_train + 3) & ~3) + (size_t)s->n_test * s->IP + ((s->n_test + 3) & ~3)) * 4;
     p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
     const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
-    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test);
+    const int team_floats = UseSgdTeam<1>::value ? 0 : (c.n_hidden > 64 ? c.n_hidden + c.n_out : 0);   // mirrors UseSgdTeam<H>
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats);
     if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
     CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int per_sm = 0;
@@ -807,9 +808,27 @@ extern "C" int ptfnn_op_likelihood(int32_t device, int32_t task, int32_t I, int3
     return PTFNN_OK;
 }
 
+static int op_langevin_impl(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                            int32_t rows, int32_t n_cols, const double *w, double learn_rate, int32_t depth,
+                            double *w_out, int repeats, double *kernel_ms);
+
 extern "C" int ptfnn_op_langevin_gradient(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
                                           int32_t rows, int32_t n_cols, const double *w, double learn_rate, int32_t depth,
                                           double *w_out) {
+    return op_langevin_impl(device, task, I, H, O, data, rows, n_cols, w, learn_rate, depth, w_out, 1, nullptr);
+}
+
+extern "C" int ptfnn_time_langevin_gradient(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                                            int32_t rows, int32_t n_cols, const double *w, double learn_rate, int32_t depth,
+                                            int32_t repeats, double *kernel_ms) {
+    if (!kernel_ms || repeats < 1) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    std::vector<double> out((size_t)I * H + (size_t)H * O + H + O);
+    return op_langevin_impl(device, task, I, H, O, data, rows, n_cols, w, learn_rate, depth, out.data(), repeats, kernel_ms);
+}
+
+static int op_langevin_impl(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                            int32_t rows, int32_t n_cols, const double *w, double learn_rate, int32_t depth,
+                            double *w_out, int repeats, double *kernel_ms) {
     if (!data || !w_out || depth < 0) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
     const KernelSet *ks;
     OpData od;
@@ -821,10 +840,22 @@ extern "C" int ptfnn_op_langevin_gradient(int32_t device, int32_t task, int32_t 
     DataView v{od.x.p, od.y.p, rows};
     const float *wp = od.w.p; float *op = d_out.p; float lr = (float)learn_rate; int dep = depth;
     void *args[] = {&wp, &op, &v, &lr, &dep};
-    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 16 + (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4);
+    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 16 + (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4) + (size_t)(H + O) * 4 + 16;
     CU_TRY(nullptr, cudaFuncSetAttribute(ks->sgd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_TRY(nullptr, cudaLaunchKernel(ks->sgd, dim3(1), dim3(32), args, smem, 0));
-    CU_TRY(nullptr, cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CU_TRY(nullptr, cudaEventCreate(&e0)); CU_TRY(nullptr, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < repeats; ++rep) {
+        CU_TRY(nullptr, cudaEventRecord(e0, 0));
+        CU_TRY(nullptr, cudaLaunchKernel(ks->sgd, dim3(1), dim3(ks->sgd_threads), args, smem, 0));
+        CU_TRY(nullptr, cudaEventRecord(e1, 0));
+        CU_TRY(nullptr, cudaDeviceSynchronize());
+        float ms = 0.f;
+        CU_TRY(nullptr, cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = best;
     std::vector<float> t(P);
     CU_TRY(nullptr, cudaMemcpy(t.data(), d_out.p, (size_t)P * 4, cudaMemcpyDeviceToHost));
     for (int j = 0; j < P; ++j) w_out[j] = t[j];

@@ -152,6 +152,31 @@ __device__ __forceinline__ float warp_sum(float v, int levels) {
     return warp_sum_shfl(v, 5);
 }
 
+// O sums at once: the O integer REDUX operations are independent (they pipeline), and ONE range
+// guard covers all of them, so there is a single warp-uniform branch per row instead of O.
+template <int O>
+__device__ __forceinline__ void warp_sum_vec(float (&v)[O], int levels) {
+    if (levels <= 1) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) v[o] = warp_sum_shfl(v[o], levels);
+        return;
+    }
+    unsigned int m = 0u;
+#pragma unroll
+    for (int o = 0; o < O; ++o) m = max(m, __float_as_uint(v[o]) & 0x7fffffffu);
+    const unsigned int mag = __reduce_max_sync(0xffffffffu, m);
+    int s[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) s[o] = __reduce_add_sync(0xffffffffu, __float2int_rn(v[o] * 4194304.0f));
+    if (mag < 0x417e6666u) {   // 15.9f
+#pragma unroll
+        for (int o = 0; o < O; ++o) v[o] = (float)s[o] * (1.0f / 4194304.0f);
+    } else {
+#pragma unroll
+        for (int o = 0; o < O; ++o) v[o] = warp_sum_shfl(v[o], 5);
+    }
+}
+
 __device__ __forceinline__ unsigned int hw_smid() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned int hw_warpid() { unsigned int r; asm volatile("mov.u32 %0, %%warpid;" : "=r"(r)); return r; }
 

@@ -137,10 +137,11 @@ struct SgdWarp {
                 p[o] = a0 + a1;
             }
         }
+        if constexpr (!GATHER) warp_sum_vec<O>(p, LEVELS);
         float od[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
-            const float zo = (GATHER ? p[o] : warp_sum(p[o], LEVELS)) - b2[o];
+            const float zo = p[o] - b2[o];
             const float out = sigmoid_fast(zo);                                   // R:54-55
             float d;
             if constexpr (TASK == kTaskCls) d = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75 one-hot
@@ -277,6 +278,211 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
         }
     }
     net.store(w_out, lane);
+}
+
+// ==========================================================================================
+// K2 (wide hidden layers): the serial recurrence run by a TEAM of NWT warps.  With H = 256, one
+// warp would need ~216 live registers per lane (8 hidden units x (I + O + 1)) and spills; here
+// thread t owns hidden unit(s) t, t + T, ... (row view: W1 column, B1, W2 row in registers) and the
+// output layer is evaluated in a column view: output o belongs to warp o % NWT, which keeps that
+// W2 column in registers (H/32 per lane), reads the hidden activations from shared memory, and
+// reduces with one REDUX.  Two team barriers per row (hid -> out_delta -> hid_delta).  Both views of
+// W2 receive the same update (R:67-69), so they stay bit-identical.
+// ==========================================================================================
+template <int H>
+struct UseSgdTeam {
+    static constexpr bool value = H > 64;
+};
+
+template <int I, int H, int O, int TASK, int NT>
+__device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, const DataView &d, bool staged, float lr,
+                                              SgdStream &st, float *s_hid /* [H] */, float *s_od /* [O] */) {
+    constexpr int IP = IPad<I>::value;
+    constexpr int NWT = NT / 32;
+    constexpr int HPT = (H + NT - 1) / NT;        // hidden units per thread (row view)
+    constexpr int OPW = (O + NWT - 1) / NWT;      // outputs per warp (column view)
+    constexpr int HC = (H + 31) / 32;             // hidden units per lane in the column view
+    constexpr int oW2 = I * H, oB1 = I * H + H * O, oB2 = I * H + H * O + H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float w1[HPT][I], b1[HPT], w2r[HPT][O];
+    float w2c[OPW][HC], b2c[OPW];
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+        const int h = tid + NT * k;
+        const bool a = h < H;
+#pragma unroll
+        for (int i = 0; i < I; ++i) w1[k][i] = a ? w_in[i * H + h] : 0.0f;
+#pragma unroll
+        for (int o = 0; o < O; ++o) w2r[k][o] = a ? w_in[oW2 + h * O + o] : 0.0f;
+        b1[k] = a ? w_in[oB1 + h] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < OPW; ++j) {
+        const int o = warp + NWT * j;
+#pragma unroll
+        for (int m = 0; m < HC; ++m) {
+            const int h = lane + 32 * m;
+            w2c[j][m] = (o < O && h < H) ? w_in[oW2 + h * O + o] : 0.0f;
+        }
+        b2c[j] = o < O ? w_in[oB2 + o] : 0.0f;
+    }
+    __syncthreads();   // w_in may alias w_out; everybody has read its share
+
+    auto preact = [&](const float(&x)[IP], float(&z)[HPT]) {
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+            float t = -b1[k];
+#pragma unroll
+            for (int i = 0; i < I; ++i) t = fmaf(x[i], w1[k][i], t);
+            z[k] = t;
+        }
+    };
+    auto row = [&](const float(&x)[IP], float yv, const float(&xn)[IP], float(&z)[HPT]) {
+        float hid[HPT];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+            const int h = tid + NT * k;
+            hid[k] = h < H ? sigmoid_fast(z[k]) : 0.0f;
+            if (h < H) s_hid[h] = hid[k];
+        }
+        float zn[HPT];
+        preact(xn, zn);
+        float c = 1.0f;
+#pragma unroll
+        for (int i = 0; i < I; ++i) c = fmaf(xn[i], x[i], c);
+        __syncthreads();
+        // ---- column view: this warp's outputs (all OPW of them at once: independent dot products,
+        //      one vectorised REDUX, pipelined sigmoids)
+        {
+            float hv[HC];
+#pragma unroll
+            for (int m = 0; m < HC; ++m) hv[m] = (lane + 32 * m < H) ? s_hid[lane + 32 * m] : 0.0f;
+            float acc[OPW];
+#pragma unroll
+            for (int j = 0; j < OPW; ++j) {
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                for (int m = 0; m + 1 < HC; m += 2) { a0 = fmaf(hv[m], w2c[j][m], a0); a1 = fmaf(hv[m + 1], w2c[j][m + 1], a1); }
+                if (HC & 1) a0 = fmaf(hv[HC - 1], w2c[j][HC - 1], a0);
+                acc[j] = a0 + a1;
+            }
+            warp_sum_vec<OPW>(acc, 5);
+#pragma unroll
+            for (int j = 0; j < OPW; ++j) {
+                const int o = warp + NWT * j;
+                const float out = sigmoid_fast(acc[j] - b2c[j]);                      // R:54-55
+                float dd;
+                if constexpr (TASK == kTaskCls) dd = ((int)yv == o) ? 1.0f : 0.0f;    // C:73-75
+                else dd = yv;
+                const float od = (o < O) ? (dd - out) * (out * (1.0f - out)) : 0.0f;  // R:58
+                if (lane == 0 && o < O) s_od[o] = od;
+                const float lo = lr * od;
+#pragma unroll
+                for (int m = 0; m < HC; ++m) w2c[j][m] = fmaf(lo, hv[m], w2c[j][m]);   // R:67-69
+                b2c[j] -= lo;                                                         // R:70-71
+            }
+        }
+        __syncthreads();
+        // ---- row view: hid_delta with the pre-update W2 row (R:59), then the updates
+        float od[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) od[o] = s_od[o];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int o = 0; o + 1 < O; o += 2) { s0 = fmaf(od[o], w2r[k][o], s0); s1 = fmaf(od[o + 1], w2r[k][o + 1], s1); }
+            if (O & 1) s0 = fmaf(od[O - 1], w2r[k][O - 1], s0);
+            const float lh = lr * ((s0 + s1) * (hid[k] * (1.0f - hid[k])));
+            z[k] = fmaf(lh, c, zn[k]);
+#pragma unroll
+            for (int o = 0; o < O; ++o) w2r[k][o] = fmaf(lr * od[o], hid[k], w2r[k][o]);
+#pragma unroll
+            for (int i = 0; i < I; ++i) w1[k][i] = fmaf(lh, x[i], w1[k][i]);           // R:74-76
+            b1[k] -= lh;                                                               // R:77-78
+        }
+    };
+
+    float xc[IP], xz[IP], yc;
+    float z[HPT];
+#pragma unroll
+    for (int i = 0; i < IP; ++i) xz[i] = 0.0f;
+    auto run_rows = [&](uint32_t xa, uint32_t ya, int count) {   // look-ahead row inside the same tile
+        for (int r = 0; r < count; ++r) {
+            float xn[IP];
+            lds_row<IP>(xa + (uint32_t)(r + 1) * IP * 4u, xn);
+            const float yn = lds_f32(ya + (uint32_t)(r + 1) * 4u);
+            row(xc, yc, xn, z);
+#pragma unroll
+            for (int i = 0; i < IP; ++i) xc[i] = xn[i];
+            yc = yn;
+        }
+    };
+    if (staged) {
+        const uint32_t xa = smem_u32(d.x), ya = smem_u32(d.y);
+        lds_row<IP>(xa, xc);
+        yc = lds_f32(ya);
+        preact(xc, z);
+        run_rows(xa, ya, d.n - 1);
+        row(xc, yc, xz, z);
+    } else {
+        const int ntiles = (d.n + kTileRows - 1) / kTileRows;
+        auto issue = [&](int t) {
+            const int rows = min(kTileRows, d.n - t * kTileRows);
+            const uint32_t bx = (uint32_t)rows * IP * 4u;
+            const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;
+            if (tid == 0) {
+                uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
+                mbar_arrive_expect_tx(bar, bx + by);
+                tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
+                tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
+            }
+        };
+        auto wait = [&](int t) {
+            if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
+            else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
+        };
+        issue(0);
+        wait(0);
+        lds_row<IP>(smem_u32(st.tile_x0), xc);
+        yc = lds_f32(smem_u32(st.tile_y0));
+        preact(xc, z);
+        for (int t = 0; t < ntiles; ++t) {
+            const bool more = t + 1 < ntiles;
+            if (more) issue(t + 1);      // other buffer: every thread is past tile t-1 (team barriers in row())
+            const int rows = min(kTileRows, d.n - t * kTileRows);
+            run_rows(smem_u32((t & 1) ? st.tile_x1 : st.tile_x0), smem_u32((t & 1) ? st.tile_y1 : st.tile_y0), rows - 1);
+            if (more) {
+                wait(t + 1);
+                float xn[IP];
+                lds_row<IP>(smem_u32((t & 1) ? st.tile_x0 : st.tile_x1), xn);
+                const float yn = lds_f32(smem_u32((t & 1) ? st.tile_y0 : st.tile_y1));
+                row(xc, yc, xn, z);
+#pragma unroll
+                for (int i = 0; i < IP; ++i) xc[i] = xn[i];
+                yc = yn;
+            } else {
+                row(xc, yc, xz, z);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+        const int h = tid + NT * k;
+        if (h < H) {
+#pragma unroll
+            for (int i = 0; i < I; ++i) w_out[i * H + h] = w1[k][i];
+#pragma unroll
+            for (int o = 0; o < O; ++o) w_out[oW2 + h * O + o] = w2r[k][o];
+            w_out[oB1 + h] = b1[k];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < OPW; ++j) {
+        const int o = warp + NWT * j;
+        if (o < O && lane == 0) w_out[oB2 + o] = b2c[j];
+    }
+    __syncthreads();
 }
 
 // ==========================================================================================
@@ -454,10 +660,10 @@ struct NetSizes {
 // dynamic shared memory layout (floats unless noted); host computes the same with chain_smem_bytes()
 struct ChainSmem {
     int P4;          // P rounded up to 4
-    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep, off_stage, total;
+    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep, off_team, off_stage, total;
 };
 __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
-                                                       int n_test) {
+                                                       int n_test, int team_floats = 0) {
     ChainSmem L;
     L.P4 = (P + 3) & ~3;
     size_t o = 0;
@@ -468,6 +674,7 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
     L.off_bar = take(8 * 4);
     L.off_tiles = take(staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4));
     L.off_sweep = take(Rg > 1 ? (size_t)kSweepChunk * 8 : 0);   // one chunk of lhood fields for the streaming sweep
+    L.off_team = take((size_t)team_floats * 4);
     auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
     L.off_stage = take(staged ? ((size_t)n_train * IP + pad4(n_train) + (size_t)n_test * IP + pad4(n_test)) * 4 : 0);
     L.total = o;
@@ -543,7 +750,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int IP = NetSizes<I, H, O>::IP;
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n);
+    constexpr bool TEAM = UseSgdTeam<H>::value;
+    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? H + O : 0);
+    float *s_team_hid = reinterpret_cast<float *>(smem_raw + L.off_team);
+    float *s_team_od = s_team_hid + H;
     float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
     float *s_prop = reinterpret_cast<float *>(smem_raw + L.off_prop);
     float *s_gd = reinterpret_cast<float *>(smem_raw + L.off_gd);
@@ -670,7 +880,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 const bool lg = p.use_lg && ((double)lx < p.l_prob);              // R:329
                 // ---- Langevin branch, first SGD epoch: w_gd = langevin_gradient(w)   (R:330)
                 if (lg && !gd_valid) {
-                    if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
+                    if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_gd, train, p.staged != 0, p.lr, stream, s_team_hid, s_team_od);
+                    else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
                     __syncthreads();
                     gd_valid = p.memo;
                 }
@@ -699,7 +910,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[k] = 0.0;
                 int c_tr = 0, c_te = 0;
-                if (lg && NW > 1) {
+                if (lg && NW > 1 && !TEAM) {
                     if (is_sgd_warp) {
                         sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                     } else {
@@ -708,7 +919,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     }
                 } else {
                     if (lg) {
-                        if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
+                        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream, s_team_hid, s_team_od);
+                        else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
                     lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, train, tid, NT, s[0], s[1], c_tr);
@@ -928,16 +1140,18 @@ __global__ void __launch_bounds__(NT) op_forward_kernel(const float *w, DataView
     if (threadIdx.x == 0) { sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2]; }
 }
 
-template <int I, int H, int O, int TASK>
-__global__ void __launch_bounds__(32) op_sgd_kernel(const float *w_in, float *w_out, DataView d, float lr, int depth) {
+template <int I, int H, int O, int TASK, int NT>
+__global__ void __launch_bounds__(UseSgdTeam<H>::value ? NT : 32) op_sgd_kernel(const float *w_in, float *w_out, DataView d, float lr, int depth) {
     constexpr int P = NetSizes<I, H, O>::P;
     constexpr int IP = IPad<I>::value;
+    constexpr bool TEAM = UseSgdTeam<H>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_w = reinterpret_cast<float *>(smem_raw);
     const size_t wbytes = ((size_t)P * 4 + 15) & ~(size_t)15;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + wbytes);
     float *tiles = reinterpret_cast<float *>(smem_raw + wbytes + 16);
-    for (int j = threadIdx.x; j < P; j += 32) s_w[j] = w_in[j];
+    float *s_team = tiles + 2 * (kTileRows * IP + kTileRows);
+    for (int j = threadIdx.x; j < P; j += blockDim.x) s_w[j] = w_in[j];
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     SgdStream st;
@@ -946,10 +1160,11 @@ __global__ void __launch_bounds__(32) op_sgd_kernel(const float *w_in, float *w_
     st.bar0 = &s_bar[0]; st.bar1 = &s_bar[1];
     st.parity0 = st.parity1 = 0u;
     for (int e = 0; e < depth; ++e) {                       // R:108 `depth` epochs (sgd_depth is always 1, R:170)
-        sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
-        __syncwarp();
+        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_w, d, false, lr, st, s_team, s_team + H);
+        else sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
+        __syncthreads();
     }
-    for (int j = threadIdx.x; j < P; j += 32) w_out[j] = s_w[j];
+    for (int j = threadIdx.x; j < P; j += blockDim.x) w_out[j] = s_w[j];
 }
 
 }  // namespace ptfnn

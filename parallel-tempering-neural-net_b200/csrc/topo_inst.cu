@@ -16,7 +16,8 @@ const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
         (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT, PTFNN_T_MINB>,
         (const void *)init_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_forward_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
-        (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK>,
+        (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
+        ptfnn::UseSgdTeam<PTFNN_T_H>::value ? PTFNN_T_NT : 32,
     };
     return &ks;
 }

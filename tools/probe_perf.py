@@ -11,14 +11,8 @@ from oracle import ptfnn_numpy as on
 
 def sgd_row_latency(task, topo, data, lr=0.01, d0=1, d1=9):
     w = np.random.RandomState(0).randn(on.num_params(topo)) * 0.3
-    capi.op_langevin_gradient(task, topo, data, w, lr, depth=d0)
-    ts = []
-    for d in (d0, d1):
-        torch.cuda.synchronize(); t = time.perf_counter()
-        capi.op_langevin_gradient(task, topo, data, w, lr, depth=d)
-        torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
-    per_row = (ts[1] - ts[0]) / ((d1 - d0) * data.shape[0])
-    return per_row * 1e9
+    ms = capi.time_langevin_gradient(task, topo, data, w, lr, depth=1, repeats=3)
+    return ms * 1e6 / data.shape[0]
 
 
 def chain_step_cost(task, topo, train, test, R, si, lr, memo, n=8):
