@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -498,13 +499,17 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
     const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
     const int team_floats = UseSgdTeam<1>::value ? 0 : (c.n_hidden > 64 ? c.n_hidden + c.n_out : 0);   // mirrors UseSgdTeam<H>
-    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats);
+    const int lik_floats = c.n_hidden * ((c.n_in + 1 + c.n_out + 3) & ~3);   // mirrors LikLayout<I, O>::LW
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats);
     if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
     CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int per_sm = 0;
     CU_TRY(s, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->ks->chain, NT, L.total));
     if (per_sm < 1) return fail(s, PTFNN_E_CUDA, "chain kernel does not fit on an SM (smem %zu)", L.total);
     const int grid = std::min(R, per_sm * s->num_sms);
+    // many temperatures per SM: keep the serial warps' sub-partitions quiet (see chain_kernel)
+    p.lik_team_warps = 0;
+    if (const char *e = getenv("PTFNN_LIK_TEAM_WARPS")) p.lik_team_warps = atoi(e);
     void *args[] = {&p};
     CU_TRY(s, cudaLaunchCooperativeKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());

@@ -32,20 +32,88 @@ constexpr bool kPreciseLik = false;  // rows per TMA tile when the training set 
 
 // ==========================================================================================
 // K2: serial SGD recurrence, one warp.  Lane l owns hidden units l, l+32, ... in registers.
+//
+// The recurrence is latency-bound (one dependent chain per row) and the warp issues in order, so
+// both the LENGTH of the chain and the instruction COUNT per row matter.  Per row the chain is
+//     EX2 -> FADD -> RCP            hidden sigmoid, pre-activation kept pre-multiplied by -log2(e)
+//     -> FMUL/FFMA -> F2I -> REDUX  output-layer sum in 2^-22 fixed point on the integer REDUX unit
+//        (H <= 8: SHFL all-gather + local dot product with a replicated, pre-scaled W2 instead)
+//     -> I2F -> FFMA                un-scale, subtract B2 and multiply by -log2(e) in ONE FFMA
+//     -> EX2 -> FADD -> RCP         output sigmoid
+//     -> {FADD | FFMA} -> FMUL      out_delta = (d - out) * (out - out^2)
+//     -> FFMA                       next row's scaled pre-activation = stale value + out_delta * K
+// where everything else (stale pre-activation of the next row with the not-yet-updated weights,
+// K = -log2(e) lr (x_next.x + 1) hid (1 - hid) W2, the weight updates, the range guard of the fixed
+// point sum) is independent of the chain and fills its MUFU / REDUX latencies.  With two hidden
+// units per lane (H = 64) the lane-local arithmetic uses the packed FFMA2 / FMUL2 / FADD2
+// instructions of sm_100 (two fp32 operations per issue slot).
 // ==========================================================================================
+constexpr float kL2E = 1.4426950408889634f;
+constexpr float kFix = 4194304.0f;               // 2^22
+constexpr float kInvFix = 1.0f / 4194304.0f;
+
+// elementwise helpers over the HPL hidden units of a lane; adjacent pairs go through f32x2
+template <int N>
+__device__ __forceinline__ void vfma(float (&r)[N], const float (&a)[N], const float (&b)[N], const float (&c)[N]) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+        const float2 t = __ffma2_rn(make_float2(a[k], a[k + 1]), make_float2(b[k], b[k + 1]), make_float2(c[k], c[k + 1]));
+        r[k] = t.x; r[k + 1] = t.y;
+    }
+    if (N & 1) r[N - 1] = fmaf(a[N - 1], b[N - 1], c[N - 1]);
+}
+template <int N>
+__device__ __forceinline__ void vfma_s(float (&r)[N], const float (&a)[N], float s, const float (&c)[N]) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+        const float2 t = __ffma2_rn(make_float2(a[k], a[k + 1]), make_float2(s, s), make_float2(c[k], c[k + 1]));
+        r[k] = t.x; r[k + 1] = t.y;
+    }
+    if (N & 1) r[N - 1] = fmaf(a[N - 1], s, c[N - 1]);
+}
+template <int N>
+__device__ __forceinline__ void vmul(float (&r)[N], const float (&a)[N], const float (&b)[N]) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+        const float2 t = __fmul2_rn(make_float2(a[k], a[k + 1]), make_float2(b[k], b[k + 1]));
+        r[k] = t.x; r[k + 1] = t.y;
+    }
+    if (N & 1) r[N - 1] = a[N - 1] * b[N - 1];
+}
+template <int N>
+__device__ __forceinline__ void vmul_s(float (&r)[N], const float (&a)[N], float s) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+        const float2 t = __fmul2_rn(make_float2(a[k], a[k + 1]), make_float2(s, s));
+        r[k] = t.x; r[k + 1] = t.y;
+    }
+    if (N & 1) r[N - 1] = a[N - 1] * s;
+}
+template <int N>
+__device__ __forceinline__ void vadd_s(float (&r)[N], const float (&a)[N], float s) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+        const float2 t = __fadd2_rn(make_float2(a[k], a[k + 1]), make_float2(s, s));
+        r[k] = t.x; r[k + 1] = t.y;
+    }
+    if (N & 1) r[N - 1] = a[N - 1] + s;
+}
+
 template <int I, int H, int O, int TASK>
 struct SgdWarp {
     static constexpr int HPL = (H + 31) / 32;
     static constexpr int IP = IPad<I>::value;
     static constexpr int LEVELS = H > 16 ? 5 : H > 8 ? 4 : H > 4 ? 3 : H > 2 ? 2 : H > 1 ? 1 : 0;
     // Small H: the output layer is evaluated from an ALL-GATHER of the hidden activations -- H
-    // independent SHFLs (pipelined: ~40 cycles for H = 5, ~60 for H = 12, measured) + a local dot
-    // product with a replicated copy of W2 -- instead of a dependent log-depth reduction
-    // (3 butterfly levels = 107 cycles, REDUX path = 78).
-    static constexpr bool GATHER = H <= 8;    // measured: H = 10 is faster on the REDUX path (201 vs 218 cycles/row)
+    // independent SHFLs (pipelined: ~40 cycles for H = 5, measured) + a local dot product with a
+    // replicated copy of W2 -- instead of a dependent reduction (REDUX path ~78 cycles).
+    static constexpr bool GATHER = H <= 8;    // measured: H = 10 is faster on the REDUX path
     static constexpr int HG = GATHER ? H : 1;
-    float w1[HPL][I], b1[HPL], w2[HPL][O], b2[O];
-    float w2f[HG][O];   // GATHER only: full W2, identical in every lane
+    // hidden-unit index k is the FASTEST index so that pairs (k, k+1) feed the f32x2 instructions
+    float w1[I][HPL], b1[HPL], w2[O][HPL], b2[O];
+    float b2l[O];        // log2(e) * B2
+    float w2q[O][HPL];   // REDUX path: 2^22 * W2 (exact scaling)
+    float w2f[HG][O];    // GATHER: full W2, identical in every lane (same update, bit for bit)
 
     // weight vector layout a1 (R:80-90): [W1 (I x H), W2 (H x O), B1 (H), B2 (O)]
     __device__ __forceinline__ void load(const float *w, int lane) {
@@ -54,19 +122,22 @@ struct SgdWarp {
             const int h = lane + 32 * k;
             const bool a = h < H;
 #pragma unroll
-            for (int i = 0; i < I; ++i) w1[k][i] = a ? w[i * H + h] : 0.0f;
+            for (int i = 0; i < I; ++i) w1[i][k] = a ? w[i * H + h] : 0.0f;
 #pragma unroll
-            for (int o = 0; o < O; ++o) w2[k][o] = a ? w[I * H + h * O + o] : 0.0f;
-            b1[k] = a ? w[I * H + H * O + h] : 0.0f;
+            for (int o = 0; o < O; ++o) w2[o][k] = a ? w[I * H + h * O + o] : 0.0f;
+            // lanes without a hidden unit: z = x.0 - 1e4 -> sigmoid = 0 exactly (ex2 -> +inf, rcp -> 0),
+            // so every one of their updates is an exact zero and no select sits on the dependent chain
+            b1[k] = a ? w[I * H + H * O + h] : 1.0e4f;
         }
 #pragma unroll
-        for (int o = 0; o < O; ++o) b2[o] = w[I * H + H * O + H + o];
+        for (int o = 0; o < O; ++o) { b2[o] = w[I * H + H * O + H + o]; b2l[o] = kL2E * b2[o]; }
         if constexpr (GATHER) {
 #pragma unroll
             for (int h = 0; h < H; ++h)
 #pragma unroll
                 for (int o = 0; o < O; ++o) w2f[h][o] = w[I * H + h * O + o];
         }
+        refresh(lane);
     }
     __device__ __forceinline__ void store(float *w, int lane) const {
 #pragma unroll
@@ -74,9 +145,9 @@ struct SgdWarp {
             const int h = lane + 32 * k;
             if (h < H) {
 #pragma unroll
-                for (int i = 0; i < I; ++i) w[i * H + h] = w1[k][i];
+                for (int i = 0; i < I; ++i) w[i * H + h] = w1[i][k];
 #pragma unroll
-                for (int o = 0; o < O; ++o) w[I * H + h * O + o] = w2[k][o];
+                for (int o = 0; o < O; ++o) w[I * H + h * O + o] = w2[o][k];
                 w[I * H + H * O + h] = b1[k];
             }
         }
@@ -85,90 +156,152 @@ struct SgdWarp {
             for (int o = 0; o < O; ++o) w[I * H + H * O + H + o] = b2[o];
         }
     }
-
-    // Pre-activation of the hidden units for row x with the CURRENT weights: z = x.W1 - B1 (R:52).
-    __device__ __forceinline__ void preact(const float (&x)[IP], float (&z)[HPL]) const {
+    // derived copy of the output layer for the next row; off the dependent chain
+    __device__ __forceinline__ void refresh(int) {
+        if constexpr (!GATHER) {
 #pragma unroll
-        for (int k = 0; k < HPL; ++k) {
-            float t = -b1[k];                                   // bias is SUBTRACTED (R:52)
-#pragma unroll
-            for (int i = 0; i < I; ++i) t = fmaf(x[i], w1[k][i], t);
-            z[k] = t;
+            for (int o = 0; o < O; ++o) vmul_s<HPL>(w2q[o], w2[o], kFix);
         }
+    }
+    // Range guard of the fixed-point sum for the next `rows` rows (warp-uniform).  |p_lane[o]| <=
+    // sum_k |W2[k][o]| because hid is in [0,1], and one row moves each |W2| entry by at most
+    // lr * |out_delta| * hid <= lr / 4.  All lanes below 15.9 keeps both the per-lane conversion and
+    // the 32-lane integer sum inside int32 at 2^-22 resolution; otherwise the SHFL butterfly is used.
+    __device__ __forceinline__ bool guard(int rows, float lr) const {
+        if constexpr (GATHER) return true;
+        float m = 0.0f;
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float a = 0.0f;
+#pragma unroll
+            for (int k = 0; k < HPL; ++k) a += fabsf(w2[o][k]);
+            m = fmaxf(m, a);
+        }
+        m += (float)(rows * HPL) * 0.25f * fabsf(lr);
+        return __reduce_max_sync(0xffffffffu, __float_as_uint(m)) < 0x417e6666u;   // 15.9f; NaN bits compare high
+    }
+
+    // Scaled pre-activation of the hidden units for row x with the CURRENT weights:
+    // zs = -log2(e) * (x.W1 - B1)   (bias is SUBTRACTED, R:52)
+    __device__ __forceinline__ void preact(const float (&x)[IP], float (&zs)[HPL]) const {
+        float t[HPL];
+        vmul_s<HPL>(t, b1, -1.0f);
+#pragma unroll
+        for (int i = 0; i < I; ++i) vfma_s<HPL>(t, w1[i], x[i], t);
+        vmul_s<HPL>(zs, t, -kL2E);
     }
 
     // One row: ForwardPass (R:51-55) then BackwardPass (R:57-78 / C:72-82).
-    //   z      in:  pre-activations of THIS row (all earlier updates included)
-    //          out: pre-activations of the NEXT row xn, obtained off the critical path as
-    //               xn.W1_old - B1_old (computed while the output-layer reduction is in flight)
-    //               + lr*hid_delta * (xn.x + 1)   (the rank-1 update W1 += lr*hd (x) x, B1 -= lr*hd)
-    //   so the dependent chain from hid_delta to the next row's sigmoid is one FFMA instead of
-    //   an update FFMA plus an I-long dot product.
-    __device__ __forceinline__ void row(const float (&x)[IP], float yv, const float (&xn)[IP], float (&z)[HPL],
+    //   zs     in:  scaled pre-activations of THIS row (all earlier updates included)
+    //          out: scaled pre-activations of the NEXT row xn = stale value (xn.W1_old - B1_old, computed
+    //               while the output-layer reduction is in flight) + the effect of this row's rank-1
+    //               update W1 += lr*hd (x) x, B1 -= lr*hd, i.e. lr*hd*(xn.x + 1), folded into one FFMA
+    //               per output on the chain.
+    //   FIX: the output-layer sum goes through the fixed-point REDUX (the caller checked guard());
+    //   a template parameter rather than a branch so that a row is ONE basic block the scheduler
+    //   can interleave freely (no branch in the shadow of the REDUX).
+    template <bool FIX>
+    __device__ __forceinline__ void row(const float (&x)[IP], float yv, const float (&xn)[IP], float (&zs)[HPL],
                                         float lr, int lane) {
         float hid[HPL];
-        float p[O];
+        {
+            float e[HPL], d[HPL];
 #pragma unroll
-        for (int o = 0; o < O; ++o) p[o] = 0.0f;
+            for (int k = 0; k < HPL; ++k) e[k] = ex2_ftz(zs[k]);
+            vadd_s<HPL>(d, e, 1.0f);
 #pragma unroll
-        for (int k = 0; k < HPL; ++k) {
-            hid[k] = (lane + 32 * k < H) ? sigmoid_fast(z[k]) : 0.0f;
-            if constexpr (!GATHER) {
+            for (int k = 0; k < HPL; ++k) hid[k] = rcp_ftz(d[k]);                 // R:52-53
+        }
+        // ---- output layer (chain)
+        float t[O];
+        float g_all[HG];
+        if constexpr (GATHER) {
 #pragma unroll
-                for (int o = 0; o < O; ++o) p[o] = fmaf(hid[k], w2[k][o], p[o]);
+            for (int h = 0; h < H; ++h) g_all[h] = __shfl_sync(0xffffffffu, hid[0], h);
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                float a0 = b2l[o], a1 = 0.0f;                // two partial sums: shorter dependent chain
+#pragma unroll
+                for (int h = 0; h + 1 < H; h += 2) {
+                    a0 = fmaf(g_all[h], -kL2E * w2f[h][o], a0);
+                    a1 = fmaf(g_all[h + 1], -kL2E * w2f[h + 1][o], a1);
+                }
+                if (H & 1) a0 = fmaf(g_all[H - 1], -kL2E * w2f[H - 1][o], a0);
+                t[o] = a0 + a1;
+            }
+        } else {
+            float p[O];
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                float a0 = hid[0] * w2q[o][0];
+#pragma unroll
+                for (int k = 1; k < HPL; ++k) a0 = fmaf(hid[k], w2q[o][k], a0);
+                p[o] = a0;
+            }
+            if constexpr (FIX) {
+                int s[O];
+#pragma unroll
+                for (int o = 0; o < O; ++o) s[o] = __reduce_add_sync(0xffffffffu, __float2int_rn(p[o]));
+#pragma unroll
+                for (int o = 0; o < O; ++o) t[o] = fmaf((float)s[o], -kL2E * kInvFix, b2l[o]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < O; ++o) t[o] = fmaf(warp_sum_shfl(p[o], 5), -kL2E * kInvFix, b2l[o]);
             }
         }
-        // independent of the reduction below: stale pre-activation of the next row and xn.x + 1
+        // ---- independent of the chain: stale scaled pre-activation of the next row, xn.x + 1,
+        //      hid (1 - hid) W2 with the PRE-update W2 (R:59)
         float zn[HPL];
         preact(xn, zn);
         float c = 1.0f;
 #pragma unroll
         for (int i = 0; i < I; ++i) c = fmaf(xn[i], x[i], c);
-        float g[HG];
-        if constexpr (GATHER) {
+        const float ccl = (-kL2E * lr) * c;
+        float g[HPL], nh[HPL];
+        vmul_s<HPL>(nh, hid, -1.0f);
+        vfma<HPL>(g, nh, hid, hid);                                               // hid - hid^2
+        float gw[O][HPL], ks[O][HPL];
 #pragma unroll
-            for (int h = 0; h < H; ++h) g[h] = __shfl_sync(0xffffffffu, hid[0], h);
-#pragma unroll
-            for (int o = 0; o < O; ++o) {
-                float a0 = 0.0f, a1 = 0.0f;                  // two partial sums: shorter dependent chain
-#pragma unroll
-                for (int h = 0; h + 1 < H; h += 2) { a0 = fmaf(g[h], w2f[h][o], a0); a1 = fmaf(g[h + 1], w2f[h + 1][o], a1); }
-                if (H & 1) a0 = fmaf(g[H - 1], w2f[H - 1][o], a0);
-                p[o] = a0 + a1;
-            }
+        for (int o = 0; o < O; ++o) {
+            vmul<HPL>(gw[o], g, w2[o]);
+            vmul_s<HPL>(ks[o], gw[o], ccl);
         }
-        if constexpr (!GATHER) warp_sum_vec<O>(p, LEVELS);
+        // ---- output sigmoid and delta (chain)
         float od[O];
 #pragma unroll
         for (int o = 0; o < O; ++o) {
-            const float zo = p[o] - b2[o];
-            const float out = sigmoid_fast(zo);                                   // R:54-55
-            float d;
-            if constexpr (TASK == kTaskCls) d = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75 one-hot
-            else d = yv;                                                          // O == 1 (R:132)
-            od[o] = (d - out) * (out * (1.0f - out));                             // R:58
+            const float out = rcp_ftz(1.0f + ex2_ftz(t[o]));                       // R:54-55
+            float dd;
+            if constexpr (TASK == kTaskCls) dd = ((int)yv == o) ? 1.0f : 0.0f;      // C:73-75 one-hot
+            else dd = yv;                                                          // O == 1 (R:132)
+            od[o] = (dd - out) * fmaf(-out, out, out);                             // R:58
         }
-        if constexpr (GATHER) {                                                   // replicated W2 follows R:67-69 too
+        // ---- next row's scaled pre-activation (chain: O FFMAs)
 #pragma unroll
-            for (int h = 0; h < H; ++h)
+        for (int o = 0; o < O; ++o) vfma_s<HPL>(zn, ks[o], od[o], zn);
 #pragma unroll
-                for (int o = 0; o < O; ++o) w2f[h][o] = fmaf(lr * od[o], g[h], w2f[h][o]);
+        for (int k = 0; k < HPL; ++k) zs[k] = zn[k];
+        // ---- updates (off the chain)
+        float lh[HPL];
+        vmul_s<HPL>(lh, gw[0], od[0]);
+#pragma unroll
+        for (int o = 1; o < O; ++o) vfma_s<HPL>(lh, gw[o], od[o], lh);
+        vmul_s<HPL>(lh, lh, lr);                                                   // lr * hid_delta (R:59)
+#pragma unroll
+        for (int i = 0; i < I; ++i) vfma_s<HPL>(w1[i], lh, x[i], w1[i]);           // R:74-76
+        vfma_s<HPL>(b1, lh, -1.0f, b1);                                            // R:77-78
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            const float lo = lr * od[o];
+            vfma_s<HPL>(w2[o], hid, lo, w2[o]);                                    // R:67-69
+            b2[o] -= lo;                                                           // R:70-71
+            b2l[o] = kL2E * b2[o];
+            if constexpr (GATHER) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) w2f[h][o] = fmaf(lo, g_all[h], w2f[h][o]);
+            }
         }
-#pragma unroll
-        for (int k = 0; k < HPL; ++k) {
-            float s = 0.0f;
-#pragma unroll
-            for (int o = 0; o < O; ++o) s = fmaf(od[o], w2[k][o], s);             // pre-update W2 (R:59)
-            const float lh = lr * (s * (hid[k] * (1.0f - hid[k])));
-            z[k] = fmaf(lh, c, zn[k]);
-#pragma unroll
-            for (int o = 0; o < O; ++o) w2[k][o] = fmaf(lr * od[o], hid[k], w2[k][o]);   // R:67-69
-#pragma unroll
-            for (int i = 0; i < I; ++i) w1[k][i] = fmaf(lh, x[i], w1[k][i]);      // R:74-76
-            b1[k] -= lh;                                                          // R:77-78
-        }
-#pragma unroll
-        for (int o = 0; o < O; ++o) b2[o] -= lr * od[o];                          // R:70-71
+        refresh(lane);
     }
 };
 
@@ -195,86 +328,104 @@ struct SgdStream {
     uint32_t parity0, parity1;
 };
 
-// Rows [0, count) of a shared-memory tile whose look-ahead row (r+1) lies in the same tile.
-// (xc, yc) = the row about to be processed (already in registers), z = its pre-activations.
-template <int I, int H, int O, int TASK>
-__device__ __forceinline__ void sgd_rows(SgdWarp<I, H, O, TASK> &net, uint32_t xa, uint32_t ya, int count,
-                                         float (&xc)[IPad<I>::value], float &yc,
-                                         float (&z)[SgdWarp<I, H, O, TASK>::HPL], float lr, int lane) {
-    constexpr int IP = IPad<I>::value;
-    for (int r = 0; r < count; ++r) {
-        float xn[IP];
-        lds_row<IP>(xa + (uint32_t)(r + 1) * IP * 4u, xn);
-        const float yn = lds_f32(ya + (uint32_t)(r + 1) * 4u);
-        net.row(xc, yc, xn, z, lr, lane);
-#pragma unroll
-        for (int i = 0; i < IP; ++i) xc[i] = xn[i];
-        yc = yn;
-    }
-}
-
-// One epoch of online SGD over the training rows in order.  Called by warp 0 only.
+// One epoch of online SGD over the training rows in order.  Called by the serial warp only.
+//
+// Row r needs row r+1 (look-ahead pre-activation) in registers when it starts, so row r+2 is
+// fetched from shared memory at the top of row r: three register buffers rotate A -> B -> C and
+// the hot loop is unrolled by three (no register moves, and the scheduler sees the loop-carried
+// chain across rows).  Streamed training sets (two 128-row TMA tiles) cut the epoch into chunks at
+// the rows where something else has to happen: r = 128k (refill the tile buffer that was just
+// vacated) and r = 128k + 126 (the fetch of row r+2 crosses into the next tile: wait for it).
 template <int I, int H, int O, int TASK>
 __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const DataView &d, bool staged,
                                          float lr, SgdStream &st) {
     constexpr int IP = IPad<I>::value;
+    constexpr uint32_t RB = IP * 4u;
     const int lane = threadIdx.x & 31;
+    const int n = d.n;
     SgdWarp<I, H, O, TASK> net;
     net.load(w_in, lane);
-    float xc[IP], yc, xz[IP];
-    float z[SgdWarp<I, H, O, TASK>::HPL];
-#pragma unroll
-    for (int i = 0; i < IP; ++i) xz[i] = 0.0f;
-    if (staged) {
-        const uint32_t xa = smem_u32(d.x), ya = smem_u32(d.y);
-        lds_row<IP>(xa, xc);
-        yc = lds_f32(ya);
-        net.preact(xc, z);
-        sgd_rows<I, H, O, TASK>(net, xa, ya, d.n - 1, xc, yc, z, lr, lane);
-        net.row(xc, yc, xz, z, lr, lane);                       // last row: nothing to look ahead to
-    } else {
-        const int ntiles = (d.n + kTileRows - 1) / kTileRows;
-        auto issue = [&](int t) {
-            const int rows = min(kTileRows, d.n - t * kTileRows);
-            const uint32_t bx = (uint32_t)rows * IP * 4u;
-            const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;   // y is allocated padded to 4 floats
-            if (lane == 0) {
-                uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
-                mbar_arrive_expect_tx(bar, bx + by);
-                tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
-                tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    const uint32_t sx = smem_u32(d.x), sy = smem_u32(d.y);                       // staged copy
+    const uint32_t tx0 = smem_u32(st.tile_x0), tx1 = smem_u32(st.tile_x1);       // streamed tiles
+    const uint32_t ty0 = smem_u32(st.tile_y0), ty1 = smem_u32(st.tile_y1);
+    auto xaddr = [&](int r) -> uint32_t {
+        return staged ? sx + (uint32_t)r * RB : (((r / kTileRows) & 1) ? tx1 : tx0) + (uint32_t)(r % kTileRows) * RB;
+    };
+    auto yaddr = [&](int r) -> uint32_t {
+        return staged ? sy + (uint32_t)r * 4u : (((r / kTileRows) & 1) ? ty1 : ty0) + (uint32_t)(r % kTileRows) * 4u;
+    };
+    auto issue = [&](int t) {
+        const int rows = min(kTileRows, n - t * kTileRows);
+        const uint32_t bx = (uint32_t)rows * RB;
+        const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;   // y is allocated padded to 4 floats
+        if (lane == 0) {
+            uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
+            mbar_arrive_expect_tx(bar, bx + by);
+            tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
+            tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
+        }
+    };
+    auto wait = [&](int t) {
+        if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
+        else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
+    };
+    if (!staged) { issue(0); wait(0); }
+    float A[IP], B[IP], C[IP], ya, yb, yc;
+    float zs[SgdWarp<I, H, O, TASK>::HPL];
+    lds_row<IP>(xaddr(0), A);
+    ya = lds_f32(yaddr(0));
+    lds_row<IP>(xaddr(min(1, n - 1)), B);
+    yb = lds_f32(yaddr(min(1, n - 1)));
+    net.preact(A, zs);
+    int r = 0;
+    while (r < n) {
+        int e = n;
+        if (!staged) {
+            const int k = r % kTileRows;
+            if (k == 0) {                        // every lane is past the previous tile: refill its buffer
+                __syncwarp();
+                if (r / kTileRows + 1 < ntiles) issue(r / kTileRows + 1);
             }
-        };
-        auto wait = [&](int t) {
-            if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
-            else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
-        };
-        issue(0);
-        wait(0);
-        lds_row<IP>(smem_u32(st.tile_x0), xc);
-        yc = lds_f32(smem_u32(st.tile_y0));
-        net.preact(xc, z);
-        for (int t = 0; t < ntiles; ++t) {
-            // tile t is resident; tile t+1 streams into the other buffer (free: all lanes are past
-            // tile t-1 and past the look-ahead read of this tile's first row) while tile t is consumed
-            __syncwarp();
-            const bool more = t + 1 < ntiles;
-            if (more) issue(t + 1);
-            const int rows = min(kTileRows, d.n - t * kTileRows);
-            sgd_rows<I, H, O, TASK>(net, smem_u32((t & 1) ? st.tile_x1 : st.tile_x0),
-                                    smem_u32((t & 1) ? st.tile_y1 : st.tile_y0), rows - 1, xc, yc, z, lr, lane);
-            if (more) {                                          // the tile's last row looks ahead into tile t+1
-                wait(t + 1);
-                float xn[IP];
-                lds_row<IP>(smem_u32((t & 1) ? st.tile_x0 : st.tile_x1), xn);
-                const float yn = lds_f32(smem_u32((t & 1) ? st.tile_y0 : st.tile_y1));
-                net.row(xc, yc, xn, z, lr, lane);
-#pragma unroll
-                for (int i = 0; i < IP; ++i) xc[i] = xn[i];
-                yc = yn;
+            if (k == kTileRows - 2 && r + 2 < n) wait((r + 2) / kTileRows);
+            e = min(n, r - k + (k < kTileRows - 2 ? kTileRows - 2 : kTileRows));
+        }
+        int cnt = e - r;
+        uint32_t px = xaddr(min(r + 2, n - 1)), py = yaddr(min(r + 2, n - 1));
+        // rows r, r+1, r+2 per iteration; fetches r+2, r+3, r+4 (same tile by construction).  The guard
+        // of the NEXT iteration is evaluated at the top of this one (6 rows of margin), so the branch
+        // that selects the variant never waits for the CREDUX.
+        bool ok = net.guard(3, lr);
+        while (cnt >= 3 && r + 4 < n) {
+            const bool ok_next = net.guard(6, lr);
+            if (ok) {
+                lds_row<IP>(px, C); yc = lds_f32(py);
+                net.template row<true>(A, ya, B, zs, lr, lane);
+                lds_row<IP>(px + RB, A); ya = lds_f32(py + 4u);
+                net.template row<true>(B, yb, C, zs, lr, lane);
+                lds_row<IP>(px + 2u * RB, B); yb = lds_f32(py + 8u);
+                net.template row<true>(C, yc, A, zs, lr, lane);
             } else {
-                net.row(xc, yc, xz, z, lr, lane);
+                lds_row<IP>(px, C); yc = lds_f32(py);
+                net.template row<false>(A, ya, B, zs, lr, lane);
+                lds_row<IP>(px + RB, A); ya = lds_f32(py + 4u);
+                net.template row<false>(B, yb, C, zs, lr, lane);
+                lds_row<IP>(px + 2u * RB, B); yb = lds_f32(py + 8u);
+                net.template row<false>(C, yc, A, zs, lr, lane);
             }
+            ok = ok_next;
+            px += 3u * RB; py += 12u;
+            r += 3; cnt -= 3;
+        }
+        while (cnt > 0) {
+            const int q = min(r + 2, n - 1);     // past the end: any finite row (the look-ahead result is unused)
+            lds_row<IP>(xaddr(q), C); yc = lds_f32(yaddr(q));
+            if (net.guard(1, lr)) net.template row<true>(A, ya, B, zs, lr, lane);
+            else net.template row<false>(A, ya, B, zs, lr, lane);
+#pragma unroll
+            for (int i = 0; i < IP; ++i) { A[i] = B[i]; B[i] = C[i]; }
+            ya = yb; yb = yc;
+            ++r; --cnt;
         }
     }
     net.store(w_out, lane);
@@ -597,6 +748,196 @@ __device__ __forceinline__ void lik_rows(const float *__restrict__ w, const Data
 }
 
 // ==========================================================================================
+// K1 (chain kernel): the same pass with the instruction count cut down.  ncu on the random-walk
+// step of 4-64-1 showed 12.5 issued instructions per hidden-unit sigmoid with the issue slots 64 %
+// busy, so the pass is rewritten around a per-proposal "likelihood layout" of the weights in shared
+// memory, one 16-byte-aligned record per hidden unit:
+//     [ -log2(e) W1[0..I)[h],  log2(e) B1[h],  -log2(e) W2[h][0..O),  pad ]
+// (one or two LDS.128 per hidden unit instead of I + O + 1 scalar loads, no scaling multiplies in
+// the loop, pre-activations born in the ex2 domain), rows processed in PAIRS through the packed
+// FFMA2 / FMUL2 / FADD2 instructions, and one MUFU.RCP per four sigmoids (sigmoid_group).  For
+// 4-64-1 that is 29 instructions and 5 MUFU per 4 rows x 1 hidden unit (was 50 and 5).
+// ==========================================================================================
+template <int I, int O>
+struct LikLayout {
+    static constexpr int LW = (I + 1 + O + 3) & ~3;
+};
+
+// element j of the weight vector (layout a1) with value v -> its slot in the likelihood layout
+template <int I, int H, int O>
+__device__ __forceinline__ void lik_scatter(float *lw, int j, float v) {
+    constexpr int LW = LikLayout<I, O>::LW;
+    constexpr int oW2 = I * H, oB1 = I * H + H * O, oB2 = I * H + H * O + H;
+    if (j < oW2) { const int i = j / H, h = j - i * H; lw[h * LW + i] = -kL2E * v; }
+    else if (j < oB1) { const int q = j - oW2, h = q / O, o = q - h * O; lw[h * LW + I + 1 + o] = -kL2E * v; }
+    else if (j < oB2) { lw[(j - oB1) * LW + I] = kL2E * v; }
+}
+template <int I, int H, int O>
+__device__ __forceinline__ void lik_prepare(float *lw, const float *w, int t, int nt) {
+    for (int j = t; j < I * H + H * O + H; j += nt) lik_scatter<I, H, O>(lw, j, w[j]);
+}
+
+// Packed pairs kept in 64-bit registers for the whole hidden-unit loop (building the pair from two
+// scalar registers costs a MOV each time, which is what the loop is trying to get rid of).
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Sigmoids of NP row pairs from their ex2-domain pre-activations (sigmoid(z), zs = -log2(e) z):
+// one MUFU.EX2 each, ONE MUFU.RCP per four (per two when NP == 1).
+template <int NP>
+__device__ __forceinline__ void sigmoid_pairs(const f2_t (&zs)[NP], f2_t (&s)[NP]) {
+    constexpr float kClamp = 30.0f;     // the product of up to four denominators must not overflow
+    f2_t d[NP];
+    const f2_t one = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        float a, b;
+        unpack2(zs[j], a, b);
+        d[j] = add2(pack2(ex2_ftz(fminf(a, kClamp)), ex2_ftz(fminf(b, kClamp))), one);
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < NP; j += 2) {
+        float pa, pb;
+        unpack2(mul2(d[j], d[j + 1]), pa, pb);             // {d0 d2, d1 d3}
+        const float r = rcp_ftz(pa * pb);
+        const f2_t qs = pack2(r * pb, r * pa);
+        s[j] = mul2(qs, d[j + 1]);                         // {1/d0, 1/d1}
+        s[j + 1] = mul2(qs, d[j]);                         // {1/d2, 1/d3}
+    }
+    if (NP & 1) {
+        float a, b;
+        unpack2(d[NP - 1], a, b);
+        const float r = rcp_ftz(a * b);
+        s[NP - 1] = pack2(r * b, r * a);
+    }
+}
+
+template <int I, int H, int O, int TASK, int RB>
+__device__ __forceinline__ void lik_fast_impl(const float *__restrict__ lw, const float *__restrict__ w,
+                                              const DataView &d, int t, int nt, double &s0, double &s1, int &correct) {
+    constexpr int IP = IPad<I>::value;
+    constexpr int LW = LikLayout<I, O>::LW;
+    constexpr int oB2 = I * H + H * O + H;
+    constexpr int HU = (H <= 16) ? H : 4;
+    constexpr int NP = RB / 2;           // row pairs (RB == 1: scalar path)
+    for (int r0 = t * RB; r0 < d.n; r0 += nt * RB) {
+        float acc[O][RB];
+        if constexpr (RB == 1) {
+            float x[1][IP];
+            {
+                const float4 *xr = reinterpret_cast<const float4 *>(d.x + (size_t)r0 * IP);
+#pragma unroll
+                for (int q = 0; q < IP / 4; ++q) {
+                    const float4 v = xr[q];
+                    x[0][4 * q] = v.x; x[0][4 * q + 1] = v.y; x[0][4 * q + 2] = v.z; x[0][4 * q + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < O; ++o) acc[o][0] = kL2E * w[oB2 + o];
+#pragma unroll HU
+            for (int h = 0; h < H; ++h) {
+                float wl[LW];
+                const float4 *wr = reinterpret_cast<const float4 *>(lw + h * LW);
+#pragma unroll
+                for (int q = 0; q < LW / 4; ++q) {
+                    const float4 v = wr[q];
+                    wl[4 * q] = v.x; wl[4 * q + 1] = v.y; wl[4 * q + 2] = v.z; wl[4 * q + 3] = v.w;
+                }
+                float zs = wl[I];
+#pragma unroll
+                for (int i = 0; i < I; ++i) zs = fmaf(x[0][i], wl[i], zs);
+                const float hid = rcp_ftz(1.0f + ex2_ftz(zs));
+#pragma unroll
+                for (int o = 0; o < O; ++o) acc[o][0] = fmaf(hid, wl[I + 1 + o], acc[o][0]);
+            }
+        } else {
+            // scalar loads (once per row block) so that each pair is born in an aligned register pair
+            f2_t x2[NP][I], a2[NP][O];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const float *xa = d.x + (size_t)min(r0 + 2 * j, d.n - 1) * IP;
+                const float *xb = d.x + (size_t)min(r0 + 2 * j + 1, d.n - 1) * IP;
+#pragma unroll
+                for (int i = 0; i < I; ++i) x2[j][i] = pack2(xa[i], xb[i]);
+#pragma unroll
+                for (int o = 0; o < O; ++o) { const float b2l = kL2E * w[oB2 + o]; a2[j][o] = pack2(b2l, b2l); }
+            }
+#pragma unroll HU
+            for (int h = 0; h < H; ++h) {
+                float wl[LW];
+                const float4 *wr = reinterpret_cast<const float4 *>(lw + h * LW);
+#pragma unroll
+                for (int q = 0; q < LW / 4; ++q) {
+                    const float4 v = wr[q];
+                    wl[4 * q] = v.x; wl[4 * q + 1] = v.y; wl[4 * q + 2] = v.z; wl[4 * q + 3] = v.w;
+                }
+                f2_t zs[NP], hid[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    zs[j] = pack2(wl[I], wl[I]);
+#pragma unroll
+                    for (int i = 0; i < I; ++i) zs[j] = fma2(x2[j][i], pack2(wl[i], wl[i]), zs[j]);
+                }
+                sigmoid_pairs<NP>(zs, hid);
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+#pragma unroll
+                    for (int o = 0; o < O; ++o) a2[j][o] = fma2(hid[j], pack2(wl[I + 1 + o], wl[I + 1 + o]), a2[j][o]);
+            }
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+#pragma unroll
+                for (int o = 0; o < O; ++o) unpack2(a2[j][o], acc[o][2 * j], acc[o][2 * j + 1]);
+        }
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            const int r = r0 + b;
+            if (r < d.n) {
+                const float yv = d.y[r];
+                if constexpr (TASK == kTaskReg) {
+                    const float fx = rcp_ftz(1.0f + ex2_ftz(acc[0][b]));          // R:55, R:132
+                    const float e = yv - fx;
+                    s0 += (double)(e * e);
+                } else {
+                    float out[O];
+                    int am = 0;
+                    float se = 0.0f;
+#pragma unroll
+                    for (int o = 0; o < O; ++o) {
+                        out[o] = rcp_ftz(1.0f + ex2_ftz(acc[o][b]));
+                        se += expf(out[o]);            // C:108-110
+                    }
+#pragma unroll
+                    for (int o = 1; o < O; ++o) am = (out[o] > out[am]) ? o : am; // np.argmax: first max
+                    const int lab = (int)yv;
+                    float ol = out[0];
+#pragma unroll
+                    for (int o = 1; o < O; ++o) ol = (o == lab) ? out[o] : ol;
+                    s0 += (double)(ol - logf(se));
+                    const float e = (float)am - yv;
+                    s1 += (double)(e * e);
+                    correct += ((float)am == yv) ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
+template <int I, int H, int O, int TASK>
+__device__ __forceinline__ void lik_fast(const float *__restrict__ lw, const float *__restrict__ w, const DataView &d,
+                                         int t, int nt, double &s0, double &s1, int &correct) {
+    // row blocking only pays when every thread has several rows and the registers allow it
+    constexpr int RBMAX = (I * 4 + O * 4 <= 96) ? 4 : ((I * 2 + O * 2 <= 96) ? 2 : 1);
+    if (RBMAX >= 4 && d.n >= 8 * nt) lik_fast_impl<I, H, O, TASK, RBMAX>(lw, w, d, t, nt, s0, s1, correct);
+    else if (RBMAX >= 2 && d.n >= 4 * nt) lik_fast_impl<I, H, O, TASK, 2>(lw, w, d, t, nt, s0, s1, correct);
+    else lik_fast_impl<I, H, O, TASK, 1>(lw, w, d, t, nt, s0, s1, correct);
+}
+
+// ==========================================================================================
 // K3 + K4: the persistent chain kernel
 // ==========================================================================================
 struct ChainParams {
@@ -640,6 +981,7 @@ struct ChainParams {
     int max_rounds;
     int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
     int P;
+    int lik_team_warps;            // warps per CTA that evaluate the likelihood while the serial warp runs (0 = all)
     int *smsp_load;                // [num_SMs] ticket counter used to spread serial (SGD) warps over the SM sub-partitions
 };
 
@@ -660,16 +1002,17 @@ struct NetSizes {
 // dynamic shared memory layout (floats unless noted); host computes the same with chain_smem_bytes()
 struct ChainSmem {
     int P4;          // P rounded up to 4
-    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_red, off_bar, off_tiles, off_sweep, off_team, off_stage, total;
+    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_lw, off_red, off_bar, off_tiles, off_sweep, off_team, off_stage, total;
 };
 __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
-                                                       int n_test, int team_floats = 0) {
+                                                       int n_test, int team_floats = 0, int lik_floats = 0) {
     ChainSmem L;
     L.P4 = (P + 3) & ~3;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
     L.off_w = take(L.P4 * 4); L.off_prop = take(L.P4 * 4); L.off_gd = take(L.P4 * 4);
     L.off_pgd = take(L.P4 * 4); L.off_last = take(L.P4 * 4);
+    L.off_lw = take((size_t)lik_floats * 4);   // likelihood layout of the proposal (LikLayout)
     L.off_red = take((size_t)8 * (nt / 32) * 8);
     L.off_bar = take(8 * 4);
     L.off_tiles = take(staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4));
@@ -751,7 +1094,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool TEAM = UseSgdTeam<H>::value;
-    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? H + O : 0);
+    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? H + O : 0,
+                                          H * LikLayout<I, O>::LW);
+    float *s_lw = reinterpret_cast<float *>(smem_raw + L.off_lw);
     float *s_team_hid = reinterpret_cast<float *>(smem_raw + L.off_team);
     float *s_team_od = s_team_hid + H;
     float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
@@ -858,7 +1203,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     double s[2] = {0.0, 0.0};
                     double dummy = 0.0;
                     int c0 = 0;
-                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_w, train, tid, NT, s[0], dummy, c0);
+                    lik_prepare<I, H, O>(s_lw, s_w, tid, NT);
+                    __syncthreads();
+                    lik_fast<I, H, O, TASK>(s_lw, s_w, train, tid, NT, s[0], dummy, c0);
                     block_sum<2, NT>(s, s_red);
                     if constexpr (TASK == kTaskReg)
                         lik = (-0.5 * train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / adapt;
@@ -890,7 +1237,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     const float *base = lg ? s_gd : s_w;
                     if (p.replay) {
                         const float *zz = p.z + ((size_t)r * p.replay_n + di) * P;
-                        for (int j = tid; j < P; j += NT) s_prop[j] = fmaf(p.step_w, zz[j], base[j]);
+                        for (int j = tid; j < P; j += NT) {
+                            const float v = fmaf(p.step_w, zz[j], base[j]);
+                            s_prop[j] = v;
+                            lik_scatter<I, H, O>(s_lw, j, v);
+                        }
                     } else {
                         for (int b = tid; b < (P + 3) / 4; b += NT) {
                             float z4[4];
@@ -898,7 +1249,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int j = 4 * b + k;
-                                if (j < P) s_prop[j] = fmaf(p.step_w, z4[k], base[j]);
+                                if (j < P) {
+                                    const float v = fmaf(p.step_w, z4[k], base[j]);
+                                    s_prop[j] = v;
+                                    lik_scatter<I, H, O>(s_lw, j, v);
+                                }
                             }
                         }
                     }
@@ -910,12 +1265,17 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[k] = 0.0;
                 int c_tr = 0, c_te = 0;
-                if (lg && NW > 1 && !TEAM) {
+                if (lg && NW > 1 && !TEAM && p.lik_team_warps >= 0) {
                     if (is_sgd_warp) {
                         sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
-                    } else {
-                        lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, train, lik_tid, NT - 32, s[0], s[1], c_tr);
-                        lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, test, lik_tid, NT - 32, s[2], s[3], c_te);
+                    } else if (p.lik_team_warps <= 0 || lik_tid < 32 * p.lik_team_warps) {
+                        // The serial warp is latency-bound and has no issue priority: every additional
+                        // ready warp on its sub-partition delays each of its dependent instructions.
+                        // When many temperatures share an SM the likelihood (which has the whole SGD
+                        // epoch to finish) is therefore left to `lik_team_warps` warps per CTA.
+                        const int team = p.lik_team_warps <= 0 ? NT - 32 : 32 * p.lik_team_warps;
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, train, lik_tid, team, s[0], s[1], c_tr);
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, test, lik_tid, team, s[2], s[3], c_te);
                     }
                 } else {
                     if (lg) {
@@ -923,8 +1283,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                         else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
-                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, train, tid, NT, s[0], s[1], c_tr);
-                    lik_rows<I, H, O, TASK, kPreciseLik, false>(s_prop, test, tid, NT, s[2], s[3], c_te);
+                    lik_fast<I, H, O, TASK>(s_lw, s_prop, train, tid, NT, s[0], s[1], c_tr);
+                    lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, s[2], s[3], c_te);
                 }
                 __syncthreads();
                 // ---- reductions: likelihood sums, |w_prop|^2 (prior), Langevin asymmetry norms
