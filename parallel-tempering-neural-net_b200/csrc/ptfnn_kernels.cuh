@@ -36,7 +36,9 @@ constexpr bool kPreciseLik = false;  // rows per TMA tile when the training set 
 // The recurrence is latency-bound (one dependent chain per row) and the warp issues in order, so
 // both the LENGTH of the chain and the instruction COUNT per row matter.  Per row the chain is
 //     EX2 -> FADD -> RCP            hidden sigmoid, pre-activation kept pre-multiplied by -log2(e)
-//     -> FMUL/FFMA -> F2I -> REDUX  output-layer sum in 2^-22 fixed point on the integer REDUX unit
+//     -> FFMA(s) -> REDUX -> IADD   output-layer sum in block fixed point on the integer REDUX unit: the
+//        lane's partial sum is accumulated ON TOP of the magic constant 1.5 * 2^23, so its float bit
+//        pattern already is (constant + integer) and no F2I (22 cycles) is needed
 //        (H <= 8: SHFL all-gather + local dot product with a replicated, pre-scaled W2 instead)
 //     -> I2F -> FFMA                un-scale, subtract B2 and multiply by -log2(e) in ONE FFMA
 //     -> EX2 -> FADD -> RCP         output sigmoid
@@ -49,8 +51,9 @@ constexpr bool kPreciseLik = false;  // rows per TMA tile when the training set 
 // instructions of sm_100 (two fp32 operations per issue slot).
 // ==========================================================================================
 constexpr float kL2E = 1.4426950408889634f;
-constexpr float kFix = 4194304.0f;               // 2^22
-constexpr float kInvFix = 1.0f / 4194304.0f;
+constexpr float kMagic = 12582912.0f;            // 1.5 * 2^23: float(kMagic + v) has integer resolution for |v| < 2^22
+constexpr int kMagicSum32 = 0x68000000;          // 32 * bits(kMagic) mod 2^32: what 32 lanes of bare magic add up to
+constexpr int kGuardRows = 30;                   // rows covered by one choice of the fixed-point scale
 
 // elementwise helpers over the HPL hidden units of a lane; adjacent pairs go through f32x2
 template <int N>
@@ -112,7 +115,8 @@ struct SgdWarp {
     // hidden-unit index k is the FASTEST index so that pairs (k, k+1) feed the f32x2 instructions
     float w1[I][HPL], b1[HPL], w2[O][HPL], b2[O];
     float b2l[O];        // log2(e) * B2
-    float w2q[O][HPL];   // REDUX path: 2^22 * W2 (exact scaling)
+    float w2q[O][HPL];   // REDUX path: fscale * W2 (a power of two: exact)
+    float fscale, cdec;  // REDUX path: fixed-point scale 2^s and the decode factor -log2(e) 2^-s
     float w2f[HG][O];    // GATHER: full W2, identical in every lane (same update, bit for bit)
 
     // weight vector layout a1 (R:80-90): [W1 (I x H), W2 (H x O), B1 (H), B2 (O)]
@@ -137,6 +141,7 @@ struct SgdWarp {
 #pragma unroll
                 for (int o = 0; o < O; ++o) w2f[h][o] = w[I * H + h * O + o];
         }
+        fscale = 1.0f; cdec = -kL2E;
         refresh(lane);
     }
     __device__ __forceinline__ void store(float *w, int lane) const {
@@ -160,14 +165,17 @@ struct SgdWarp {
     __device__ __forceinline__ void refresh(int) {
         if constexpr (!GATHER) {
 #pragma unroll
-            for (int o = 0; o < O; ++o) vmul_s<HPL>(w2q[o], w2[o], kFix);
+            for (int o = 0; o < O; ++o) vmul_s<HPL>(w2q[o], w2[o], fscale);
         }
     }
-    // Range guard of the fixed-point sum for the next `rows` rows (warp-uniform).  |p_lane[o]| <=
-    // sum_k |W2[k][o]| because hid is in [0,1], and one row moves each |W2| entry by at most
-    // lr * |out_delta| * hid <= lr / 4.  All lanes below 15.9 keeps both the per-lane conversion and
-    // the 32-lane integer sum inside int32 at 2^-22 resolution; otherwise the SHFL butterfly is used.
-    __device__ __forceinline__ bool guard(int rows, float lr) const {
+    // Chooses the fixed-point scale for the next `rows` rows (warp-uniform; one CREDUX, off the
+    // chain).  |p_lane[o]| <= m = sum_k |W2[k][o]| because hid is in [0,1], and one row moves each
+    // |W2| entry by at most lr * |out_delta| * hid <= lr / 4.  With 2^E > m the scale 2^(22-E) keeps
+    // |p_lane * scale| < 2^22, where kMagic + v is exact to the integer: the sum is taken with a
+    // resolution of 2^-22 relative to the binade of the largest lane bound (block fixed point, i.e.
+    // fp32-class accuracy), and 32 lanes of < 2^22 cannot overflow the int32 REDUX.  Returns false
+    // (use the SHFL butterfly) only for non-finite weights, so that NaN propagates as in the reference.
+    __device__ __forceinline__ bool set_scale(int rows, float lr) {
         if constexpr (GATHER) return true;
         float m = 0.0f;
 #pragma unroll
@@ -175,10 +183,18 @@ struct SgdWarp {
             float a = 0.0f;
 #pragma unroll
             for (int k = 0; k < HPL; ++k) a += fabsf(w2[o][k]);
-            m = fmaxf(m, a);
+            m = fmaxf(m, a);                                    // fmaxf drops NaN: checked separately below
+            m = (a != a) ? __int_as_float(0x7fc00000) : m;
         }
-        m += (float)(rows * HPL) * 0.25f * fabsf(lr);
-        return __reduce_max_sync(0xffffffffu, __float_as_uint(m)) < 0x417e6666u;   // 15.9f; NaN bits compare high
+        m = fmaxf(m + (float)(rows * HPL) * 0.25f * fabsf(lr), 9.765625e-4f);     // >= 2^-10: scale stays finite
+        const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // NaN / Inf bits compare high
+        const unsigned int ef = mb >> 23;                        // biased exponent of the bound, 2^(ef-127) <= m < 2^(ef-126)
+        const bool ok = ef < 200u;                               // finite and far from overflow
+        const unsigned int sf = ok ? 275u - ef : 127u;           // scale 2^(22 - (ef - 126))
+        fscale = __uint_as_float(sf << 23);
+        cdec = -kL2E * __uint_as_float((254u - sf) << 23);
+        refresh(0);
+        return ok;
     }
 
     // Scaled pre-activation of the hidden units for row x with the CURRENT weights:
@@ -197,7 +213,7 @@ struct SgdWarp {
     //               while the output-layer reduction is in flight) + the effect of this row's rank-1
     //               update W1 += lr*hd (x) x, B1 -= lr*hd, i.e. lr*hd*(xn.x + 1), folded into one FFMA
     //               per output on the chain.
-    //   FIX: the output-layer sum goes through the fixed-point REDUX (the caller checked guard());
+    //   FIX: the output-layer sum goes through the fixed-point REDUX (set_scale() returned true);
     //   a template parameter rather than a branch so that a row is ONE basic block the scheduler
     //   can interleave freely (no branch in the shadow of the REDUX).
     template <bool FIX>
@@ -230,23 +246,25 @@ struct SgdWarp {
                 t[o] = a0 + a1;
             }
         } else {
-            float p[O];
-#pragma unroll
-            for (int o = 0; o < O; ++o) {
-                float a0 = hid[0] * w2q[o][0];
-#pragma unroll
-                for (int k = 1; k < HPL; ++k) a0 = fmaf(hid[k], w2q[o][k], a0);
-                p[o] = a0;
-            }
             if constexpr (FIX) {
-                int s[O];
+                int sraw[O];
 #pragma unroll
-                for (int o = 0; o < O; ++o) s[o] = __reduce_add_sync(0xffffffffu, __float2int_rn(p[o]));
+                for (int o = 0; o < O; ++o) {
+                    float a0 = kMagic;                       // every partial lands on the integer grid
 #pragma unroll
-                for (int o = 0; o < O; ++o) t[o] = fmaf((float)s[o], -kL2E * kInvFix, b2l[o]);
+                    for (int k = 0; k < HPL; ++k) a0 = fmaf(hid[k], w2q[o][k], a0);
+                    sraw[o] = __reduce_add_sync(0xffffffffu, __float_as_int(a0));    // wraps mod 2^32
+                }
+#pragma unroll
+                for (int o = 0; o < O; ++o) t[o] = fmaf((float)(int)((unsigned int)sraw[o] - (unsigned int)kMagicSum32), cdec, b2l[o]);
             } else {
 #pragma unroll
-                for (int o = 0; o < O; ++o) t[o] = fmaf(warp_sum_shfl(p[o], 5), -kL2E * kInvFix, b2l[o]);
+                for (int o = 0; o < O; ++o) {
+                    float a0 = hid[0] * w2[o][0];
+#pragma unroll
+                    for (int k = 1; k < HPL; ++k) a0 = fmaf(hid[k], w2[o][k], a0);
+                    t[o] = fmaf(warp_sum_shfl(a0, 5), -kL2E, b2l[o]);
+                }
             }
         }
         // ---- independent of the chain: stale scaled pre-activation of the next row, xn.x + 1,
@@ -342,7 +360,11 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
     constexpr int IP = IPad<I>::value;
     constexpr uint32_t RB = IP * 4u;
     const int lane = threadIdx.x & 31;
-    const int n = d.n;
+    // opaque copies: kernel parameters would otherwise be re-read from the constant bank inside the
+    // row loop (an LDC and its latency in series with the dependent chain)
+    int n = d.n;
+    asm volatile("" : "+r"(n));
+    asm volatile("" : "+f"(lr));
     SgdWarp<I, H, O, TASK> net;
     net.load(w_in, lane);
     const int ntiles = (n + kTileRows - 1) / kTileRows;
@@ -390,37 +412,40 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
             if (k == kTileRows - 2 && r + 2 < n) wait((r + 2) / kTileRows);
             e = min(n, r - k + (k < kTileRows - 2 ? kTileRows - 2 : kTileRows));
         }
+        if (!SgdWarp<I, H, O, TASK>::GATHER) e = min(e, r + kGuardRows);   // rows covered by one fixed-point scale
         int cnt = e - r;
         uint32_t px = xaddr(min(r + 2, n - 1)), py = yaddr(min(r + 2, n - 1));
-        // rows r, r+1, r+2 per iteration; fetches r+2, r+3, r+4 (same tile by construction).  The guard
-        // of the NEXT iteration is evaluated at the top of this one (6 rows of margin), so the branch
-        // that selects the variant never waits for the CREDUX.
-        bool ok = net.guard(3, lr);
-        while (cnt >= 3 && r + 4 < n) {
-            const bool ok_next = net.guard(6, lr);
-            if (ok) {
+        // rows r, r+1, r+2 per iteration; fetches r+2, r+3, r+4 (same tile by construction).  The scale
+        // of the fixed-point sum is chosen once per chunk (its CREDUX would otherwise sit in the loop
+        // header, serial with the chain), with the margin for kGuardRows rows.
+        int iters = min(cnt, max(n - 4 - r + 2, 0)) / 3;   // every fetch stays below n
+        const bool ok = net.set_scale(kGuardRows, lr);
+        r += 3 * iters; cnt -= 3 * iters;
+        if (ok) {
+            for (; iters > 0; --iters) {
                 lds_row<IP>(px, C); yc = lds_f32(py);
                 net.template row<true>(A, ya, B, zs, lr, lane);
                 lds_row<IP>(px + RB, A); ya = lds_f32(py + 4u);
                 net.template row<true>(B, yb, C, zs, lr, lane);
                 lds_row<IP>(px + 2u * RB, B); yb = lds_f32(py + 8u);
                 net.template row<true>(C, yc, A, zs, lr, lane);
-            } else {
+                px += 3u * RB; py += 12u;
+            }
+        } else {
+            for (; iters > 0; --iters) {
                 lds_row<IP>(px, C); yc = lds_f32(py);
                 net.template row<false>(A, ya, B, zs, lr, lane);
                 lds_row<IP>(px + RB, A); ya = lds_f32(py + 4u);
                 net.template row<false>(B, yb, C, zs, lr, lane);
                 lds_row<IP>(px + 2u * RB, B); yb = lds_f32(py + 8u);
                 net.template row<false>(C, yc, A, zs, lr, lane);
+                px += 3u * RB; py += 12u;
             }
-            ok = ok_next;
-            px += 3u * RB; py += 12u;
-            r += 3; cnt -= 3;
         }
         while (cnt > 0) {
             const int q = min(r + 2, n - 1);     // past the end: any finite row (the look-ahead result is unused)
             lds_row<IP>(xaddr(q), C); yc = lds_f32(yaddr(q));
-            if (net.guard(1, lr)) net.template row<true>(A, ya, B, zs, lr, lane);
+            if (ok) net.template row<true>(A, ya, B, zs, lr, lane);
             else net.template row<false>(A, ya, B, zs, lr, lane);
 #pragma unroll
             for (int i = 0; i < IP; ++i) { A[i] = B[i]; B[i] = C[i]; }
