@@ -107,7 +107,7 @@ struct ptfnn_sampler {
 
     DevBuf<float> train_x, train_y, test_x, test_y;
     DevBuf<double> temperature;
-    DevBuf<float> w, last_w, gd_cache, pos_w, pub_rows;
+    DevBuf<float> w, gd_cache, pgd_buf, pos_w, pub_rows;
     DevBuf<double> eta, tau, lik, prior, last4, init_rmse, pub_lhood;
     DevBuf<double> lik_prop, rmse_tr, rmse_te, acc_tr, acc_te, dbg_prior, dbg_diff, dbg_mh;
     DevBuf<int> n_acc, init_count, gd_valid, accept_list;
@@ -121,7 +121,7 @@ struct ptfnn_sampler {
 
     void release_all() {
         train_x.release(); train_y.release(); test_x.release(); test_y.release(); temperature.release();
-        w.release(); last_w.release(); gd_cache.release(); pos_w.release(); pub_rows.release();
+        w.release(); gd_cache.release(); pgd_buf.release(); pos_w.release(); pub_rows.release();
         eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
         pub_lhood.release(); lik_prop.release(); rmse_tr.release(); rmse_te.release(); acc_tr.release();
         acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
@@ -246,7 +246,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
         rc = fail(nullptr, PTFNN_E_NOMEM, "cudaMalloc(" #buf ", %zu elems): %s", (size_t)(count), cudaGetErrorString(e)); \
         s->release_all(); delete s; cudaGetLastError(); return rc;                            \
     }
-    ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(last_w, R * P); ALLOC(gd_cache, R * P);
+    ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(gd_cache, R * P); ALLOC(pgd_buf, cfg->n_hidden > 64 ? R * P : 1);
     ALLOC(pos_w, R * S * P); ALLOC(pub_rows, 2 * R * (P + 1)); ALLOC(pub_lhood, 2 * (size_t)Rg);
     ALLOC(eta, R); ALLOC(tau, R); ALLOC(lik, R); ALLOC(prior, R); ALLOC(last4, R * 4); ALLOC(init_rmse, R * 2);
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
@@ -334,7 +334,6 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     // trace row 0 and carried rows: pos_w = 1, likelihood = -100, everything else 0
     {
         std::vector<float> ones(R * P, 1.0f);
-        CU_TRY(s, cudaMemcpyAsync(s->last_w.p, ones.data(), R * P * 4, cudaMemcpyHostToDevice, s->stream));
         for (size_t r = 0; r < R; ++r)
             CU_TRY(s, cudaMemcpyAsync(s->pos_w.p + r * S * P, ones.data(), P * 4, cudaMemcpyHostToDevice, s->stream));
         std::vector<double> m100(R * S, 0.0);
@@ -462,8 +461,8 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.train = view(s->train_x, s->train_y, s->n_train);
     p.test = view(s->test_x, s->test_y, s->n_test);
     p.w = s->w.p; p.eta = s->eta.p; p.tau = s->tau.p; p.lik = s->lik.p; p.prior = s->prior.p;
-    p.n_acc = s->n_acc.p; p.init_count = s->init_count.p; p.last_w = s->last_w.p; p.last4 = s->last4.p;
-    p.gd_cache = s->gd_cache.p; p.gd_valid = s->gd_valid.p;
+    p.n_acc = s->n_acc.p; p.init_count = s->init_count.p; p.last4 = s->last4.p;
+    p.gd_cache = s->gd_cache.p; p.pgd_buf = s->pgd_buf.p; p.gd_valid = s->gd_valid.p;
     p.pos_w = s->pos_w.p; p.lik_prop = s->lik_prop.p; p.rmse_tr = s->rmse_tr.p; p.rmse_te = s->rmse_te.p;
     p.acc_tr = s->acc_tr.p; p.acc_te = s->acc_te.p; p.accept_list = s->accept_list.p;
     p.dbg_prior = s->dbg_prior.p; p.dbg_diff = s->dbg_diff.p; p.dbg_mh = s->dbg_mh.p; p.dbg_acc = s->dbg_acc.p;
@@ -498,9 +497,9 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     const size_t stage_bytes = ((size_t)s->n_train * s->IP + ((s->n_train + 3) & ~3) + (size_t)s->n_test * s->IP + ((s->n_test + 3) & ~3)) * 4;
     p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
     const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
-    const int team_floats = UseSgdTeam<1>::value ? 0 : (c.n_hidden > 64 ? c.n_hidden + c.n_out : 0);   // mirrors UseSgdTeam<H>
+    const int team_floats = c.n_hidden > 64 ? team_smem_floats(c.n_hidden, c.n_out) : 0;   // mirrors UseSgdTeam<H>
     const int lik_floats = c.n_hidden * ((c.n_in + 1 + c.n_out + 3) & ~3);   // mirrors LikLayout<I, O>::LW
-    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats);
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats, team_floats == 0);
     if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
     CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int per_sm = 0;
@@ -845,7 +844,7 @@ static int op_langevin_impl(int32_t device, int32_t task, int32_t I, int32_t H, 
     DataView v{od.x.p, od.y.p, rows};
     const float *wp = od.w.p; float *op = d_out.p; float lr = (float)learn_rate; int dep = depth;
     void *args[] = {&wp, &op, &v, &lr, &dep};
-    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 16 + (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4) + (size_t)(H + O) * 4 + 16;
+    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 16 + (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4) + (size_t)team_smem_floats(H, O) * 4 + 16;
     CU_TRY(nullptr, cudaFuncSetAttribute(ks->sgd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     CU_TRY(nullptr, cudaEventCreate(&e0)); CU_TRY(nullptr, cudaEventCreate(&e1));

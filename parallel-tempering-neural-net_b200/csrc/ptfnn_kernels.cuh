@@ -457,41 +457,76 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
 }
 
 // ==========================================================================================
-// K2 (wide hidden layers): the serial recurrence run by a TEAM of NWT warps.  With H = 256, one
+// K2 (wide hidden layers): the serial recurrence run by a TEAM of NT threads.  With H = 256 one
 // warp would need ~216 live registers per lane (8 hidden units x (I + O + 1)) and spills; here
-// thread t owns hidden unit(s) t, t + T, ... (row view: W1 column, B1, W2 row in registers) and the
-// output layer is evaluated in a column view: output o belongs to warp o % NWT, which keeps that
-// W2 column in registers (H/32 per lane), reads the hidden activations from shared memory, and
-// reduces with one REDUX.  Two team barriers per row (hid -> out_delta -> hid_delta).  Both views of
-// W2 receive the same update (R:67-69), so they stay bit-identical.
+// thread t owns hidden unit t (row view: W1 column, B1, W2 row in registers) and the output layer is
+// evaluated in a column view: output o belongs to warp o % NWT, which keeps that W2 column in
+// registers (H/32 per lane), reads the hidden activations from shared memory and sums across lanes
+// on the integer REDUX unit (block fixed point on the magic constant, as in SgdWarp).  Two team
+// barriers per row (hid -> out_delta -> hid_delta).  Both views of W2 receive the same update
+// (R:67-69), so they stay bit-identical.
+//
+// The first version of this kernel issued 240 instructions per thread and row -- 480 issue cycles
+// per row and CTA, i.e. it was bound by the issue slots, not by the chain, and two co-resident
+// CTAs simply took twice as long.  This version: packed FFMA2 dot products / rank-1 updates over
+// the inputs and outputs of a thread, look-ahead pre-activation in the ex2 domain (one FFMA on
+// the chain), x_next.x + 1 computed once per 128-row tile by the whole team instead of by every
+// thread and row, rows unrolled by two (no register rotation).
 // ==========================================================================================
 template <int H>
 struct UseSgdTeam {
     static constexpr bool value = H > 64;
 };
+__host__ __device__ constexpr int team_smem_floats(int H, int O) {
+    return ((H + 31) / 32) * 32 + ((O + 3) & ~3) + kTileRows + 4;  // s_hid, s_od, s_c, two mbarriers
+}
+
+// init + sum_i a[i] * b[i] through two packed partial sums
+template <int N>
+__device__ __forceinline__ float vdot(const float (&a)[N], const float (&b)[N], float init) {
+    float2 acc = make_float2(init, 0.0f);
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) acc = __ffma2_rn(make_float2(a[k], a[k + 1]), make_float2(b[k], b[k + 1]), acc);
+    float r = acc.x + acc.y;
+    if (N & 1) r = fmaf(a[N - 1], b[N - 1], r);
+    return r;
+}
+
+#ifdef PTFNN_TEAM_TRACE     // measurement builds only (tools/team_trace.cu): per-phase clock stamps of a few rows
+__device__ long long g_team_trace[8][16][8];
+#define TEAM_STAMP(k) do { if (lane == 0 && trace_row >= 0 && trace_row < 16) g_team_trace[warp][trace_row][k] = clock64(); } while (0)
+#else
+#define TEAM_STAMP(k) do { } while (0)
+#endif
 
 template <int I, int H, int O, int TASK, int NT>
 __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, const DataView &d, bool staged, float lr,
-                                              SgdStream &st, float *s_hid /* [H] */, float *s_od /* [O] */) {
+                                              SgdStream &st, float *s_team) {
     constexpr int IP = IPad<I>::value;
+    constexpr uint32_t RBY = IP * 4u;
     constexpr int NWT = NT / 32;
-    constexpr int HPT = (H + NT - 1) / NT;        // hidden units per thread (row view)
     constexpr int OPW = (O + NWT - 1) / NWT;      // outputs per warp (column view)
     constexpr int HC = (H + 31) / 32;             // hidden units per lane in the column view
+    constexpr int OP = (O + 3) & ~3;
     constexpr int oW2 = I * H, oB1 = I * H + H * O, oB2 = I * H + H * O + H;
+    static_assert(H <= NT && NT % 32 == 0 && HC * 32 <= NT, "one hidden unit per thread");
+    float *s_hid = s_team;                        // [HC * 32]
+    float *s_od = s_hid + HC * 32;                // [OP]
+    float *s_c = s_od + OP;                       // [kTileRows]  x_{r+1}.x_r + 1 of the resident tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float w1[HPT][I], b1[HPT], w2r[HPT][O];
-    float w2c[OPW][HC], b2c[OPW];
+    int n = d.n;
+    asm volatile("" : "+r"(n));                   // keep loop invariants in registers (no LDC in the row loop)
+    asm volatile("" : "+f"(lr));
+    const bool act = tid < H;
+
+    // ---- row view (hidden unit tid) and column view (outputs warp, warp + NWT, ...)
+    float w1[I], b1, w2r[O];
+    float w2c[OPW][HC], b2[OPW], b2l[OPW];
 #pragma unroll
-    for (int k = 0; k < HPT; ++k) {
-        const int h = tid + NT * k;
-        const bool a = h < H;
+    for (int i = 0; i < I; ++i) w1[i] = act ? w_in[i * H + tid] : 0.0f;
 #pragma unroll
-        for (int i = 0; i < I; ++i) w1[k][i] = a ? w_in[i * H + h] : 0.0f;
-#pragma unroll
-        for (int o = 0; o < O; ++o) w2r[k][o] = a ? w_in[oW2 + h * O + o] : 0.0f;
-        b1[k] = a ? w_in[oB1 + h] : 0.0f;
-    }
+    for (int o = 0; o < O; ++o) w2r[o] = act ? w_in[oW2 + tid * O + o] : 0.0f;
+    b1 = act ? w_in[oB1 + tid] : 1.0e4f;          // no hidden unit: sigmoid = 0 exactly, every update an exact zero
 #pragma unroll
     for (int j = 0; j < OPW; ++j) {
         const int o = warp + NWT * j;
@@ -500,163 +535,255 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
             const int h = lane + 32 * m;
             w2c[j][m] = (o < O && h < H) ? w_in[oW2 + h * O + o] : 0.0f;
         }
-        b2c[j] = o < O ? w_in[oB2 + o] : 0.0f;
+        b2[j] = o < O ? w_in[oB2 + o] : 0.0f;
+        b2l[j] = kL2E * b2[j];
     }
+    if (tid < OP) s_od[tid] = 0.0f;
     __syncthreads();   // w_in may alias w_out; everybody has read its share
 
-    auto preact = [&](const float(&x)[IP], float(&z)[HPT]) {
-#pragma unroll
-        for (int k = 0; k < HPT; ++k) {
-            float t = -b1[k];
-#pragma unroll
-            for (int i = 0; i < I; ++i) t = fmaf(x[i], w1[k][i], t);
-            z[k] = t;
+    // ---- data addressing: staged copy or two TMA tiles
+    const int ntiles = (n + kTileRows - 1) / kTileRows;
+    const uint32_t sx = smem_u32(d.x), sy = smem_u32(d.y);
+    const uint32_t tx0 = smem_u32(st.tile_x0), tx1 = smem_u32(st.tile_x1);
+    const uint32_t ty0 = smem_u32(st.tile_y0), ty1 = smem_u32(st.tile_y1);
+    auto xaddr = [&](int r) -> uint32_t {
+        return staged ? sx + (uint32_t)r * RBY : (((r / kTileRows) & 1) ? tx1 : tx0) + (uint32_t)(r % kTileRows) * RBY;
+    };
+    auto yaddr = [&](int r) -> uint32_t {
+        return staged ? sy + (uint32_t)r * 4u : (((r / kTileRows) & 1) ? ty1 : ty0) + (uint32_t)(r % kTileRows) * 4u;
+    };
+    auto issue = [&](int t) {
+        const int rows = min(kTileRows, n - t * kTileRows);
+        const uint32_t bx = (uint32_t)rows * RBY;
+        const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;
+        if (tid == 0) {
+            uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
+            mbar_arrive_expect_tx(bar, bx + by);
+            tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
+            tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
         }
     };
-    auto row = [&](const float(&x)[IP], float yv, const float(&xn)[IP], float(&z)[HPT]) {
-        float hid[HPT];
-#pragma unroll
-        for (int k = 0; k < HPT; ++k) {
-            const int h = tid + NT * k;
-            hid[k] = h < H ? sigmoid_fast(z[k]) : 0.0f;
-            if (h < H) s_hid[h] = hid[k];
-        }
-        float zn[HPT];
-        preact(xn, zn);
-        float c = 1.0f;
-#pragma unroll
-        for (int i = 0; i < I; ++i) c = fmaf(xn[i], x[i], c);
-        __syncthreads();
-        // ---- column view: this warp's outputs (all OPW of them at once: independent dot products,
-        //      one vectorised REDUX, pipelined sigmoids)
-        {
-            float hv[HC];
-#pragma unroll
-            for (int m = 0; m < HC; ++m) hv[m] = (lane + 32 * m < H) ? s_hid[lane + 32 * m] : 0.0f;
-            float acc[OPW];
-#pragma unroll
-            for (int j = 0; j < OPW; ++j) {
-                float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-                for (int m = 0; m + 1 < HC; m += 2) { a0 = fmaf(hv[m], w2c[j][m], a0); a1 = fmaf(hv[m + 1], w2c[j][m + 1], a1); }
-                if (HC & 1) a0 = fmaf(hv[HC - 1], w2c[j][HC - 1], a0);
-                acc[j] = a0 + a1;
-            }
-            warp_sum_vec<OPW>(acc, 5);
-#pragma unroll
-            for (int j = 0; j < OPW; ++j) {
-                const int o = warp + NWT * j;
-                const float out = sigmoid_fast(acc[j] - b2c[j]);                      // R:54-55
-                float dd;
-                if constexpr (TASK == kTaskCls) dd = ((int)yv == o) ? 1.0f : 0.0f;    // C:73-75
-                else dd = yv;
-                const float od = (o < O) ? (dd - out) * (out * (1.0f - out)) : 0.0f;  // R:58
-                if (lane == 0 && o < O) s_od[o] = od;
-                const float lo = lr * od;
-#pragma unroll
-                for (int m = 0; m < HC; ++m) w2c[j][m] = fmaf(lo, hv[m], w2c[j][m]);   // R:67-69
-                b2c[j] -= lo;                                                         // R:70-71
-            }
-        }
-        __syncthreads();
-        // ---- row view: hid_delta with the pre-update W2 row (R:59), then the updates
-        float od[O];
-#pragma unroll
-        for (int o = 0; o < O; ++o) od[o] = s_od[o];
-#pragma unroll
-        for (int k = 0; k < HPT; ++k) {
-            float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-            for (int o = 0; o + 1 < O; o += 2) { s0 = fmaf(od[o], w2r[k][o], s0); s1 = fmaf(od[o + 1], w2r[k][o + 1], s1); }
-            if (O & 1) s0 = fmaf(od[O - 1], w2r[k][O - 1], s0);
-            const float lh = lr * ((s0 + s1) * (hid[k] * (1.0f - hid[k])));
-            z[k] = fmaf(lh, c, zn[k]);
-#pragma unroll
-            for (int o = 0; o < O; ++o) w2r[k][o] = fmaf(lr * od[o], hid[k], w2r[k][o]);
-#pragma unroll
-            for (int i = 0; i < I; ++i) w1[k][i] = fmaf(lh, x[i], w1[k][i]);           // R:74-76
-            b1[k] -= lh;                                                               // R:77-78
-        }
+    auto wait = [&](int t) {
+        if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
+        else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
     };
 
-    float xc[IP], xz[IP], yc;
-    float z[HPT];
+    float zs;                 // ex2-domain pre-activation of this thread's hidden unit for the current row
+    float fscale = 1.0f, cdec = -kL2E;
+    // fixed-point scale of this warp's output sums for the next `rows` rows (see SgdWarp::set_scale);
+    // non-finite weights poison the decode factor so that NaN propagates as in the reference
+    auto set_scale = [&](int rows) {
+        float m = 0.0f;
 #pragma unroll
-    for (int i = 0; i < IP; ++i) xz[i] = 0.0f;
-    auto run_rows = [&](uint32_t xa, uint32_t ya, int count) {   // look-ahead row inside the same tile
-        for (int r = 0; r < count; ++r) {
-            float xn[IP];
-            lds_row<IP>(xa + (uint32_t)(r + 1) * IP * 4u, xn);
-            const float yn = lds_f32(ya + (uint32_t)(r + 1) * 4u);
-            row(xc, yc, xn, z);
+        for (int j = 0; j < OPW; ++j) {
+            float a = 0.0f;
 #pragma unroll
-            for (int i = 0; i < IP; ++i) xc[i] = xn[i];
-            yc = yn;
+            for (int k = 0; k < HC; ++k) a += fabsf(w2c[j][k]);
+            m = fmaxf(m, a);
+            m = (a != a) ? __int_as_float(0x7fc00000) : m;
         }
+        m = fmaxf(m + (float)(rows * HC) * 0.25f * fabsf(lr), 9.765625e-4f);
+        const unsigned int ef = __reduce_max_sync(0xffffffffu, __float_as_uint(m)) >> 23;
+        const bool ok = ef < 200u;
+        const unsigned int sf = ok ? 275u - ef : 127u;
+        fscale = __uint_as_float(sf << 23);
+        cdec = ok ? -kL2E * __uint_as_float((254u - sf) << 23) : __int_as_float(0x7fc00000);
     };
-    if (staged) {
-        const uint32_t xa = smem_u32(d.x), ya = smem_u32(d.y);
-        lds_row<IP>(xa, xc);
-        yc = lds_f32(ya);
-        preact(xc, z);
-        run_rows(xa, ya, d.n - 1);
-        row(xc, yc, xz, z);
-    } else {
-        const int ntiles = (d.n + kTileRows - 1) / kTileRows;
-        auto issue = [&](int t) {
-            const int rows = min(kTileRows, d.n - t * kTileRows);
-            const uint32_t bx = (uint32_t)rows * IP * 4u;
-            const uint32_t by = (uint32_t)((rows + 3) & ~3) * 4u;
-            if (tid == 0) {
-                uint64_t *bar = (t & 1) ? st.bar1 : st.bar0;
-                mbar_arrive_expect_tx(bar, bx + by);
-                tma_load_1d((t & 1) ? st.tile_x1 : st.tile_x0, d.x + (size_t)t * kTileRows * IP, bx, bar);
-                tma_load_1d((t & 1) ? st.tile_y1 : st.tile_y0, d.y + (size_t)t * kTileRows, by, bar);
-            }
-        };
-        auto wait = [&](int t) {
-            if (t & 1) { mbar_wait(st.bar1, st.parity1); st.parity1 ^= 1u; }
-            else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
-        };
-        issue(0);
-        wait(0);
-        lds_row<IP>(smem_u32(st.tile_x0), xc);
-        yc = lds_f32(smem_u32(st.tile_y0));
-        preact(xc, z);
-        for (int t = 0; t < ntiles; ++t) {
-            const bool more = t + 1 < ntiles;
-            if (more) issue(t + 1);      // other buffer: every thread is past tile t-1 (team barriers in row())
-            const int rows = min(kTileRows, d.n - t * kTileRows);
-            run_rows(smem_u32((t & 1) ? st.tile_x1 : st.tile_x0), smem_u32((t & 1) ? st.tile_y1 : st.tile_y0), rows - 1);
-            if (more) {
-                wait(t + 1);
-                float xn[IP];
-                lds_row<IP>(smem_u32((t & 1) ? st.tile_x0 : st.tile_x1), xn);
-                const float yn = lds_f32(smem_u32((t & 1) ? st.tile_y0 : st.tile_y1));
-                row(xc, yc, xn, z);
+
+    // Team barriers: BAR.SYNC on sm_100 blocks at the first instruction that touches barrier-protected
+    // state, not at issue, so register-only work placed right after a barrier (weight updates of the
+    // previous row, column-view updates, look-ahead) runs while the other warps arrive.  (mbarrier
+    // arrive / try_wait pairs were measured too: ~75 cycles per phase against ~30 for BAR.SYNC.)
+
+    // carried from one row to the next: what the deferred updates of the previous row need
+    float hid_p = 0.0f, lh_p = 0.0f, lo_p[O];
 #pragma unroll
-                for (int i = 0; i < IP; ++i) xc[i] = xn[i];
-                yc = yn;
+    for (int o = 0; o < O; ++o) lo_p[o] = 0.0f;
+
+    // One row.  pbuf holds the PREVIOUS row on entry (its W1 update is still pending) and the NEXT row
+    // (look-ahead) on exit; cbuf is the current row (only the tile's last row needs it, for x_next.x + 1).
+    // The current row itself enters through zs (its pre-activation) and y.
+    auto row = [&](const bool boundary, float (&pbuf)[IP], const float (&cbuf)[IP], uint32_t y_addr, uint32_t xn_addr,
+                   float c_in, bool has_next) {
+        const float yv = lds_f32(y_addr);
+#ifdef PTFNN_TEAM_TRACE
+        const int trace_row = (int)((y_addr - yaddr(0)) / 4u) - 64;     // rows 64..79 of the first tile
+#endif
+        TEAM_STAMP(0);
+        // ---- A: hidden activation (R:52-53), published to the team
+        const float hid = rcp_ftz(1.0f + ex2_ftz(zs));
+        if (NT == HC * 32 || tid < HC * 32) s_hid[tid] = hid;
+        __syncthreads();
+        TEAM_STAMP(1);
+        // ---- deferred updates of the PREVIOUS row (off the chain; its hid_delta is already inside zs)
+        {
+            float xi[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) xi[i] = pbuf[i];
+            vfma_s<I>(w1, xi, lh_p, w1);                         // R:74-76
+            b1 -= lh_p;                                          // R:77-78
+            vfma_s<O>(w2r, lo_p, hid_p, w2r);                    // R:67-69
+        }
+        hid_p = hid;
+        // the look-ahead row takes the place of the row that has just been applied
+        float cr = c_in;
+        if (boundary) {                               // literal at every call site: folded after inlining
+            if (has_next) {
+                lds_row<IP>(xn_addr, pbuf);
+                cr = 1.0f;
+#pragma unroll
+                for (int i = 0; i < I; ++i) cr = fmaf(cbuf[i], pbuf[i], cr);
             } else {
-                row(xc, yc, xz, z);
+#pragma unroll
+                for (int i = 0; i < IP; ++i) pbuf[i] = 0.0f;
+                cr = 1.0f;
+            }
+        } else {
+            lds_row<IP>(xn_addr, pbuf);
+        }
+        TEAM_STAMP(2);
+        // ---- B: column view -- all OPW outputs of the warp at once (unused slots have W2 = 0):
+        //      independent dot products, pipelined REDUX and sigmoids
+        float hv[HC];
+#pragma unroll
+        for (int m = 0; m < HC; ++m) hv[m] = s_hid[lane + 32 * m];
+        float lo_j[OPW];
+        int sraw[OPW];
+#pragma unroll
+        for (int j = 0; j < OPW; ++j) {
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int m = 0; m + 1 < HC; m += 2) { a0 = fmaf(hv[m], w2c[j][m], a0); a1 = fmaf(hv[m + 1], w2c[j][m + 1], a1); }
+            if (HC & 1) a0 = fmaf(hv[HC - 1], w2c[j][HC - 1], a0);
+            sraw[j] = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(a0 + a1, fscale, kMagic)));
+        }
+#pragma unroll
+        for (int j = 0; j < OPW; ++j) {
+            const int o = warp + NWT * j;
+            const float t = fmaf((float)(int)((unsigned int)sraw[j] - (unsigned int)kMagicSum32), cdec, b2l[j]);
+            const float out = rcp_ftz(1.0f + ex2_ftz(t));                          // R:54-55
+            float dd;
+            if constexpr (TASK == kTaskCls) dd = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75
+            else dd = yv;
+            const float q = lr * fmaf(-out, out, out);
+            const float lo = (o < O) ? (dd - out) * q : 0.0f;                      // lr * out_delta (R:58)
+            if (lane == 0 && o < O) s_od[o] = lo;
+            lo_j[j] = lo;
+        }
+        __syncthreads();
+        TEAM_STAMP(4);
+        // ---- column-view updates and this thread's look-ahead (off the chain)
+#pragma unroll
+        for (int j = 0; j < OPW; ++j) {
+#pragma unroll
+            for (int m = 0; m < HC; ++m) w2c[j][m] = fmaf(lo_j[j], hv[m], w2c[j][m]);   // R:67-69 (column view)
+            b2[j] -= lo_j[j];                                                         // R:70-71
+            b2l[j] = kL2E * b2[j];
+        }
+        // stale pre-activation of the next row: the weights BEFORE this row's update, i.e. after the
+        // previous row's, which was applied above;  hid (1 - hid) W2 with the pre-update W2 (R:59)
+        float xni[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) xni[i] = pbuf[i];
+        const float zns = -kL2E * vdot<I>(xni, w1, -b1);
+        const float ccl = -kL2E * cr;
+        const float g = fmaf(-hid, hid, hid);
+        float gw[O];
+        vmul_s<O>(gw, w2r, g);
+        TEAM_STAMP(5);
+        // ---- C: row view -- lr * hid_delta; next row's pre-activation
+        float od[OP];
+#pragma unroll
+        for (int q = 0; q < OP / 4; ++q) {
+            const float4 v = reinterpret_cast<const float4 *>(s_od)[q];
+            od[4 * q] = v.x; od[4 * q + 1] = v.y; od[4 * q + 2] = v.z; od[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) lo_p[o] = od[o];
+        lh_p = vdot<O>(lo_p, gw, 0.0f);                          // lr * hid_delta
+        zs = fmaf(lh_p, ccl, zns);                               // chain: lr*hd*(xn.x + 1) on top of the stale value
+        TEAM_STAMP(7);
+    };
+    // applies the updates still pending after the last row
+    auto flush = [&](const float (&xp)[IP]) {
+        float xi[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) xi[i] = xp[i];
+        vfma_s<I>(w1, xi, lh_p, w1);
+        b1 -= lh_p;
+        vfma_s<O>(w2r, lo_p, hid_p, w2r);
+        lh_p = 0.0f; hid_p = 0.0f;
+    };
+
+    // ---- rows.  Register buffers A / B alternate between "previous row" and "current row".
+    constexpr bool PlainRow = false, TileEnd = true;
+    float A[IP], B[IP];
+#pragma unroll
+    for (int i = 0; i < IP; ++i) A[i] = 0.0f;      // "previous row" of row 0: nothing pending
+    if (!staged) { issue(0); wait(0); }
+    lds_row<IP>(xaddr(0), B);
+    {
+        float xi[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) xi[i] = B[i];
+        zs = -kL2E * vdot<I>(xi, w1, -b1);
+    }
+    int r = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int base = t * kTileRows;
+        const int rows = min(kTileRows, n - base);
+        // tile t is resident.  x_{r+1}.x_r + 1 for its rows (the last one needs the next tile: done in its row)
+        for (int q = tid; q < rows - 1; q += NT) {
+            float u[IP], v[IP];
+            lds_row<IP>(xaddr(base + q), u);
+            lds_row<IP>(xaddr(base + q + 1), v);
+            float c = 1.0f;
+#pragma unroll
+            for (int i = 0; i < I; ++i) c = fmaf(u[i], v[i], c);
+            s_c[q] = c;
+        }
+        __syncthreads();          // s_c visible; every thread is past its reads of tile t-1
+        if (!staged && t + 1 < ntiles) issue(t + 1);
+        const int last = base + rows - 1;            // the tile's last row looks ahead into the next tile
+        while (last - r >= 2) {                      // pairs of rows whose look-ahead rows are in this tile
+            int pairs = min(kGuardRows, last - r) / 2;
+            set_scale(kGuardRows);
+            uint32_t px = xaddr(r + 1), py = yaddr(r);
+            const float *pc = s_c + (r - base);
+            r += 2 * pairs;
+            for (; pairs > 0; --pairs) {
+                row(PlainRow, A, B, py, px, pc[0], true);             // prev A, current B; A <- next
+                row(PlainRow, B, A, py + 4u, px + RBY, pc[1], true);  // prev B, current A; B <- next
+                px += 2u * RBY; py += 8u; pc += 2;
             }
         }
-    }
+        set_scale(2);
+        const bool has_next = last + 1 < n;
+        if (has_next && !staged) wait(t + 1);        // issued 127 rows ago
+        const uint32_t xnext = xaddr(has_next ? last + 1 : last);
+        if (last - r == 1) {
+            row(PlainRow, A, B, yaddr(r), xaddr(r + 1), s_c[r - base], true);
+            row(TileEnd, B, A, yaddr(last), xnext, 1.0f, has_next);
+        } else {                                     // odd-sized (last) tile: the roles end up swapped
+            row(TileEnd, A, B, yaddr(last), xnext, 1.0f, has_next);
 #pragma unroll
-    for (int k = 0; k < HPT; ++k) {
-        const int h = tid + NT * k;
-        if (h < H) {
-#pragma unroll
-            for (int i = 0; i < I; ++i) w_out[i * H + h] = w1[k][i];
-#pragma unroll
-            for (int o = 0; o < O; ++o) w_out[oW2 + h * O + o] = w2r[k][o];
-            w_out[oB1 + h] = b1[k];
+            for (int i = 0; i < IP; ++i) { const float tmp = A[i]; A[i] = B[i]; B[i] = tmp; }
         }
+        r = last + 1;
+    }
+    flush(A);                                        // A = the last row processed
+
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < I; ++i) w_out[i * H + tid] = w1[i];
+#pragma unroll
+        for (int o = 0; o < O; ++o) w_out[oW2 + tid * O + o] = w2r[o];
+        w_out[oB1 + tid] = b1;
     }
 #pragma unroll
     for (int j = 0; j < OPW; ++j) {
         const int o = warp + NWT * j;
-        if (o < O && lane == 0) w_out[oB2 + o] = b2c[j];
+        if (o < O && lane == 0) w_out[oB2 + o] = b2[j];
     }
     __syncthreads();
 }
@@ -985,9 +1112,9 @@ struct ChainParams {
     float *w;                      // [R][P]
     double *eta, *tau, *lik, *prior;
     int *n_acc, *init_count;
-    float *last_w;                 // [R][P]  last recorded pos_w row (R:417)
     double *last4;                 // [R][4]  rmse_train, rmse_test, acc_train, acc_test carried rows (R:420-423)
-    float *gd_cache;               // [R][P]  langevin_gradient(w) memo
+    float *gd_cache;               // [R][P]  langevin_gradient(w) memo (wide nets: the working copy too)
+    float *pgd_buf;                // [R][P]  langevin_gradient(w_prop) of wide nets (0 otherwise)
     int *gd_valid;                 // [R]
     // ---- traces
     float *pos_w;                  // [R][S][P]
@@ -1027,16 +1154,18 @@ struct NetSizes {
 // dynamic shared memory layout (floats unless noted); host computes the same with chain_smem_bytes()
 struct ChainSmem {
     int P4;          // P rounded up to 4
-    size_t off_w, off_prop, off_gd, off_pgd, off_last, off_lw, off_red, off_bar, off_tiles, off_sweep, off_team, off_stage, total;
+    size_t off_w, off_prop, off_gd, off_pgd, off_lw, off_red, off_bar, off_tiles, off_sweep, off_team, off_stage, total;
 };
 __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
-                                                       int n_test, int team_floats = 0, int lik_floats = 0) {
+                                                       int n_test, int team_floats = 0, int lik_floats = 0,
+                                                       bool gd_in_smem = true) {
     ChainSmem L;
     L.P4 = (P + 3) & ~3;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    L.off_w = take(L.P4 * 4); L.off_prop = take(L.P4 * 4); L.off_gd = take(L.P4 * 4);
-    L.off_pgd = take(L.P4 * 4); L.off_last = take(L.P4 * 4);
+    L.off_w = take(L.P4 * 4); L.off_prop = take(L.P4 * 4);
+    // langevin_gradient(w) and langevin_gradient(w_prop): shared memory, or (wide nets) the replica's global rows
+    L.off_gd = take(gd_in_smem ? L.P4 * 4 : 0); L.off_pgd = take(gd_in_smem ? L.P4 * 4 : 0);
     L.off_lw = take((size_t)lik_floats * 4);   // likelihood layout of the proposal (LikLayout)
     L.off_red = take((size_t)8 * (nt / 32) * 8);
     L.off_bar = take(8 * 4);
@@ -1119,16 +1248,14 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool TEAM = UseSgdTeam<H>::value;
-    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? H + O : 0,
-                                          H * LikLayout<I, O>::LW);
+    const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? team_smem_floats(H, O) : 0,
+                                          H * LikLayout<I, O>::LW, !TEAM);
     float *s_lw = reinterpret_cast<float *>(smem_raw + L.off_lw);
-    float *s_team_hid = reinterpret_cast<float *>(smem_raw + L.off_team);
-    float *s_team_od = s_team_hid + H;
+    float *s_team = reinterpret_cast<float *>(smem_raw + L.off_team);
     float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
     float *s_prop = reinterpret_cast<float *>(smem_raw + L.off_prop);
-    float *s_gd = reinterpret_cast<float *>(smem_raw + L.off_gd);
+    float *s_gd = reinterpret_cast<float *>(smem_raw + L.off_gd);      // re-pointed per replica when TEAM
     float *s_pgd = reinterpret_cast<float *>(smem_raw + L.off_pgd);
-    float *s_last = reinterpret_cast<float *>(smem_raw + L.off_last);
     double *s_red = reinterpret_cast<double *>(smem_raw + L.off_red);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + L.off_bar);
     double *s_sweep = reinterpret_cast<double *>(smem_raw + L.off_sweep);
@@ -1204,10 +1331,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 
         for (int r = blockIdx.x; r < p.R; r += nblocks) {
             // ---------------- load this replica's state ----------------
+            if constexpr (TEAM) { s_gd = p.gd_cache + (size_t)r * P; s_pgd = p.pgd_buf + (size_t)r * P; }
             for (int j = tid; j < P; j += NT) {
                 s_w[j] = p.w[(size_t)r * P + j];
-                s_last[j] = p.last_w[(size_t)r * P + j];
-                s_gd[j] = p.gd_cache[(size_t)r * P + j];
+                if constexpr (!TEAM) s_gd[j] = p.gd_cache[(size_t)r * P + j];
             }
             double eta = p.eta[r], tau = p.tau[r], lik = p.lik[r], prior_cur = p.prior[r];
             int n_acc = p.n_acc[r], init_count = p.init_count[r];
@@ -1252,7 +1379,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 const bool lg = p.use_lg && ((double)lx < p.l_prob);              // R:329
                 // ---- Langevin branch, first SGD epoch: w_gd = langevin_gradient(w)   (R:330)
                 if (lg && !gd_valid) {
-                    if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_gd, train, p.staged != 0, p.lr, stream, s_team_hid, s_team_od);
+                    if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_gd, train, p.staged != 0, p.lr, stream, s_team);
                     else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
                     __syncthreads();
                     gd_valid = p.memo;
@@ -1304,7 +1431,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     }
                 } else {
                     if (lg) {
-                        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream, s_team_hid, s_team_od);
+                        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream, s_team);
                         else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
@@ -1372,7 +1499,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     else { last_atr = 0.0; last_ate = 0.0; }                                   // R:403-404
                     for (int j = tid; j < P; j += NT) {
                         const float v = s_prop[j];
-                        s_w[j] = v; s_last[j] = v;
+                        s_w[j] = v;
                         if (lg && p.memo) s_gd[j] = s_pgd[j];   // langevin_gradient(new w) is already known
                     }
                     gd_valid = (lg && p.memo) ? 1 : 0;
@@ -1383,7 +1510,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 }
                 __syncthreads();
                 float *pw = p.pos_w + ti * P;
-                for (int j = tid; j < P; j += NT) pw[j] = s_last[j];                  // R:408 | R:417
+                // accepted: the new state (R:408); rejected: the previous row is carried (R:417) -- it was
+                // written by these same threads (or is row 0 = ones), so no copy of it is kept on chip
+                if (accept) { for (int j = tid; j < P; j += NT) pw[j] = s_w[j]; }
+                else { for (int j = tid; j < P; j += NT) pw[j] = pw[j - P]; }
             }
 
             // ---------------- publish for the hand-shake (R:427-431 / C:438-440) ----------------
@@ -1399,8 +1529,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             // ---------------- store state ----------------
             for (int j = tid; j < P; j += NT) {
                 p.w[(size_t)r * P + j] = s_w[j];
-                p.last_w[(size_t)r * P + j] = s_last[j];
-                if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j];
+                if constexpr (!TEAM) { if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
             }
             if (tid == 0) {
                 p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior_cur;
@@ -1545,7 +1674,7 @@ __global__ void __launch_bounds__(UseSgdTeam<H>::value ? NT : 32) op_sgd_kernel(
     st.bar0 = &s_bar[0]; st.bar1 = &s_bar[1];
     st.parity0 = st.parity1 = 0u;
     for (int e = 0; e < depth; ++e) {                       // R:108 `depth` epochs (sgd_depth is always 1, R:170)
-        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_w, d, false, lr, st, s_team, s_team + H);
+        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_w, d, false, lr, st, s_team);
         else sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
         __syncthreads();
     }

@@ -107,6 +107,20 @@ def test_wide_hidden_topology_ops():
     assert cm.relerr(w_gd, oc.langevin_gradient(on.CLASSIFICATION, topo, data, w, 0.01)) < RTOL
 
 
+def test_wide_hidden_ragged_rows():
+    """The team kernel's tile logic: one row, a pair, odd / even last tiles, exactly one tile, one past it."""
+    rs = np.random.RandomState(11)
+    topo = (16, 256, 10)
+    for n in (1, 2, 3, 127, 128, 129, 257):
+        data = np.hstack([rs.randn(n, 16), rs.randint(0, 10, size=(n, 1)).astype(float)])
+        w = rs.randn(on.num_params(topo)) * 0.2
+        w_gd = capi.op_langevin_gradient(capi.TASK_CLASSIFICATION, topo, data, w, 0.02)
+        assert cm.relerr(w_gd, oc.langevin_gradient(on.CLASSIFICATION, topo, data, w, 0.02)) < RTOL, n
+        fx, prob = capi.op_evaluate_proposal(capi.TASK_CLASSIFICATION, topo, data, w)
+        _, prob_ref = oc.evaluate(on.CLASSIFICATION, topo, data, w)
+        assert cm.relerr(prob, prob_ref) < RTOL, n
+
+
 def test_swap_sweep_matches_reference_rule():
     rs = np.random.RandomState(3)
     lh = [0.0, 10.0, 20.0, 30.0]

@@ -139,3 +139,40 @@ def test_trace_row_zero_and_carried_rows():
         assert np.all(t["pos_w"][r, :first] == 1.0) and np.all(t["rmse_train"][r, :first] == 0.0)
         assert np.array_equal(t["accept_list"][r, 1:], np.cumsum(t["accepted"][r])[:-1])
     assert np.all(t["acc_train"] == 0.0)                                              # R:403-404
+
+
+@pytest.mark.parametrize("memo", [0, 1])
+def test_wide_hidden_chain_replay(memo):
+    """[16,256,10] (BASELINE configs[4] shape): the team SGD kernel, langevin_gradient buffers in global
+    memory and the wide-hidden likelihood path inside the chain kernel, against the float64 oracle on the
+    same draws (Langevin and random-walk steps, swaps, the 60% temperature switch at step 6)."""
+    rs = np.random.RandomState(21)
+    topo = (16, 256, 10)
+    cfg = on.PTConfig(task=on.CLASSIFICATION, topology=topo, samples=10, swap_interval=3,
+                      use_langevin_gradients=True, l_prob=0.5, learn_rate=0.01)
+    mk = lambda n: np.hstack([rs.randn(n, 16), rs.randint(0, 10, size=(n, 1)).astype(float)])   # noqa: E731
+    tr, te = mk(300), mk(131)
+    R = 3
+    temps = np.array([1.0, 1.5, 2.25])
+    draws = on.random_draws(cfg, R, 5, common_random_numbers=True)
+    draws.lx[:, ::2] = 0.1                 # Langevin steps
+    draws.lx[:, 1::2] = 0.9                # random-walk steps
+    w0 = rs.randn(R, cfg.P) * 0.2
+    ref = oc.run_pt(cfg, tr, te, temps, w0, draws)
+    with _sampler(cfg, temps, memoize_gradient=memo) as s:
+        s.set_data(tr, te)
+        s.init_chains(w0)
+        assert s.replay(draws) == cfg.samples - 1
+        t = s.traces()
+    diff = np.argwhere(t["accepted"] != ref.accepted)
+    i_star = int(diff[:, 1].min()) - 1 if diff.size else cfg.samples - 1
+    if diff.size:                          # only a documented near-tie may differ
+        r, c = diff[np.argmin(diff[:, 1])]
+        lo, hi = sorted([t["mh_prob"][r, c], ref.mh_prob[r, c]])
+        assert lo - 1e-7 <= draws.u[r, c - 1] <= hi + 1e-7
+    rows = slice(1, i_star + 2)
+    assert cm.relerr(t["lik_prop"][:, rows], ref.lik_prop[:, rows]) < RTOL
+    assert cm.relerr(t["prior_prop"][:, rows], ref.prior_prop[:, rows]) < RTOL
+    assert np.max(np.abs(t["diff_prop"][:, rows] - ref.diff_prop[:, rows])) < RTOL * cfg.P
+    assert cm.relerr(t["pos_w"][:, :i_star + 1], ref.pos_w[:, :i_star + 1]) < RTOL
+    assert i_star >= 4
