@@ -744,24 +744,48 @@ static int op_prepare(int device, int task, int I, int H, int O, const double *d
     return PTFNN_OK;
 }
 
+// data set (padded row-major x[rows][IP]) -> UMMA A tiles of the tcgen05 likelihood pass (K5)
+static int pack_a_tiles(ptfnn_sampler *s, const KernelSet *ks, const float *x, int rows, int IP, DevBuf<float> &tiles, cudaStream_t st) {
+    const size_t ntiles = ((size_t)rows + 127) / 128;
+    CU_TRY(s, tiles.ensure(ntiles * (size_t)ks->a_tile_floats));
+    int n = rows, ip = IP; float *tp = tiles.p;
+    void *args[] = {&x, &n, &ip, &tp};
+    const unsigned blocks = (unsigned)std::min<size_t>(1024, (ntiles * 128 * 16 + 255) / 256);
+    CU_TRY(s, cudaLaunchKernel(ks->pack_a, dim3(blocks), dim3(256), args, 0, st));
+    CU_TRY(s, cudaGetLastError());
+    return PTFNN_OK;
+}
+
 static int op_forward(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
                       const double *w, double *fx, double *prob, double sums[3]) {
     const KernelSet *ks;
     OpData od;
     int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od);
     if (rc) { od.release(); return rc; }
-    const int P = I * H + H * O + H + O;
+    const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
     DevBuf<float> d_fx, d_prob;
     DevBuf<double> d_sums;
     CU_TRY(nullptr, d_fx.ensure(rows)); CU_TRY(nullptr, d_sums.ensure(3));
     if (prob) CU_TRY(nullptr, d_prob.ensure((size_t)rows * O));
     DataView v{od.x.p, od.y.p, rows};
     const float *wp = od.w.p; float *fxp = d_fx.p; float *pp = prob ? d_prob.p : nullptr; double *sp = d_sums.p;
-    void *args[] = {&wp, &v, &fxp, &pp, &sp};
-    const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
-    CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_TRY(nullptr, cudaLaunchKernel(ks->fwd, dim3(1), dim3(ks->NT), args, smem, 0));
+    DevBuf<float> d_tiles;
+    if (ks->fwd_tc) {
+        // K5: wide-hidden nets go through the tcgen05 path (data set -> UMMA A tiles -> tensor-core forward)
+        int rc2 = pack_a_tiles(nullptr, ks, od.x.p, rows, IP, d_tiles, 0);
+        if (rc2) { od.release(); d_fx.release(); d_prob.release(); d_sums.release(); d_tiles.release(); return rc2; }
+        const float *tp = d_tiles.p, *yp = od.y.p; int n = rows;
+        void *args[] = {&wp, &tp, &yp, &n, &fxp, &pp, &sp};
+        CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ks->tc_smem_bytes));
+        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd_tc, dim3(1), dim3(ks->NT), args, (size_t)ks->tc_smem_bytes, 0));
+    } else {
+        void *args[] = {&wp, &v, &fxp, &pp, &sp};
+        const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
+        CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd, dim3(1), dim3(ks->NT), args, smem, 0));
+    }
     CU_TRY(nullptr, cudaDeviceSynchronize());
+    d_tiles.release();
     if (fx) {
         std::vector<float> t(rows);
         CU_TRY(nullptr, cudaMemcpy(t.data(), d_fx.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));

@@ -1089,6 +1089,17 @@ __device__ __forceinline__ void lik_fast(const float *__restrict__ lw, const flo
     else lik_fast_impl<I, H, O, TASK, 1>(lw, w, d, t, nt, s0, s1, correct);
 }
 
+}  // namespace ptfnn
+#include "ptfnn_tc.cuh"
+namespace ptfnn {
+
+// K5 applies to the wide-hidden specialisations whose geometry matches the tcgen05 tile (M = 128 rows,
+// N = H = 256 accumulator columns, two epilogue warps per TMEM lane quadrant)
+template <int I, int H, int O, int NT>
+struct UseTc {
+    static constexpr bool value = (H == 256 && NT == 256 && (O % 2) == 0 && ((H * O) % 4) == 0);
+};
+
 // ==========================================================================================
 // K3 + K4: the persistent chain kernel
 // ==========================================================================================
@@ -1679,6 +1690,29 @@ __global__ void __launch_bounds__(UseSgdTeam<H>::value ? NT : 32) op_sgd_kernel(
         __syncthreads();
     }
     for (int j = threadIdx.x; j < P; j += blockDim.x) w_out[j] = s_w[j];
+}
+
+// K5 as a single operation (one CTA): evaluate_proposal / likelihood_func of a wide-hidden net on the
+// tensor cores.  tiles = A tiles of the data (tc::pack_a_kernel).
+template <int I, int H, int O, int TASK, int NT>
+__global__ void __launch_bounds__(NT) op_forward_tc_kernel(const float *w, const float *tiles, const float *y, int n,
+                                                           float *fx, float *prob, double *sums) {
+    if constexpr (UseTc<I, H, O, NT>::value) {
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        __shared__ double s_red[3 * (NT / 32)];
+        tc::State st;
+        tc::setup<I, H, O>(smem_raw, st);
+        tc::build_b<I, H, O>(smem_raw, w, threadIdx.x, NT);
+        tc::fence_async_smem();
+        __syncthreads();
+        double s[3] = {0.0, 0.0, 0.0};
+        int c = 0;
+        tc::lik_pass<I, H, O, TASK, NT, true>(smem_raw, st, tiles, y, n, w, s[0], s[1], c, fx, prob);
+        s[2] = (double)c;
+        block_sum<3, NT>(s, s_red);
+        if (threadIdx.x == 0) { sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2]; }
+        tc::teardown<I, H, O>(st);
+    }
 }
 
 }  // namespace ptfnn

@@ -11,6 +11,7 @@
 using namespace ptfnn;
 
 const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
+    constexpr bool kTc = UseTc<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_NT>::value;
     static const PtfnnKernelSet ks = {
         PTFNN_STR(PTFNN_T_NAME), PTFNN_T_TASK, PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_NT,
         (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT, PTFNN_T_MINB>,
@@ -18,6 +19,9 @@ const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
         (const void *)op_forward_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         ptfnn::UseSgdTeam<PTFNN_T_H>::value ? PTFNN_T_NT : 32,
+        kTc ? (const void *)op_forward_tc_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT> : nullptr,
+        kTc ? (const void *)tc::pack_a_kernel<PTFNN_T_I> : nullptr,
+        tc::a_tile_floats(PTFNN_T_I), tc::tc_smem_bytes(PTFNN_T_I, PTFNN_T_H, PTFNN_T_O),
     };
     return &ks;
 }
