@@ -94,7 +94,8 @@ struct ptfnn_sampler {
     int P = 0, IP = 0;
     int swap_rule = 0;
     cudaStream_t stream = nullptr;
-    int num_sms = 0;
+    int num_sms = 0, regs_per_sm = 0, threads_per_sm = 0;
+    size_t smem_per_sm = 0;
     std::string err;
 
     bool have_data = false, have_state = false;
@@ -106,6 +107,7 @@ struct ptfnn_sampler {
     std::vector<int> host_swap_log_round;
 
     DevBuf<float> train_x, train_y, test_x, test_y;
+    DevBuf<float> a_train, a_test;                    // K5: UMMA A tiles of the data sets (wide-hidden topologies)
     DevBuf<double> temperature;
     DevBuf<float> w, gd_cache, pgd_buf, pos_w, pub_rows;
     DevBuf<double> eta, tau, lik, prior, last4, init_rmse, pub_lhood;
@@ -120,7 +122,7 @@ struct ptfnn_sampler {
     DevBuf<double> d_scratch;
 
     void release_all() {
-        train_x.release(); train_y.release(); test_x.release(); test_y.release(); temperature.release();
+        train_x.release(); train_y.release(); test_x.release(); test_y.release(); a_train.release(); a_test.release(); temperature.release();
         w.release(); gd_cache.release(); pgd_buf.release(); pos_w.release(); pub_rows.release();
         eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
         pub_lhood.release(); lik_prop.release(); rmse_tr.release(); rmse_te.release(); acc_tr.release();
@@ -237,6 +239,8 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
     if (e != cudaSuccess) { rc = fail(nullptr, PTFNN_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); delete s; return rc; }
     s->num_sms = prop.multiProcessorCount;
+    s->regs_per_sm = prop.regsPerMultiprocessor; s->threads_per_sm = prop.maxThreadsPerMultiProcessor;
+    s->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (!prop.cooperativeLaunch) { rc = fail(nullptr, PTFNN_E_CUDA, "device lacks cooperative launch"); delete s; return rc; }
 
     const size_t R = cfg->n_replicas, S = cfg->samples, P = s->P;
@@ -281,6 +285,8 @@ extern "C" int ptfnn_set_stream(ptfnn_sampler *s, void *cuda_stream) {
     return PTFNN_OK;
 }
 
+static int pack_a_tiles(ptfnn_sampler *s, const KernelSet *ks, const float *x, int rows, int IP, DevBuf<float> &tiles, cudaStream_t st);
+
 // row-major float64 [rows, n_cols] -> padded float32 X [rows][IP] + y [pad4(rows)]
 static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP, std::vector<float> &x,
                          std::vector<float> &y) {
@@ -310,6 +316,12 @@ extern "C" int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_t
     CU_TRY(s, cudaMemcpyAsync(s->test_y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice, s->stream));
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     s->n_train = n_train; s->n_test = n_test;
+    if (s->ks->fwd_tc) {
+        int rc = pack_a_tiles(s, s->ks, s->train_x.p, n_train, s->IP, s->a_train, s->stream);
+        if (!rc) rc = pack_a_tiles(s, s->ks, s->test_x.p, n_test, s->IP, s->a_test, s->stream);
+        if (rc) return rc;
+        CU_TRY(s, cudaStreamSynchronize(s->stream));
+    }
     s->have_data = true;
     return PTFNN_OK;
 }
@@ -460,6 +472,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.temperature = s->temperature.p;
     p.train = view(s->train_x, s->train_y, s->n_train);
     p.test = view(s->test_x, s->test_y, s->n_test);
+    p.a_train = s->a_train.p; p.a_test = s->a_test.p;
     p.w = s->w.p; p.eta = s->eta.p; p.tau = s->tau.p; p.lik = s->lik.p; p.prior = s->prior.p;
     p.n_acc = s->n_acc.p; p.init_count = s->init_count.p; p.last4 = s->last4.p;
     p.gd_cache = s->gd_cache.p; p.pgd_buf = s->pgd_buf.p; p.gd_valid = s->gd_valid.p;
@@ -499,18 +512,42 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
     const int team_floats = c.n_hidden > 64 ? team_smem_floats(c.n_hidden, c.n_out) : 0;   // mirrors UseSgdTeam<H>
     const int lik_floats = c.n_hidden * ((c.n_in + 1 + c.n_out + 3) & ~3);   // mirrors LikLayout<I, O>::LW
-    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats, team_floats == 0);
+    const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats, team_floats == 0,
+                                          s->ks->fwd_tc ? s->ks->tc_smem_bytes : 0, s->ks->tc_alias_off);
     if (L.total > 227 * 1024) return fail(s, PTFNN_E_UNSUPPORTED, "needs %zu bytes of shared memory per CTA (> 227 KB)", L.total);
     CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    CU_TRY(s, cudaFuncSetAttribute(s->ks->chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     CU_TRY(s, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->ks->chain, NT, L.total));
     if (per_sm < 1) return fail(s, PTFNN_E_CUDA, "chain kernel does not fit on an SM (smem %zu)", L.total);
+    const bool uses_tmem = s->ks->fwd_tc != nullptr;
+    if (uses_tmem) {
+        // The occupancy calculator answers 1 for every kernel that executes tcgen05.alloc, although the
+        // hardware co-schedules CTAs as long as their TMEM columns fit (tools/occ_probe.cu: two CTAs of
+        // 256 columns per SM).  Count the resources ourselves; such kernels are launched without the
+        // cooperative-launch check (the grid barrier has a time-out instead of a co-residency proof).
+        cudaFuncAttributes fa;
+        CU_TRY(s, cudaFuncGetAttributes(&fa, s->ks->chain));
+        const int regs = ((fa.numRegs + 7) / 8) * 8;
+        const int by_regs = s->regs_per_sm / std::max(1, regs * NT);
+        const int by_smem = (int)(s->smem_per_sm / (L.total + fa.sharedSizeBytes + 1024));
+        const int by_thr = s->threads_per_sm / NT;
+        const int by_tmem = 512 / c.n_hidden;
+        per_sm = std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_thr, by_tmem)));
+    }
     const int grid = std::min(R, per_sm * s->num_sms);
+    if (getenv("PTFNN_DEBUG")) {
+        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, s->ks->chain);
+        int o2 = 0, o3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, s->ks->chain, NT, 90000); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, s->ks->chain, NT, 0);
+        fprintf(stderr, "[ptfnn] regs %d static smem %zu local %zu maxdyn %d; occ@90000=%d occ@0=%d\n", fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, o2, o3);
+    }
+    if (getenv("PTFNN_DEBUG")) fprintf(stderr, "[ptfnn] chain launch: smem %zu B, %d CTAs/SM, grid %d, threads %d\n", L.total, per_sm, grid, NT);
     // many temperatures per SM: keep the serial warps' sub-partitions quiet (see chain_kernel)
     p.lik_team_warps = 0;
     if (const char *e = getenv("PTFNN_LIK_TEAM_WARPS")) p.lik_team_warps = atoi(e);
     void *args[] = {&p};
-    CU_TRY(s, cudaLaunchCooperativeKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
+    if (uses_tmem) CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
+    else CU_TRY(s, cudaLaunchCooperativeKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());
     s->step = end;
     if (external) {
@@ -533,11 +570,19 @@ extern "C" int ptfnn_replay(ptfnn_sampler *s, const ptfnn_draws *d, int32_t *ste
     return launch_chain(s, d->n, d, steps_done);
 }
 
+// stream synchronisation + the device-side failure flag of the grid barrier
+static int sync_and_check(ptfnn_sampler *s) {
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    GridBarrier b;
+    CU_TRY(s, cudaMemcpy(&b, s->barrier.p, sizeof b, cudaMemcpyDeviceToHost));
+    if (b.failed) return fail(s, PTFNN_E_CUDA, "swap-round grid barrier timed out: the temperatures of one launch were not co-resident on the device");
+    return PTFNN_OK;
+}
+
 extern "C" int ptfnn_sync(ptfnn_sampler *s) {
     if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
     CU_TRY(s, cudaSetDevice(s->cfg.device));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
-    return PTFNN_OK;
+    return sync_and_check(s);
 }
 
 extern "C" int ptfnn_generate_draws(ptfnn_sampler *s, int32_t i0, int32_t n, float *lx, float *z, float *z_eta, float *u) {
@@ -585,8 +630,8 @@ extern "C" int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, 
     if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
     if (first < 0 || count < 1 || first + count > s->cfg.samples) return fail(s, PTFNN_E_INVALID, "rows [%d,%d) outside [0,%d)", first, first + count, s->cfg.samples);
     CU_TRY(s, cudaSetDevice(s->cfg.device));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
-    int rc = 0;
+    int rc = sync_and_check(s);
+    if (rc) return rc;
     if (t->pos_w && (rc = fetch_rows(s, s->pos_w.p, s->P, first, count, t->pos_w))) return rc;
     if (t->lik_prop && (rc = fetch_rows(s, s->lik_prop.p, 1, first, count, t->lik_prop))) return rc;
     if (t->rmse_train && (rc = fetch_rows(s, s->rmse_tr.p, 1, first, count, t->rmse_train))) return rc;

@@ -254,7 +254,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 struct GridBarrier {
     unsigned int count;
     unsigned int generation;
+    unsigned int failed;      // set when a CTA gave up waiting (the grid was not co-resident): reported by the host
+    unsigned int pad;
 };
+constexpr long long kBarrierTimeoutCycles = 1ll << 35;   // ~17 s: far above any legitimate skew between CTAs
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
@@ -272,7 +275,11 @@ __device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblock
             __threadfence();
             atomicAdd(&b->generation, 1u);
         } else {
-            while (ld_acquire_u32(&b->generation) == gen) __nanosleep(32);
+            const long long t0 = clock64();
+            while (ld_acquire_u32(&b->generation) == gen) {
+                __nanosleep(32);
+                if (clock64() - t0 > kBarrierTimeoutCycles) { atomicExch(&b->failed, 1u); break; }   // never hang the device
+            }
         }
         __threadfence();
     }

@@ -1119,6 +1119,7 @@ struct ChainParams {
     const double *temperature;     // [R]
     // ---- data
     DataView train, test;
+    const float *a_train, *a_test; // K5: UMMA A tiles of the two data sets (tc::pack_a_kernel), else 0
     // ---- chain state (global, one row per local replica)
     float *w;                      // [R][P]
     double *eta, *tau, *lik, *prior;
@@ -1169,20 +1170,25 @@ struct ChainSmem {
 };
 __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, int Rg, bool staged, int n_train,
                                                        int n_test, int team_floats = 0, int lik_floats = 0,
-                                                       bool gd_in_smem = true) {
+                                                       bool gd_in_smem = true, int tc_bytes = 0, int tc_alias_off = 0) {
     ChainSmem L;
     L.P4 = (P + 3) & ~3;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    L.off_w = take(L.P4 * 4); L.off_prop = take(L.P4 * 4);
+    // K5 topologies (tc_bytes > 0): the state vector stays in its global row, the likelihood layout is
+    // replaced by the tcgen05 operands, and the SGD pass's TMA tiles + team scratch alias the A tile
+    // (the two passes never overlap in time)
+    const bool tc = tc_bytes > 0;
+    L.off_w = take(tc ? 0 : L.P4 * 4); L.off_prop = take(L.P4 * 4);
     // langevin_gradient(w) and langevin_gradient(w_prop): shared memory, or (wide nets) the replica's global rows
     L.off_gd = take(gd_in_smem ? L.P4 * 4 : 0); L.off_pgd = take(gd_in_smem ? L.P4 * 4 : 0);
-    L.off_lw = take((size_t)lik_floats * 4);   // likelihood layout of the proposal (LikLayout)
+    L.off_lw = take(tc ? (size_t)tc_bytes : (size_t)lik_floats * 4);   // likelihood layout of the proposal (LikLayout) | tc::Smem
     L.off_red = take((size_t)8 * (nt / 32) * 8);
     L.off_bar = take(8 * 4);
-    L.off_tiles = take(staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4));
+    const size_t tile_bytes = staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4);
+    L.off_tiles = tc ? L.off_lw + tc_alias_off : take(tile_bytes);
     L.off_sweep = take(Rg > 1 ? (size_t)kSweepChunk * 8 : 0);   // one chunk of lhood fields for the streaming sweep
-    L.off_team = take((size_t)team_floats * 4);
+    L.off_team = tc ? L.off_tiles + ((tile_bytes + 15) & ~(size_t)15) : take((size_t)team_floats * 4);
     auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
     L.off_stage = take(staged ? ((size_t)n_train * IP + pad4(n_train) + (size_t)n_test * IP + pad4(n_test)) * 4 : 0);
     L.total = o;
@@ -1259,8 +1265,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool TEAM = UseSgdTeam<H>::value;
+    constexpr bool TC = UseTc<I, H, O, NT>::value;              // K5: tcgen05 likelihood pass
+    static_assert(!TC || TEAM, "the tcgen05 path belongs to the wide-hidden team topologies");
     const ChainSmem L = chain_smem_layout(P, IP, NT, p.external_swap ? 1 : p.Rg, p.staged != 0, p.train.n, p.test.n, TEAM ? team_smem_floats(H, O) : 0,
-                                          H * LikLayout<I, O>::LW, !TEAM);
+                                          H * LikLayout<I, O>::LW, !TEAM, TC ? tc::Smem<I, H, O>::total : 0, tc::Smem<I, H, O>::off_a);
+    unsigned char *s_tc = smem_raw + L.off_lw;
     float *s_lw = reinterpret_cast<float *>(smem_raw + L.off_lw);
     float *s_team = reinterpret_cast<float *>(smem_raw + L.off_team);
     float *s_w = reinterpret_cast<float *>(smem_raw + L.off_w);
@@ -1308,6 +1317,19 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         stream.bar0 = &s_bar[0]; stream.bar1 = &s_bar[1];
     }
     stream.parity0 = stream.parity1 = 0u;
+    tc::State tcst;
+    if constexpr (TC) tc::setup<I, H, O>(s_tc, tcst);            // TMEM: 256 columns per CTA, two CTAs per SM
+    // likelihood sums of weight vector wv on both data sets (K5 path)
+    auto tc_likelihood = [&](const float *wv, bool with_test, double &a0, double &a1, int &c0, double &b0, double &b1, int &c1) {
+        if constexpr (TC) {
+            tc::build_b<I, H, O>(s_tc, wv, tid, NT);
+            tc::fence_async_smem();
+            __syncthreads();
+            tc::lik_pass<I, H, O, TASK, NT, false>(s_tc, tcst, p.a_train, train.y, train.n, wv, a0, a1, c0, nullptr, nullptr);
+            if (with_test)
+                tc::lik_pass<I, H, O, TASK, NT, false>(s_tc, tcst, p.a_test, test.y, test.n, wv, b0, b1, c1, nullptr, nullptr);
+        }
+    };
 
     // ---- which warp runs the serial recurrence.  Warps are bound to one of the SM's four
     // sub-partitions (hardware warp slot % 4); co-resident CTAs would otherwise all put their
@@ -1343,8 +1365,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         for (int r = blockIdx.x; r < p.R; r += nblocks) {
             // ---------------- load this replica's state ----------------
             if constexpr (TEAM) { s_gd = p.gd_cache + (size_t)r * P; s_pgd = p.pgd_buf + (size_t)r * P; }
+            if constexpr (TC) s_w = p.w + (size_t)r * P;             // the state vector stays in its global row
             for (int j = tid; j < P; j += NT) {
-                s_w[j] = p.w[(size_t)r * P + j];
+                if constexpr (!TC) s_w[j] = p.w[(size_t)r * P + j];
                 if constexpr (!TEAM) s_gd[j] = p.gd_cache[(size_t)r * P + j];
             }
             double eta = p.eta[r], tau = p.tau[r], lik = p.lik[r], prior_cur = p.prior[r];
@@ -1366,9 +1389,19 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     double s[2] = {0.0, 0.0};
                     double dummy = 0.0;
                     int c0 = 0;
-                    lik_prepare<I, H, O>(s_lw, s_w, tid, NT);
-                    __syncthreads();
-                    lik_fast<I, H, O, TASK>(s_lw, s_w, train, tid, NT, s[0], dummy, c0);
+                    if constexpr (TC) {
+                        // through s_prop (dead at this point): the epilogue reads the output layer with
+                        // 16-byte loads and the global rows of w are only 8-byte aligned for odd P
+                        for (int j = tid; j < P; j += NT) s_prop[j] = s_w[j];
+                        __syncthreads();
+                        double d2 = 0.0, d3 = 0.0;
+                        int c1 = 0;
+                        tc_likelihood(s_prop, false, s[0], dummy, c0, d2, d3, c1);
+                    } else {
+                        lik_prepare<I, H, O>(s_lw, s_w, tid, NT);
+                        __syncthreads();
+                        lik_fast<I, H, O, TASK>(s_lw, s_w, train, tid, NT, s[0], dummy, c0);
+                    }
                     block_sum<2, NT>(s, s_red);
                     if constexpr (TASK == kTaskReg)
                         lik = (-0.5 * train.n * log(2.0 * 3.14159265358979323846 * tau) - 0.5 * s[0] / tau) / adapt;
@@ -1403,7 +1436,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                         for (int j = tid; j < P; j += NT) {
                             const float v = fmaf(p.step_w, zz[j], base[j]);
                             s_prop[j] = v;
-                            lik_scatter<I, H, O>(s_lw, j, v);
+                            if constexpr (!TC) lik_scatter<I, H, O>(s_lw, j, v);
                         }
                     } else {
                         for (int b = tid; b < (P + 3) / 4; b += NT) {
@@ -1415,7 +1448,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                                 if (j < P) {
                                     const float v = fmaf(p.step_w, z4[k], base[j]);
                                     s_prop[j] = v;
-                                    lik_scatter<I, H, O>(s_lw, j, v);
+                                    if constexpr (!TC) lik_scatter<I, H, O>(s_lw, j, v);
                                 }
                             }
                         }
@@ -1446,8 +1479,12 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                         else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
-                    lik_fast<I, H, O, TASK>(s_lw, s_prop, train, tid, NT, s[0], s[1], c_tr);
-                    lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, s[2], s[3], c_te);
+                    if constexpr (TC) {
+                        tc_likelihood(s_prop, true, s[0], s[1], c_tr, s[2], s[3], c_te);
+                    } else {
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, train, tid, NT, s[0], s[1], c_tr);
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, s[2], s[3], c_te);
+                    }
                 }
                 __syncthreads();
                 // ---- reductions: likelihood sums, |w_prop|^2 (prior), Langevin asymmetry norms
@@ -1539,7 +1576,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             }
             // ---------------- store state ----------------
             for (int j = tid; j < P; j += NT) {
-                p.w[(size_t)r * P + j] = s_w[j];
+                if constexpr (!TC) p.w[(size_t)r * P + j] = s_w[j];
                 if constexpr (!TEAM) { if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
             }
             if (tid == 0) {
@@ -1570,6 +1607,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         grid_barrier(p.barrier, nblocks);
         if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nblocks);
     }
+    if constexpr (TC) tc::teardown<I, H, O>(tcst);
 }
 
 // ==========================================================================================

@@ -7,5 +7,5 @@ struct PtfnnKernelSet {
     int sgd_threads;   // 32, or NT when the wide-hidden team variant is used
     const void *fwd_tc;   // K5: tcgen05 forward / likelihood of wide-hidden nets (0 = not applicable)
     const void *pack_a;   // data set -> UMMA A tiles for fwd_tc and the chain kernel
-    int a_tile_floats, tc_smem_bytes;
+    int a_tile_floats, tc_smem_bytes, tc_alias_off;
 };

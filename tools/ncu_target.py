@@ -9,7 +9,10 @@ from ptnn_b200.sampler import Sampler, geometric_ladder
 from oracle import ptfnn_numpy as on
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "synth_ts"
-if wl == "synth_ts":
+task = 0
+if wl == "pendigit":
+    tr, te = datasets.synthetic_pendigit(); topo, R, lr, n, task = (16, 256, 10), 256, 0.01, 1, 1
+elif wl == "synth_ts":
     tr, te = datasets.synthetic_timeseries(); topo, R, lr, n = (4, 64, 1), 1024, 0.01, 2
 else:
     d = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "datasets.npz"))
@@ -17,7 +20,7 @@ else:
 R = int(sys.argv[2]) if len(sys.argv) > 2 else R
 n = int(sys.argv[3]) if len(sys.argv) > 3 else n
 S = 4 * n + 2
-s = Sampler(0, topo, geometric_ladder(R, 2), S, 10 ** 6, learn_rate=lr, memoize_gradient=0)
+s = Sampler(task, topo, geometric_ladder(R, 2), S, 10 ** 6, learn_rate=lr, memoize_gradient=0)
 s.set_data(tr, te)
 s.init_chains(np.random.RandomState(1).randn(R, s.P))
 lx, z, ze, u = s.generate_draws(0, S - 1)
