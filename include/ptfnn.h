@@ -168,6 +168,17 @@ int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total_swa
  * (R:741-748) with the same device code every rank and returns src[k] = ladder slot whose vector
  * ends up in slot k.  Rows whose source is remote are received into rows_in (same shape as
  * rows_local, indexed by local destination slot); ptfnn_swap_apply installs them. */
+/* The same round completed on the device over peer memory (NVLink / NVSwitch), no host round trip:
+ * each rank exports the CUDA IPC handles of its swap window once (ptfnn_peer_export), the handles of
+ * all ranks are exchanged by the caller (e.g. torch.distributed.all_gather_object) and handed to
+ * ptfnn_peer_connect.  Afterwards ptfnn_run / ptfnn_replay advance through swap rounds like the
+ * single-GPU kernel does; every rank must request the same number of steps.  Replaces the reference's
+ * parameter queues and events between processes (R:427-437, R:730-752). */
+#define PTFNN_PEER_HANDLE_BYTES 64
+int ptfnn_peer_export(ptfnn_sampler *s, void *handles /* [3][PTFNN_PEER_HANDLE_BYTES] */);
+int ptfnn_peer_connect(ptfnn_sampler *s, int32_t n_ranks, int32_t rank,
+                       const void *handles /* [n_ranks][3][PTFNN_PEER_HANDLE_BYTES], rank order */);
+
 int ptfnn_swap_pending(const ptfnn_sampler *s, int32_t *pending, int32_t *is_final_round);
 int ptfnn_swap_export(ptfnn_sampler *s, void *lhood_local_dev, void *rows_local_dev);
 int ptfnn_swap_plan(ptfnn_sampler *s, const void *lhood_global_dev, const float *u_row /* host, NULL = Philox */,

@@ -17,6 +17,7 @@ OK, E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4, -5
 TASK_REGRESSION, TASK_CLASSIFICATION = 0, 1
 SWAP_RULE_AUTO, SWAP_RULE_AFTER_I, SWAP_RULE_BEFORE_I1 = -1, 0, 1
 ABI_VERSION = 1
+PEER_HANDLE_BYTES = 64       # cudaIpcMemHandle_t
 
 # every symbol include/ptfnn.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
@@ -25,6 +26,7 @@ SYMBOLS = [
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
     "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
+    "ptfnn_peer_export", "ptfnn_peer_connect",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
     "ptfnn_op_swap_sweep",
 ]

@@ -115,6 +115,11 @@ struct ptfnn_sampler {
     DevBuf<int> n_acc, init_count, gd_valid, accept_list;
     DevBuf<uint8_t> dbg_acc, swap_log;
     DevBuf<GridBarrier> barrier;
+    // multi-GPU ladder through peer memory (ptfnn_peer_connect)
+    DevBuf<unsigned int> peer_flags;                  // [kMaxPeers] rounds published by each rank
+    int n_ranks = 1, rank = 0;
+    void *peer_lhood[kMaxPeers] = {}, *peer_rows[kMaxPeers] = {}, *peer_flag_ptr[kMaxPeers] = {};
+    bool peer_opened[kMaxPeers][3] = {};
     DevBuf<long long> swap_counters;
     DevBuf<float> d_lx, d_z, d_zeta, d_u, d_uswap;   // replay staging
     DevBuf<int> d_src, smsp_load, swap_src;
@@ -128,6 +133,13 @@ struct ptfnn_sampler {
         pub_lhood.release(); lik_prop.release(); rmse_tr.release(); rmse_te.release(); acc_tr.release();
         acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
         init_count.release(); gd_valid.release(); accept_list.release(); dbg_acc.release(); swap_log.release();
+        for (int q = 0; q < kMaxPeers; ++q) {
+            if (peer_opened[q][0]) cudaIpcCloseMemHandle(peer_lhood[q]);
+            if (peer_opened[q][1]) cudaIpcCloseMemHandle(peer_rows[q]);
+            if (peer_opened[q][2]) cudaIpcCloseMemHandle(peer_flag_ptr[q]);
+            peer_opened[q][0] = peer_opened[q][1] = peer_opened[q][2] = false;
+        }
+        peer_flags.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
         d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release();
     }
@@ -256,11 +268,12 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
-    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2);
+    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, kMaxPeers);
     ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(swap_src, R); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
+    cudaMemset(s->peer_flags.p, 0, kMaxPeers * sizeof(unsigned int));
     cudaMemset(s->smsp_load.p, 0, s->smsp_load.n * sizeof(int));
     cudaMemset(s->swap_counters.p, 0, 2 * sizeof(long long));
     cudaMemset(s->swap_log.p, 0, s->swap_log.n);
@@ -443,7 +456,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     CU_TRY(s, cudaSetDevice(s->cfg.device));
     const ptfnn_config &c = s->cfg;
     const int R = c.n_replicas, Rg = c.n_replicas_global, S = c.samples, P = s->P;
-    const bool external = Rg > R;
+    const bool external = Rg > R && s->n_ranks == 1;   // host-completed rounds unless the ranks are peer-connected
     int n = std::min(n_steps, S - 1 - s->step);
     if (n <= 0) return PTFNN_OK;
     // multi-GPU: stop right after the first step at which a swap is due
@@ -483,6 +496,11 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.swap_counters = s->swap_counters.p; p.swap_log = s->swap_log.p;
     p.max_rounds = (int)(s->swap_log.n / std::max(Rg - 1, 1));
     p.smsp_load = s->smsp_load.p;
+    p.n_ranks = s->n_ranks; p.rank = s->rank;
+    for (int q = 0; q < kMaxPeers; ++q) {
+        p.peer_lhood[q] = (double *)s->peer_lhood[q]; p.peer_rows[q] = (const float *)s->peer_rows[q];
+        p.peer_flags[q] = (unsigned int *)s->peer_flag_ptr[q];
+    }
     p.swap_src = s->swap_src.p;
     p.P = P;
 
@@ -753,6 +771,46 @@ extern "C" int ptfnn_swap_apply(ptfnn_sampler *s, const int32_t *src, const void
     s->swap_pending = false;
     // the chain may have ended on a swap step: the coordinator's left-over round is still due (Q9)
     if (s->step == s->cfg.samples - 1 && s->rounds_done < h_total_rounds(s)) { s->swap_pending = true; s->pending_final = true; }
+    return PTFNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU swap round through peer memory: the ranks exchange CUDA IPC handles of their swap windows
+// once; afterwards the persistent kernel completes every round on the device (chain_kernel:
+// peer_exchange_lhood + chain_sweep), with no host round trip and no collective call.
+// ------------------------------------------------------------------------------------------
+extern "C" int ptfnn_peer_export(ptfnn_sampler *s, void *handles /* 3 x 64 bytes */) {
+    if (!s || !handles) return fail(s, PTFNN_E_INVALID, "null argument");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == PTFNN_PEER_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h[3];
+    CU_TRY(s, cudaIpcGetMemHandle(&h[0], s->pub_lhood.p));
+    CU_TRY(s, cudaIpcGetMemHandle(&h[1], s->pub_rows.p));
+    CU_TRY(s, cudaIpcGetMemHandle(&h[2], s->peer_flags.p));
+    memcpy(handles, h, sizeof h);
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_peer_connect(ptfnn_sampler *s, int32_t n_ranks, int32_t rank, const void *handles /* n_ranks x 3 x 64 bytes */) {
+    if (!s || !handles) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks) return fail(s, PTFNN_E_INVALID, "n_ranks %d (max %d), rank %d", n_ranks, kMaxPeers, rank);
+    const int R = s->cfg.n_replicas, Rg = s->cfg.n_replicas_global;
+    if (Rg != R * n_ranks || s->cfg.replica_offset != rank * R) return fail(s, PTFNN_E_INVALID, "peer mode needs equal contiguous blocks: Rg %d = %d ranks x %d, offset %d", Rg, n_ranks, R, s->cfg.replica_offset);
+    if (s->step != 0) return fail(s, PTFNN_E_STATE, "connect the ranks before the first step");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+    for (int q = 0; q < n_ranks; ++q) {
+        if (q == rank) {
+            s->peer_lhood[q] = s->pub_lhood.p; s->peer_rows[q] = s->pub_rows.p; s->peer_flag_ptr[q] = s->peer_flags.p;
+            continue;
+        }
+        void **dst[3] = {&s->peer_lhood[q], &s->peer_rows[q], &s->peer_flag_ptr[q]};
+        for (int k = 0; k < 3; ++k) {
+            CU_TRY(s, cudaIpcOpenMemHandle(dst[k], h[q * 3 + k], cudaIpcMemLazyEnablePeerAccess));
+            s->peer_opened[q][k] = true;
+        }
+    }
+    s->n_ranks = n_ranks; s->rank = rank;
     return PTFNN_OK;
 }
 

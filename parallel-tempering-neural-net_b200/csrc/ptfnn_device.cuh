@@ -287,6 +287,29 @@ __device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblock
 }
 
 // ------------------------------------------------------------------------------------------
+// peer memory (NVLink / NVSwitch): system-scope stores, loads and flags for the multi-GPU swap round
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys_f32(const float *p) {      // never served from a stale L1 line
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
 // swap rule (R:674): min(1, 0.5 * exp(min(709, l2 - l1))); sequential sweep (R:741-748).
 // One thread; lh/src live in shared memory.  Returns the number of accepted swaps.
 // ------------------------------------------------------------------------------------------

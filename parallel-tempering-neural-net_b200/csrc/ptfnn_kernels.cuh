@@ -1146,6 +1146,12 @@ struct ChainParams {
     int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
     int P;
     int lik_team_warps;            // warps per CTA that evaluate the likelihood while the serial warp runs (0 = all)
+    // ---- multi-GPU ladder through peer memory (n_ranks > 1): every rank's pub_lhood / pub_rows / peer_flags
+    //      are mapped into this process (CUDA IPC); entry q of the tables points at rank q's buffer
+    int n_ranks, rank;
+    double *peer_lhood[kMaxPeers];         // rank q's pub_lhood  [2][Rg]
+    const float *peer_rows[kMaxPeers];     // rank q's pub_rows   [2][R][P+1]
+    unsigned int *peer_flags[kMaxPeers];   // rank q's arrival flags [kMaxPeers]; flags[j] = rounds published by rank j
     int *smsp_load;                // [num_SMs] ticket counter used to spread serial (SGD) warps over the SM sub-partitions
 };
 
@@ -1248,12 +1254,54 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
     __syncthreads();
     if (!apply) return;
     for (int r = blockIdx.x; r < p.R; r += nblocks) {
-        const int src = p.swap_src[r] - p.replica_offset;
-        if (src != r) {
-            const float *row = p.pub_rows + ((size_t)parity * p.R + src) * (P + 1);
-            for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
-            if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
+        const int gsrc = p.swap_src[r];                       // global slot the vector comes from
+        if (gsrc != p.replica_offset + r) {
+            const int q = p.n_ranks > 1 ? gsrc / p.R : 0;     // equal contiguous blocks: owner rank of that slot
+            const int lsrc = gsrc - q * p.R - (p.n_ranks > 1 ? 0 : p.replica_offset);
+            if (p.n_ranks > 1 && q != p.rank) {               // the row lives on another GPU: pull it over NVLink
+                const float *row = p.peer_rows[q] + ((size_t)parity * p.R + lsrc) * (P + 1);
+                for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = ld_sys_f32(&row[j]);
+                if (tid == 0) { p.eta[r] = (double)ld_sys_f32(&row[P]); p.gd_valid[r] = 0; }
+            } else {
+                const float *row = p.pub_rows + ((size_t)parity * p.R + lsrc) * (P + 1);
+                for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
+                if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
+            }
         }
+    }
+    __syncthreads();
+}
+
+// Multi-GPU hand-shake of one swap round (replaces the reference's queues + events across processes,
+// R:427-437 / R:730-752, and a host round trip): after the local grid barrier (every local temperature
+// has published), block 0 PUSHES this rank's lhood fields into every peer's pub_lhood (8 bytes per
+// temperature over NVLink), raises its flag on every peer, and every CTA waits until the flags of all
+// ranks have reached this round.  The sweep then reads only local memory; (w, eta) rows are PULLED from
+// the owner's pub_rows by the CTA that needs them (in expectation the rows next to the rank boundaries).
+template <int NT>
+__device__ __forceinline__ void peer_exchange_lhood(const ChainParams &p, int round, int parity, GridBarrier *bar) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0) {
+        const double *mine = p.pub_lhood + (size_t)parity * p.Rg + p.replica_offset;
+        for (int q = 0; q < p.n_ranks; ++q) {
+            if (q == p.rank) continue;
+            double *dst = p.peer_lhood[q] + (size_t)parity * p.Rg + p.replica_offset;
+            for (int k = tid; k < p.R; k += NT) dst[k] = __ldcg(&mine[k]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < p.n_ranks) st_release_sys_u32(&p.peer_flags[tid][p.rank], (unsigned int)(round + 1));
+    }
+    if (tid == 0) {
+        const unsigned int *flags = p.peer_flags[p.rank];
+        const long long t0 = clock64();
+        for (int q = 0; q < p.n_ranks; ++q) {
+            while ((int)(ld_acquire_sys_u32(&flags[q]) - (unsigned int)(round + 1)) < 0) {
+                __nanosleep(64);
+                if (clock64() - t0 > kBarrierTimeoutCycles) { atomicExch(&bar->failed, 1u); break; }
+            }
+        }
+        __threadfence_system();
     }
     __syncthreads();
 }
@@ -1593,6 +1641,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             if (p.external_swap) break;   // multi-GPU: the host completes the round (ptfnn_swap_*)
             // ---------------- K4: swap round ----------------
             grid_barrier(p.barrier, nblocks);
+            if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
             chain_sweep<NT>(p, round, parity, /*apply=*/true, s_sweep, nblocks);
             __syncthreads();
             ++round;
@@ -1605,6 +1654,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         for (int r = blockIdx.x; r < p.R; r += nblocks)
             if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = p.lik[r];
         grid_barrier(p.barrier, nblocks);
+        if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
         if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nblocks);
     }
     if constexpr (TC) tc::teardown<I, H, O>(tcst);

@@ -10,6 +10,13 @@ R/G temperatures (ladder order = rank order) and the only communication is the s
      (P+1) float32 each -- in expectation the rows next to the G-1 rank boundaries
   4. install, continue.
 
+On GPUs that can map each other's memory (NVLink / NVSwitch, one box) steps 1-4 run INSIDE the
+persistent kernel (``peer=True``, the default of ``make_gpu_ladder``): the ranks exchange CUDA IPC
+handles of their swap windows once, then every round is a push of R/G lhood fields to the peers, a
+flag per rank, the sweep on local memory and a pull of the few rows that cross a rank boundary --
+no host round trip and no collective call (csrc/ptfnn_kernels.cuh: peer_exchange_lhood).  The
+host-completed round below stays as the portable path.
+
 ``PartitionedLadder`` holds that logic over an abstract ``chains`` object so that it is exercised
 on CPU with the gloo backend (tests/test_distributed_gloo.py, oracle-backed chains) and on GPUs
 with NCCL (``GpuChains`` over libptfnn).  The data path has no other collective.
@@ -114,6 +121,13 @@ class PartitionedLadder:
         """Advance every rank's block by up to ``n_steps`` steps, completing the swap rounds that fall
         due.  ``u_swap`` (replay): [rounds, Rg-1] indexed by absolute round number."""
         ch = self.chains
+        if getattr(ch, "peer", False):                   # rounds complete on the device
+            todo = ch.last_step - ch.step if n_steps is None else min(n_steps, ch.last_step - ch.step)
+            if draws is None:
+                return ch.s.run(todo)
+            from types import SimpleNamespace
+            return ch.s.replay(SimpleNamespace(lx=draws.lx, z=draws.z, z_eta=draws.z_eta, u=draws.u, u_swap=u_swap),
+                               n_steps=todo)
         todo = ch.last_step - ch.step if n_steps is None else min(n_steps, ch.last_step - ch.step)
         done = 0
         while done < todo:
@@ -131,8 +145,10 @@ class PartitionedLadder:
 
 
 def make_gpu_ladder(task, topology, temperatures_global, samples, swap_interval, *, group=None, device=None,
-                    **sampler_kw):
-    """One call per rank: builds the local Sampler for this rank's block and the exchange logic."""
+                    peer=True, **sampler_kw):
+    """One call per rank: builds the local Sampler for this rank's block and the exchange logic.
+    ``peer=True``: swap rounds complete on the device through peer memory (one box, NVLink);
+    ``peer=False``: the host completes them with all_gather + isend/irecv."""
     import torch
     import torch.distributed as dist
     from .sampler import Sampler
@@ -143,4 +159,11 @@ def make_gpu_ladder(task, topology, temperatures_global, samples, swap_interval,
     smp = Sampler(task, topology, temps[lo:lo + n], samples, swap_interval, n_replicas_global=len(temps),
                   replica_offset=lo, device=dev_index, **sampler_kw)
     chains = GpuChains(smp, torch.device("cuda", dev_index))
+    chains.peer = False
+    if peer and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, smp.peer_export(), group=group)
+        smp.peer_connect(handles, rank)
+        chains.peer = True
+        dist.barrier(group)                              # every rank has mapped every window
     return PartitionedLadder(chains, len(temps), lo, n, group), smp

@@ -200,7 +200,21 @@ class Sampler:
         self._ck(self._lib.ptfnn_get_swap_stats(self._h, C.byref(ns), C.byref(tot), capi.ptr(sw), rounds))
         return ns.value, tot.value, sw[:rounds, :self.Rg - 1].astype(bool)
 
-    # ---- multi-GPU round (device pointers come from torch tensors) ----
+    # ---- multi-GPU ladder through peer memory: rounds complete on the device ----
+    def peer_export(self) -> bytes:
+        """CUDA IPC handles of this rank's swap window (lhood fields, (w, eta) rows, arrival flags)."""
+        buf = C.create_string_buffer(3 * capi.PEER_HANDLE_BYTES)
+        self._ck(self._lib.ptfnn_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles, rank: int):
+        """handles: the peer_export() bytes of every rank, in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(handles)
+        if len(blob) != len(handles) * 3 * capi.PEER_HANDLE_BYTES:
+            raise ValueError("each rank contributes %d bytes of IPC handles" % (3 * capi.PEER_HANDLE_BYTES))
+        self._ck(self._lib.ptfnn_peer_connect(self._h, len(handles), int(rank), C.c_char_p(blob)))
+
+    # ---- multi-GPU round completed by the host (device pointers come from torch tensors) ----
     def swap_pending(self):
         p, f = C.c_int32(), C.c_int32()
         self._ck(self._lib.ptfnn_swap_pending(self._h, C.byref(p), C.byref(f)))

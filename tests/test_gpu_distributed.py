@@ -1,5 +1,6 @@
 """GPU (needs >= 2 devices; skipped otherwise): ladder partitioned over ranks == single-GPU run,
-bit for bit, in replay mode and in free-running (Philox) mode."""
+bit for bit, in replay mode and in free-running (Philox) mode, with the swap round completed on the
+device through peer memory (NVLink) and with the host-completed round (NCCL)."""
 import os
 import socket
 import subprocess
@@ -17,17 +18,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("exchange", ["peer", "host"])
 @pytest.mark.parametrize("mode", ["replay", "free"])
-def test_partitioned_ladder_bit_identical_to_one_gpu(mode):
+def test_partitioned_ladder_bit_identical_to_one_gpu(mode, exchange):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     world = 2 if n < 4 else 4
-    env = dict(os.environ, PT_TEST_MODE=mode)
+    env = dict(os.environ, PT_TEST_MODE=mode, PT_TEST_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "DIST_GPU_RESULT mode=%s ok=True" % mode in out.stdout, out.stdout[-2000:]
+    assert "DIST_GPU_RESULT mode=%s exchange=%s ok=True" % (mode, exchange) in out.stdout, out.stdout[-2000:]
