@@ -343,6 +343,17 @@ def run_b200_arm(args, w, rank, world, local_rank):
                  "frac": (sfu / sec / 1e9 / world / peaks["mufu_gops"]) if peaks.get("mufu_gops") else None},
         "smem_broadcast": {"achieved_gbs": byts / sec / 1e9 / world, "peak_gbs": peaks.get("smem_gbs")},
     }
+    # The Langevin steps are a serial recurrence over the training rows: their bound is the
+    # dependent-issue latency of one row, not a throughput peak.  floor = sum of the measured latencies of the
+    # instructions on the chain (tools/latency_probe.cu); the upper bound charges the WHOLE
+    # timed region (random-walk steps included) to the serial rows.
+    chain_floor = {(4, 64, 1): 176, (4, 5, 1): 138, (4, 10, 1): 150, (16, 256, 10): 346}.get(tuple(w["topology"]))
+    serial_rows = n_lg * 2 * w["train"].shape[0]
+    if chain_floor and serial_rows and clk and clk.get("sm_mhz"):
+        cyc = sec / serial_rows * clk["sm_mhz"] * 1e6
+        roofline_alt["serial_chain"] = {"bound": "dependent-issue latency of the SGD recurrence (one chain per temperature)",
+                                        "serial_rows_per_temperature": serial_rows, "cycles_per_row_upper_bound": cyc,
+                                        "floor_cycles_per_row": chain_floor, "frac": chain_floor / cyc}
 
     # ---- CPU baseline on this box's host cores (bounded sample, N = 1 only)
     cpu = None

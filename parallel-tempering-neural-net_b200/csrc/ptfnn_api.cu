@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptfnn.h"
@@ -97,6 +98,8 @@ struct ptfnn_sampler {
     int num_sms = 0, regs_per_sm = 0, threads_per_sm = 0;
     size_t smem_per_sm = 0;
     std::string err;
+    void *pinned = nullptr;           // host staging buffer of get_traces (page-locked, grows on demand)
+    size_t pinned_bytes = 0;
 
     bool have_data = false, have_state = false;
     int n_train = 0, n_test = 0;
@@ -127,6 +130,8 @@ struct ptfnn_sampler {
     DevBuf<double> d_scratch;
 
     void release_all() {
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr; pinned_bytes = 0;
         train_x.release(); train_y.release(); test_x.release(); test_y.release(); a_train.release(); a_test.release(); temperature.release();
         w.release(); gd_cache.release(); pgd_buf.release(); pos_w.release(); pub_rows.release();
         eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
@@ -634,12 +639,30 @@ extern "C" int ptfnn_swap_uniforms(const ptfnn_sampler *s, int32_t round, float 
 // ------------------------------------------------------------------------------------------
 template <class T>
 static int fetch_rows(ptfnn_sampler *s, const T *dev, size_t row_elems, int first, int count, double *out) {
-    // dev is [R][S][row_elems]; copy rows [first, first+count) of every replica and widen to float64
+    // dev is [R][S][row_elems]; copy rows [first, first+count) of every replica through the pinned staging
+    // buffer of the handle and widen to float64 (the reference's arrays are float64); large blocks are
+    // widened by a few host threads -- the traces of one swap interval of 1024 temperatures are 16 MB
     const size_t R = s->cfg.n_replicas, S = s->cfg.samples;
-    std::vector<T> tmp(R * count * row_elems);
-    CU_TRY(s, cudaMemcpy2D(tmp.data(), count * row_elems * sizeof(T), dev + (size_t)first * row_elems,
-                           S * row_elems * sizeof(T), count * row_elems * sizeof(T), R, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+    const size_t n = R * count * row_elems, bytes = n * sizeof(T);
+    if (bytes > s->pinned_bytes) {
+        if (s->pinned) cudaFreeHost(s->pinned);
+        s->pinned = nullptr; s->pinned_bytes = 0;
+        CU_TRY(s, cudaHostAlloc(&s->pinned, bytes, cudaHostAllocDefault));
+        s->pinned_bytes = bytes;
+    }
+    T *tmp = (T *)s->pinned;
+    CU_TRY(s, cudaMemcpy2DAsync(tmp, count * row_elems * sizeof(T), dev + (size_t)first * row_elems,
+                                S * row_elems * sizeof(T), count * row_elems * sizeof(T), R, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = n < (1u << 20) ? 1 : std::min<size_t>(std::min<unsigned>(hw, 8u), n >> 19);
+    auto widen = [tmp, out](size_t a, size_t b) { for (size_t i = a; i < b; ++i) out[i] = (double)tmp[i]; };
+    if (nthreads <= 1) { widen(0, n); return PTFNN_OK; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nthreads - 1) / nthreads;
+    for (size_t k = 1; k < nthreads; ++k) th.emplace_back(widen, std::min(n, k * chunk), std::min(n, (k + 1) * chunk));
+    widen(0, std::min(n, chunk));
+    for (auto &t : th) t.join();
     return PTFNN_OK;
 }
 

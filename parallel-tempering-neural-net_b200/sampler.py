@@ -176,10 +176,10 @@ class Sampler:
     def traces(self, first=0, count=None, pos_w=True, debug=None):
         count = self.S - first if count is None else count
         debug = bool(self.cfg.debug_traces) if debug is None else debug
-        out = {k: np.zeros((self.R, count)) for k in ("lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test",
-                                                      "accept_list")}
+        out = {k: np.empty((self.R, count)) for k in ("lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test",
+                                                      "accept_list")}          # filled completely by the library
         if pos_w:
-            out["pos_w"] = np.zeros((self.R, count, self.P))
+            out["pos_w"] = np.empty((self.R, count, self.P))
         if debug:
             for k in ("prior_prop", "diff_prop", "mh_prob"):
                 out[k] = np.zeros((self.R, count))
