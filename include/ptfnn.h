@@ -67,7 +67,9 @@ typedef struct ptfnn_config {
     int32_t device;                 /* CUDA ordinal */
     int32_t threads_per_block;      /* 0 = auto */
     int32_t debug_traces;           /* 1 = also record prior_prop / diff_prop / mh_prob / accepted */
-    int32_t reserved0;
+    int32_t speculation;            /* small ladders: CTAs per temperature that evaluate consecutive steps
+                                     * speculatively (results are those of the sequential chain, bit for bit);
+                                     * 0 = automatic, 1 = off, K = that depth */
     uint64_t seed;                  /* Philox key (free-running mode) */
     double l_prob;                  /* langevin_prob, R:174 (C:192 fixes 0.5) */
     double learn_rate;              /* R:172 */

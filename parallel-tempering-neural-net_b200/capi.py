@@ -42,7 +42,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "task", "n_in", "n_hidden", "n_out", "n_replicas", "n_replicas_global", "replica_offset",
         "samples", "swap_interval", "swap_rule", "use_langevin_gradients", "common_random_numbers",
-        "memoize_gradient", "device", "threads_per_block", "debug_traces", "reserved0")] + \
+        "memoize_gradient", "device", "threads_per_block", "debug_traces", "speculation")] + \
         [("seed", C.c_uint64)] + \
         [(n, C.c_double) for n in ("l_prob", "learn_rate", "step_w", "step_eta", "sigma_squared", "nu_1", "nu_2",
                                    "pt_fraction")]

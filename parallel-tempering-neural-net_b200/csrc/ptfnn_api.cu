@@ -41,6 +41,7 @@ static int fail(ptfnn_sampler *s, int code, const char *fmt, ...);
 #include "ptfnn_registry.h"
 #include "ptfnn_topologies.h"
 typedef PtfnnKernelSet KernelSet;
+static const int kMaxSpec = 16;                 // deepest speculative window (CTAs per temperature)
 
 #define X(NAME, TASK, I, H, O, NT, MINB) const PtfnnKernelSet *ptfnn_kernelset_##NAME();
 PTFNN_TOPOLOGIES(X)
@@ -117,7 +118,8 @@ struct ptfnn_sampler {
     DevBuf<double> lik_prop, rmse_tr, rmse_te, acc_tr, acc_te, dbg_prior, dbg_diff, dbg_mh;
     DevBuf<int> n_acc, init_count, gd_valid, accept_list;
     DevBuf<uint8_t> dbg_acc, swap_log;
-    DevBuf<GridBarrier> barrier;
+    DevBuf<GridBarrier> barrier, spec_bar;            // spec_bar: one per temperature (speculative windows)
+    DevBuf<unsigned int> spec_flag;
     // multi-GPU ladder through peer memory (ptfnn_peer_connect)
     DevBuf<unsigned int> peer_flags;                  // [kMaxPeers] rounds published by each rank
     int n_ranks = 1, rank = 0;
@@ -144,7 +146,7 @@ struct ptfnn_sampler {
             if (peer_opened[q][2]) cudaIpcCloseMemHandle(peer_flag_ptr[q]);
             peer_opened[q][0] = peer_opened[q][1] = peer_opened[q][2] = false;
         }
-        peer_flags.release();
+        peer_flags.release(); spec_bar.release(); spec_flag.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
         d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release();
     }
@@ -273,12 +275,14 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
-    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, kMaxPeers);
+    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, kMaxPeers); ALLOC(spec_bar, R); ALLOC(spec_flag, R * kMaxSpec);
     ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(swap_src, R); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
     cudaMemset(s->peer_flags.p, 0, kMaxPeers * sizeof(unsigned int));
+    cudaMemset(s->spec_bar.p, 0, R * sizeof(GridBarrier));
+    cudaMemset(s->spec_flag.p, 0, R * kMaxSpec * sizeof(unsigned int));
     cudaMemset(s->smsp_load.p, 0, s->smsp_load.n * sizeof(int));
     cudaMemset(s->swap_counters.p, 0, 2 * sizeof(long long));
     cudaMemset(s->swap_log.p, 0, s->swap_log.n);
@@ -380,6 +384,8 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     CU_TRY(s, cudaMemsetAsync(s->swap_counters.p, 0, 16, s->stream));
     CU_TRY(s, cudaMemsetAsync(s->swap_log.p, 0, s->swap_log.n, s->stream));
     CU_TRY(s, cudaMemsetAsync(s->barrier.p, 0, sizeof(GridBarrier), s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->spec_bar.p, 0, R * sizeof(GridBarrier), s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->spec_flag.p, 0, R * kMaxSpec * sizeof(unsigned int), s->stream));
     if (s->cfg.debug_traces) {
         CU_TRY(s, cudaMemsetAsync(s->dbg_prior.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_diff.p, 0, R * S * 8, s->stream));
         CU_TRY(s, cudaMemsetAsync(s->dbg_mh.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_acc.p, 0, R * S, s->stream));
@@ -558,7 +564,19 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
         const int by_tmem = 512 / c.n_hidden;
         per_sm = std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_thr, by_tmem)));
     }
-    const int grid = std::min(R, per_sm * s->num_sms);
+    int grid = std::min(R, per_sm * s->num_sms);
+    // Small ladders leave most of the GPU idle (10 temperatures = 10 of 148 SMs): K CTAs per temperature
+    // evaluate K consecutive steps speculatively (chain_kernel, "speculative windows").  cfg.speculation:
+    // 0 = automatic, 1 = off, K > 1 = that depth (clamped to what is co-resident).
+    int spec = 1;
+    if (!uses_tmem && c.n_hidden <= 64 && !external && R * 2 <= per_sm * s->num_sms) {
+        int want = c.speculation;
+        if (const char *e = getenv("PTFNN_SPEC")) want = atoi(e);
+        if (want == 0) want = std::max(1, s->num_sms / R);    // one CTA per SM while the ladder is that small
+        spec = std::max(1, std::min(std::min(want, kMaxSpec), per_sm * s->num_sms / R));
+    }
+    p.spec_k = spec; p.spec_bar = s->spec_bar.p; p.spec_flag = s->spec_flag.p;
+    if (spec > 1) grid = R * spec;
     if (getenv("PTFNN_DEBUG")) {
         cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, s->ks->chain);
         int o2 = 0, o3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, s->ks->chain, NT, 90000); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, s->ks->chain, NT, 0);
@@ -598,6 +616,9 @@ static int sync_and_check(ptfnn_sampler *s) {
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     GridBarrier b;
     CU_TRY(s, cudaMemcpy(&b, s->barrier.p, sizeof b, cudaMemcpyDeviceToHost));
+    std::vector<GridBarrier> sb(s->cfg.n_replicas);
+    CU_TRY(s, cudaMemcpy(sb.data(), s->spec_bar.p, sb.size() * sizeof(GridBarrier), cudaMemcpyDeviceToHost));
+    for (const GridBarrier &g : sb) b.failed |= g.failed;
     if (b.failed) return fail(s, PTFNN_E_CUDA, "swap-round grid barrier timed out: the temperatures of one launch were not co-resident on the device");
     return PTFNN_OK;
 }

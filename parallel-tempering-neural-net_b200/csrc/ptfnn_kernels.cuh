@@ -1145,6 +1145,11 @@ struct ChainParams {
     int max_rounds;
     int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
     int P;
+    // ---- speculative windows for small ladders (spec_k > 1): spec_k CTAs per temperature evaluate spec_k
+    //      consecutive steps at once, each assuming that the earlier ones are rejected
+    int spec_k;
+    GridBarrier *spec_bar;         // [R]         barrier of the CTAs of one temperature
+    unsigned int *spec_flag;       // [R][spec_k] (window base + 1) << 1 | accepted
     int lik_team_warps;            // warps per CTA that evaluate the likelihood while the serial warp runs (0 = all)
     // ---- multi-GPU ladder through peer memory (n_ranks > 1): every rank's pub_lhood / pub_rows / peer_flags
     //      are mapped into this process (CUDA IPC); entry q of the tables points at rank q's buffer
@@ -1207,25 +1212,27 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
 // (R:435-437: only w and eta are taken back, likelihood / prior stay stale -- SURVEY Q7).
 template <int NT>
 __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int parity, bool apply, double *s_chunk,
-                                            int nblocks) {
+                                            int nblocks, int bid) {
+    // bid / nblocks: this CTA's index among the CTAs that OWN temperatures (with speculative windows
+    // only the first CTA of each group does)
     const int tid = threadIdx.x;
     const int P = p.P;
     const double *L = p.pub_lhood + (size_t)parity * p.Rg;
-    const bool log_it = blockIdx.x == 0 && round < p.max_rounds;
+    const bool log_it = bid == 0 && round < p.max_rounds;
     uint8_t *lg_out = log_it ? p.swap_log + (size_t)round * (p.Rg - 1) : nullptr;
     const float *ur = p.replay ? p.u_swap + (size_t)(round - p.round_begin) * (p.Rg - 1) : nullptr;
     double cur_l = 0.0;
     int cur_src = 0, ns = 0;
     // highest slot this CTA owns: no need to scan past it (block 0 scans everything for the log)
     int last_needed = p.Rg - 1;
-    if (blockIdx.x != 0 && apply) {
-        int r_hi = blockIdx.x;
+    if (bid != 0 && apply) {
+        int r_hi = bid;
         while (r_hi + nblocks < p.R) r_hi += nblocks;
         last_needed = p.replica_offset + r_hi;
     }
     auto mine = [&](int slot) {
         const int r = slot - p.replica_offset;
-        return apply && r >= 0 && r < p.R && (r % nblocks) == (int)blockIdx.x;
+        return apply && r >= 0 && r < p.R && (r % nblocks) == bid;
     };
     for (int base = 0; base <= last_needed; base += kSweepChunk - 1) {
         // chunk holds original lhood of slots [base, base + kSweepChunk)
@@ -1249,11 +1256,11 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
     }
     if (tid == 0) {
         if (last_needed == p.Rg - 1 && mine(p.Rg - 1)) p.swap_src[p.Rg - 1 - p.replica_offset] = cur_src;
-        if (blockIdx.x == 0) { p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1; }
+        if (bid == 0) { p.swap_counters[0] += ns; p.swap_counters[1] += p.Rg - 1; }
     }
     __syncthreads();
     if (!apply) return;
-    for (int r = blockIdx.x; r < p.R; r += nblocks) {
+    for (int r = bid; r < p.R; r += nblocks) {
         const int gsrc = p.swap_src[r];                       // global slot the vector comes from
         if (gsrc != p.replica_offset + r) {
             const int q = p.n_ranks > 1 ? gsrc / p.R : 0;     // equal contiguous blocks: owner rank of that slot
@@ -1400,6 +1407,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     const int lik_tid = (warp < sgd_warp ? tid : tid - 32);     // index inside the team of the other warps
 
     const int nblocks = gridDim.x;
+    // speculative windows: K CTAs per temperature (host guarantees gridDim.x == R * K and co-residency)
+    const int K = (!TEAM && p.spec_k > 1) ? p.spec_k : 1;
+    const bool SPEC = K > 1;
+    const int kq = SPEC ? (int)blockIdx.x % K : 0;               // position inside the window
+    const int vblock = SPEC ? (int)blockIdx.x / K : (int)blockIdx.x, nvb = SPEC ? nblocks / K : nblocks;
     int step = p.step_begin;
     int round = p.round_begin;
     const double inv_sig2 = 1.0 / ((double)p.step_w * (double)p.step_w);
@@ -1410,25 +1422,65 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         if (seg_last > p.step_end - 1) { seg_last = p.step_end - 1; swap_at_end = false; }
         const int parity = round & 1;
 
-        for (int r = blockIdx.x; r < p.R; r += nblocks) {
+        for (int r = vblock; r < p.R; r += nvb) {
             // ---------------- load this replica's state ----------------
             if constexpr (TEAM) { s_gd = p.gd_cache + (size_t)r * P; s_pgd = p.pgd_buf + (size_t)r * P; }
             if constexpr (TC) s_w = p.w + (size_t)r * P;             // the state vector stays in its global row
-            for (int j = tid; j < P; j += NT) {
-                if constexpr (!TC) s_w[j] = p.w[(size_t)r * P + j];
-                if constexpr (!TEAM) s_gd[j] = p.gd_cache[(size_t)r * P + j];
-            }
-            double eta = p.eta[r], tau = p.tau[r], lik = p.lik[r], prior_cur = p.prior[r];
-            int n_acc = p.n_acc[r], init_count = p.init_count[r];
-            int gd_valid = p.memo ? p.gd_valid[r] : 0;
-            double last_rtr = p.last4[r * 4 + 0], last_rte = p.last4[r * 4 + 1];
-            double last_atr = p.last4[r * 4 + 2], last_ate = p.last4[r * 4 + 3];
+            double eta, tau, lik, prior_cur, last_rtr, last_rte, last_atr, last_ate;
+            int n_acc, init_count, gd_valid;
+            auto load_state = [&]() {            // __ldcg: with speculative windows another CTA wrote it
+                for (int j = tid; j < P; j += NT) {
+                    if constexpr (!TC) s_w[j] = __ldcg(&p.w[(size_t)r * P + j]);
+                    if constexpr (!TEAM) s_gd[j] = __ldcg(&p.gd_cache[(size_t)r * P + j]);
+                }
+                eta = __ldcg(&p.eta[r]); tau = __ldcg(&p.tau[r]); lik = __ldcg(&p.lik[r]); prior_cur = __ldcg(&p.prior[r]);
+                n_acc = __ldcg(&p.n_acc[r]); init_count = __ldcg(&p.init_count[r]);
+                gd_valid = p.memo ? __ldcg(&p.gd_valid[r]) : 0;
+                last_rtr = __ldcg(&p.last4[r * 4 + 0]); last_rte = __ldcg(&p.last4[r * 4 + 1]);
+                last_atr = __ldcg(&p.last4[r * 4 + 2]); last_ate = __ldcg(&p.last4[r * 4 + 3]);
+                __syncthreads();
+            };
+            auto store_state = [&]() {
+                for (int j = tid; j < P; j += NT) {
+                    if constexpr (!TC) p.w[(size_t)r * P + j] = s_w[j];
+                    if constexpr (!TEAM) { if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
+                }
+                if (tid == 0) {
+                    p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior_cur;
+                    p.n_acc[r] = n_acc; p.init_count[r] = init_count; p.gd_valid[r] = gd_valid;
+                    p.last4[r * 4 + 0] = last_rtr; p.last4[r * 4 + 1] = last_rte;
+                    p.last4[r * 4 + 2] = last_atr; p.last4[r * 4 + 3] = last_ate;
+                }
+                __syncthreads();
+            };
+            load_state();
             const double temperature = p.temperature[r];
             const uint32_t gr = (uint32_t)(p.replica_offset + r);
             const uint32_t rng_stream = p.crn ? kStreamCommon : gr;
-            __syncthreads();
 
-            for (int i = step; i <= seg_last; ++i) {
+            // One iteration = one step, or (speculative windows) W consecutive steps evaluated by the W
+            // first CTAs of the group, each from the state at the window base, i.e. as if the earlier steps
+            // of the window were rejected.  The first accepted step k* makes steps 0..k* stand; its CTA
+            // installs the new state and the window after it starts at base + k* + 1.  Results are those of
+            // the sequential chain bit for bit: the draws are indexed by the step, a rejected step leaves
+            // nothing behind but its trace row and tau, and trace rows past k* are rewritten later.
+            int ibase = step;
+            while (ibase <= seg_last) {
+                int W = 1;
+                if (SPEC) {
+                    if (ibase != step) load_state();
+                    W = min(K, seg_last - ibase + 1);
+                    // the temperature switch (a11) changes the state whatever the MH outcome: the step that
+                    // performs it opens a window of its own and no window runs across it
+                    const int sw = (int)p.pt_samples;
+                    if (init_count == 0 && (double)sw == p.pt_samples) {
+                        if (ibase == sw) W = 1;
+                        else if (ibase < sw && ibase + W > sw) W = sw - ibase;
+                    }
+                }
+                const int i = ibase + kq;
+                bool accept = false;
+                if (kq < W) {
                 // ---- a11: temperature schedule inside the chain (R:317-324)
                 double adapt = init_count ? 1.0 : temperature;
                 if ((double)i == p.pt_samples && init_count == 0) {
@@ -1577,7 +1629,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 const double a = (lik_prop - lik) + (prior_prop - prior_cur) + diff_prop;   // R:365-373
                 double mh = exp(a);
                 if (!(mh < 1.0)) mh = 1.0;     // min(1, .): overflow -> 1 (R:375); NaN -> 1 (Python min)
-                const bool accept = (double)u < mh;                                   // R:395
+                accept = (double)u < mh;                                              // R:395
                 // ---- traces of row i+1
                 const size_t ti = (size_t)r * p.S + (i + 1);
                 if (tid == 0) {
@@ -1609,10 +1661,30 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 // accepted: the new state (R:408); rejected: the previous row is carried (R:417) -- it was
                 // written by these same threads (or is row 0 = ones), so no copy of it is kept on chip
                 if (accept) { for (int j = tid; j < P; j += NT) pw[j] = s_w[j]; }
-                else { for (int j = tid; j < P; j += NT) pw[j] = pw[j - P]; }
+                else {
+                    const float *prev = p.pos_w + ((size_t)r * p.S + ibase) * P;      // the row before the window
+                    for (int j = tid; j < P; j += NT) pw[j] = __ldcg(&prev[j]);         // (maybe written by another CTA)
+                }
+                }   // kq < W
+                if (!SPEC) { ++ibase; continue; }
+                // ---- resolve the window
+                if (tid == 0) p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 1) | ((kq < W && accept) ? 1u : 0u);
+                grid_barrier(&p.spec_bar[r], (unsigned int)K);
+                int kstar = W;
+                for (int q = 0; q < W; ++q) {
+                    const unsigned int f = __ldcg(&p.spec_flag[r * K + q]);
+                    if ((f >> 1) == (unsigned int)(ibase + 1) && (f & 1u)) { kstar = q; break; }
+                }
+                const int committed = min(kstar, W - 1);     // the last step of the window that stands
+                // its CTA holds exactly the chain's state after that step: the accepted vector, or (no
+                // acceptance) the unchanged state with the last proposed tau and any langevin_gradient(w) memo
+                if (kq == committed) store_state();
+                grid_barrier(&p.spec_bar[r], (unsigned int)K);
+                ibase += committed + 1;
             }
 
             // ---------------- publish for the hand-shake (R:427-431 / C:438-440) ----------------
+            if (SPEC) { if (kq != 0) continue; load_state(); }
             if (swap_at_end) {
                 float *row = p.pub_rows + ((size_t)parity * p.R + r) * (P + 1);
                 for (int j = tid; j < P; j += NT) row[j] = s_w[j];
@@ -1623,17 +1695,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 }
             }
             // ---------------- store state ----------------
-            for (int j = tid; j < P; j += NT) {
-                if constexpr (!TC) p.w[(size_t)r * P + j] = s_w[j];
-                if constexpr (!TEAM) { if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
-            }
-            if (tid == 0) {
-                p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior_cur;
-                p.n_acc[r] = n_acc; p.init_count[r] = init_count; p.gd_valid[r] = gd_valid;
-                p.last4[r * 4 + 0] = last_rtr; p.last4[r * 4 + 1] = last_rte;
-                p.last4[r * 4 + 2] = last_atr; p.last4[r * 4 + 3] = last_ate;
-            }
-            __syncthreads();
+            if (!SPEC) store_state();
         }
         step = seg_last + 1;
 
@@ -1642,8 +1704,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             // ---------------- K4: swap round ----------------
             grid_barrier(p.barrier, nblocks);
             if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
-            chain_sweep<NT>(p, round, parity, /*apply=*/true, s_sweep, nblocks);
+            if (kq == 0) chain_sweep<NT>(p, round, parity, /*apply=*/true, s_sweep, nvb, vblock);
             __syncthreads();
+            if (SPEC) grid_barrier(p.barrier, nblocks);      // the pulled vectors are visible to every CTA of the group
             ++round;
         }
     }
@@ -1651,11 +1714,12 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     // ---------------- left-over coordinator round on the exit vectors (R:442-444) -------------
     if (p.final_round && !p.external_swap && step >= p.step_end) {
         const int parity = round & 1;
-        for (int r = blockIdx.x; r < p.R; r += nblocks)
-            if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = p.lik[r];
+        if (kq == 0)
+            for (int r = vblock; r < p.R; r += nvb)
+                if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = __ldcg(&p.lik[r]);
         grid_barrier(p.barrier, nblocks);
         if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
-        if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nblocks);
+        if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nvb, 0);
     }
     if constexpr (TC) tc::teardown<I, H, O>(tcst);
 }

@@ -30,7 +30,7 @@ class Sampler:
                  l_prob=0.5, learn_rate=0.1, seed=0, common_random_numbers=True, memoize_gradient=True,
                  device=0, debug_traces=False, swap_rule=capi.SWAP_RULE_AUTO, n_replicas_global=None,
                  replica_offset=0, step_w=0.025, step_eta=0.2, sigma_squared=25.0, nu_1=0.0, nu_2=0.0,
-                 pt_fraction=0.6, stream=None):
+                 pt_fraction=0.6, stream=None, speculation=0):
         lib = capi.load()
         c = capi.default_config()
         c.task = int(task)
@@ -39,6 +39,7 @@ class Sampler:
         c.n_replicas = temperatures.shape[0]
         c.n_replicas_global = int(n_replicas_global or c.n_replicas)
         c.replica_offset = int(replica_offset)
+        c.speculation = int(speculation)      # small ladders: 0 automatic, 1 off, K CTAs per temperature
         c.samples, c.swap_interval, c.swap_rule = int(samples), int(swap_interval), int(swap_rule)
         c.use_langevin_gradients = int(bool(use_langevin_gradients))
         c.common_random_numbers = int(bool(common_random_numbers))

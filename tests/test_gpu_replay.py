@@ -176,3 +176,36 @@ def test_wide_hidden_chain_replay(memo):
     assert np.max(np.abs(t["diff_prop"][:, rows] - ref.diff_prop[:, rows])) < RTOL * cfg.P
     assert cm.relerr(t["pos_w"][:, :i_star + 1], ref.pos_w[:, :i_star + 1]) < RTOL
     assert i_star >= 4
+
+
+@pytest.mark.parametrize("memo", [0, 1])
+def test_speculative_windows_are_bit_identical(memo):
+    """Small ladders: K CTAs per temperature evaluate K consecutive steps at once, each assuming the earlier
+    ones rejected.  Every depth must give the sequential chain bit for bit: traces, swap
+    decisions, counters and final state -- through swap rounds, the left-over round and the 60% temperature
+    switch (step 120 of 200)."""
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    R, S, si = 10, 200, 20
+    from ptnn_b200.sampler import geometric_ladder
+    temps = geometric_ladder(R, 2)
+    w0 = np.random.RandomState(3).randn(R, 31)
+    out = {}
+    for depth in (1, 3, 8, 14):
+        with Sampler(on.REGRESSION, (4, 5, 1), temps, S, si, use_langevin_gradients=True, l_prob=0.5, learn_rate=0.1,
+                     seed=123, common_random_numbers=False, memoize_gradient=memo, debug_traces=True,
+                     speculation=depth) as s:
+            s.set_data(tr, te)
+            s.init_chains(w0)
+            assert s.run() == S - 1
+            t = s.traces()
+            st = s.get_state()
+            out[depth] = (t, s.swap_stats(), st)
+    t1, sw1, st1 = out[1]
+    assert t1["accepted"].sum() > R and sw1[0] > 0            # the run really accepts and swaps
+    for depth in (3, 8, 14):
+        t, sw, st = out[depth]
+        for k in t1:
+            assert np.array_equal(t[k], t1[k]), (depth, k)
+        assert sw[0] == sw1[0] and sw[1] == sw1[1] and np.array_equal(sw[2], sw1[2]), depth
+        for k in ("w", "eta", "lik", "prior", "tau", "num_accepted"):
+            assert np.array_equal(st[k], st1[k]), (depth, k)
