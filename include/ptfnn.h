@@ -118,6 +118,14 @@ int ptfnn_device_count(void);                  /* < 0 on CUDA error, 0 if no dev
 void ptfnn_default_config(ptfnn_config *cfg);  /* reference defaults (R:258-275, R:301) */
 const char *ptfnn_last_error(const ptfnn_sampler *s); /* s == NULL: last error of a failed create / op */
 
+/* ---- topologies.  The kernels are compiled specialisations of [n_in, n_hidden, n_out] (the reference
+ * fixes the topology per run: R:915, C:920-986).  ptfnn_has_topology tells whether one is loaded;
+ * ptfnn_register_kernels adds one that was compiled on demand from csrc/topo_inst.cu into its own
+ * shared library (the Python binding does this automatically: capi.ensure_topology). */
+int ptfnn_has_topology(int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out);
+int ptfnn_register_kernels(const void *kernel_set /* that library's ptfnn_topology_kernels() */,
+                           int32_t registry_version /* its ptfnn_topology_registry_version() */);
+
 /* ---- lifetime: replaces ParallelTempering.__init__ + initialize_chains (R:489-527, R:639-650) ---- */
 int ptfnn_create(const ptfnn_config *cfg, const double *temperatures /* [n_replicas], R:615-636 */,
                  ptfnn_sampler **out);

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -26,7 +27,7 @@ SYMBOLS = [
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
     "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
-    "ptfnn_peer_export", "ptfnn_peer_connect",
+    "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
     "ptfnn_op_swap_sweep",
 ]
@@ -92,6 +93,65 @@ def build_info() -> str:
     return load().ptfnn_build_info().decode()
 
 
+# ---- topologies compiled on demand -------------------------------------------------------------
+_jit_libs = {}
+
+
+def has_topology(task, topology) -> bool:
+    I, H, O = (int(x) for x in topology)
+    return bool(load().ptfnn_has_topology(int(task), I, H, O))
+
+
+def ensure_topology(task, topology, verbose=False):
+    """The kernels are compile-time specialisations of [I, H, O] (csrc/ptfnn_topologies.h lists the ones
+    built into libptfnn.so).  Any other topology is compiled here, once, from the same sources into
+    csrc/build/jit/libptfnn_topo_<name>.so (nvcc, sm_100a, ~20 s; cached on disk) and registered with
+    the library.  Needs nvcc; hidden layers wider than 256 units are not supported."""
+    import hashlib
+    import subprocess
+    task = int(task)
+    I, H, O = (int(x) for x in topology)
+    lib = load()
+    if lib.ptfnn_has_topology(task, I, H, O):
+        return
+    if task == TASK_REGRESSION and O != 1:
+        raise PtfnnError(E_UNSUPPORTED, "regression needs one output (R:132)")
+    if H > 256 or min(I, H, O) < 1:
+        raise PtfnnError(E_UNSUPPORTED, "no specialisation for topology [%d,%d,%d] (hidden layers up to 256 units)" % (I, H, O))
+    name = "jit_%s_%d_%d_%d" % ("reg" if task == TASK_REGRESSION else "cls", I, H, O)
+    nt = 128 if H <= 128 else 256                      # wide nets: one thread per hidden unit (sgd_pass_team)
+    minb = 2 if (H > 32 or I > 16) else 4
+    csrc = os.path.dirname(LIB_PATH)
+    out_dir = os.path.join(csrc, "build", "jit")
+    os.makedirs(out_dir, exist_ok=True)
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cuh", ".h", ".cu"))]
+    h = hashlib.sha256()
+    for f in srcs:
+        h.update(open(f, "rb").read())
+    so = os.path.join(out_dir, "libptfnn_topo_%s_%s.so" % (name, h.hexdigest()[:12]))
+    if not os.path.exists(so):
+        nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+               "-shared", "-cudart", "shared", "-DPTFNN_T_STANDALONE",
+               "-DPTFNN_T_NAME=%s" % name, "-DPTFNN_T_TASK=%d" % task, "-DPTFNN_T_I=%d" % I, "-DPTFNN_T_H=%d" % H,
+               "-DPTFNN_T_O=%d" % O, "-DPTFNN_T_NT=%d" % nt, "-DPTFNN_T_MINB=%d" % minb,
+               os.path.join(csrc, "topo_inst.cu"), "-o", so + ".tmp"]
+        if verbose:
+            print("[ptfnn] compiling a specialisation for topology [%d,%d,%d]: %s" % (I, H, O, " ".join(cmd)), file=sys.stderr)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True)
+        except OSError as e:
+            raise PtfnnError(E_UNSUPPORTED, "topology [%d,%d,%d] is not built into libptfnn.so and nvcc is not available "
+                                            "to compile it (%s)" % (I, H, O, e))
+        if r.returncode != 0:
+            raise PtfnnError(E_UNSUPPORTED, "compiling topology [%d,%d,%d] failed:\n%s" % (I, H, O, r.stderr[-2000:]))
+        os.replace(so + ".tmp", so)
+    tl = C.CDLL(so)
+    tl.ptfnn_topology_kernels.restype = C.c_void_p
+    check(lib.ptfnn_register_kernels(C.c_void_p(tl.ptfnn_topology_kernels()), int(tl.ptfnn_topology_registry_version())))
+    _jit_libs[(task, I, H, O)] = tl                     # keep the library (its kernels) loaded
+
+
 def device_count() -> int:
     return int(load().ptfnn_device_count())
 
@@ -126,6 +186,7 @@ def op_forward_pass(topology, x, w, device=0):
 
 def op_evaluate_proposal(task, topology, data, w, device=0):
     I, H, O = topology
+    ensure_topology(task, topology)
     data, w = f64(data), f64(w)
     fx = np.zeros(data.shape[0])
     prob = np.zeros((data.shape[0], O)) if task == TASK_CLASSIFICATION else None
@@ -136,6 +197,7 @@ def op_evaluate_proposal(task, topology, data, w, device=0):
 
 def op_langevin_gradient(task, topology, data, w, learn_rate, depth=1, device=0):
     I, H, O = topology
+    ensure_topology(task, topology)
     data, w = f64(data), f64(w)
     out = np.zeros_like(w)
     check(load().ptfnn_op_langevin_gradient(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
@@ -146,6 +208,7 @@ def op_langevin_gradient(task, topology, data, w, learn_rate, depth=1, device=0)
 def time_langevin_gradient(task, topology, data, w, learn_rate, depth=1, repeats=3, device=0):
     """Device time (ms, CUDA events, best of ``repeats``) of the langevin_gradient kernel alone."""
     I, H, O = topology
+    ensure_topology(task, topology)
     data, w = f64(data), f64(w)
     ms = C.c_double(0.0)
     check(load().ptfnn_time_langevin_gradient(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
@@ -156,6 +219,7 @@ def time_langevin_gradient(task, topology, data, w, learn_rate, depth=1, repeats
 def op_likelihood(task, topology, data, w, tau_sq=1.0, adapttemp=1.0, want_fx=True, device=0):
     """-> (loglik/adapttemp, rmse, accuracy, fx)"""
     I, H, O = topology
+    ensure_topology(task, topology)
     data, w = f64(data), f64(w)
     out = np.zeros(3)
     fx = np.zeros(data.shape[0]) if want_fx else None

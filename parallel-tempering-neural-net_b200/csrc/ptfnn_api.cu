@@ -47,13 +47,13 @@ static const int kMaxSpec = 16;                 // deepest speculative window (C
 PTFNN_TOPOLOGIES(X)
 #undef X
 
-static const std::vector<const KernelSet *> &kernel_sets() {
-    static const std::vector<const KernelSet *> v = {
+static std::vector<const KernelSet *> &kernel_sets() {
+    static std::vector<const KernelSet *> v = {
 #define X(NAME, TASK, I, H, O, NT, MINB) ptfnn_kernelset_##NAME(),
         PTFNN_TOPOLOGIES(X)
 #undef X
     };
-    return v;
+    return v;      // + specialisations registered at run time (ptfnn_register_kernels)
 }
 
 static const KernelSet *find_kernels(int task, int I, int H, int O) {
@@ -183,13 +183,31 @@ extern "C" int ptfnn_abi_version(void) { return PTFNN_ABI_VERSION; }
 
 extern "C" const char *ptfnn_build_info(void) {
     static std::string info;
-    if (info.empty()) {
+    static size_t n_sets = 0;
+    if (info.empty() || n_sets != kernel_sets().size()) {
+        n_sets = kernel_sets().size();
         char buf[256];
         snprintf(buf, sizeof buf, "libptfnn abi %d, sm_100a, nvcc %d.%d, tile_rows %d, topologies: ", PTFNN_ABI_VERSION,
                  __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, kTileRows);
         info = buf + supported_list();
     }
     return info.c_str();
+}
+
+// A further specialisation, compiled on demand from csrc/topo_inst.cu into its own shared library
+// (capi.ensure_topology): both libraries link the SHARED CUDA runtime, so kernels of one can be launched
+// by the other.  `kernel_set` points at that library's static PtfnnKernelSet (csrc/ptfnn_registry.h).
+extern "C" int ptfnn_register_kernels(const void *kernel_set, int32_t registry_version) {
+    if (!kernel_set) return fail(nullptr, PTFNN_E_INVALID, "null kernel set");
+    if (registry_version != PTFNN_REGISTRY_VERSION) return fail(nullptr, PTFNN_E_INVALID, "kernel registry version %d != %d: rebuild the specialisation", registry_version, PTFNN_REGISTRY_VERSION);
+    const KernelSet *k = (const KernelSet *)kernel_set;
+    if (find_kernels(k->task, k->I, k->H, k->O)) return PTFNN_OK;
+    kernel_sets().push_back(k);
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_has_topology(int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out) {
+    return find_kernels(task, n_in, n_hidden, n_out) ? 1 : 0;
 }
 
 extern "C" int ptfnn_device_count(void) {

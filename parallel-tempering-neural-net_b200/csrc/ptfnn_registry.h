@@ -1,5 +1,6 @@
 // Kernel dispatch record: one per specialised topology (see ptfnn_topologies.h).
 #pragma once
+#define PTFNN_REGISTRY_VERSION 2      /* layout of PtfnnKernelSet; checked by ptfnn_register_kernels */
 struct PtfnnKernelSet {
     const char *name;
     int task, I, H, O, NT;

@@ -25,3 +25,9 @@ const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
     };
     return &ks;
 }
+
+#ifdef PTFNN_T_STANDALONE
+// the same, with a fixed name, for specialisations built on demand into their own shared library
+extern "C" const void *ptfnn_topology_kernels(void) { return PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)(); }
+extern "C" int ptfnn_topology_registry_version(void) { return PTFNN_REGISTRY_VERSION; }
+#endif

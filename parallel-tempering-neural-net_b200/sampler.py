@@ -32,6 +32,7 @@ class Sampler:
                  replica_offset=0, step_w=0.025, step_eta=0.2, sigma_squared=25.0, nu_1=0.0, nu_2=0.0,
                  pt_fraction=0.6, stream=None, speculation=0):
         lib = capi.load()
+        capi.ensure_topology(task, topology)      # compiles a specialisation on first use of a new topology
         c = capi.default_config()
         c.task = int(task)
         c.n_in, c.n_hidden, c.n_out = (int(x) for x in topology)

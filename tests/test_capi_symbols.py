@@ -77,8 +77,20 @@ def test_argument_validation_happens_before_cuda(lib):
         Sampler(capi.TASK_REGRESSION, (4, 5, 2), [1.0, 2.0], 10, 5)           # regression needs O == 1 (R:132)
     assert e.value.code == capi.E_UNSUPPORTED
     with pytest.raises(capi.PtfnnError) as e:
-        Sampler(capi.TASK_REGRESSION, (4, 7, 1), [1.0, 2.0], 10, 5)           # not a built specialisation
-    assert e.value.code == capi.E_UNSUPPORTED and "built:" in str(e.value)
+        Sampler(capi.TASK_REGRESSION, (4, 300, 1), [1.0, 2.0], 10, 5)         # hidden layers up to 256 units
+    assert e.value.code == capi.E_UNSUPPORTED
+
     with pytest.raises(capi.PtfnnError) as e:
         Sampler(capi.TASK_REGRESSION, (4, 5, 1), [1.0, 2.0], 1, 5)            # samples < 2
     assert e.value.code == capi.E_INVALID
+
+
+def test_topology_is_compiled_on_demand(lib):
+    """A topology that is not built into libptfnn.so is compiled from the same sources into its own shared
+    library and registered (capi.ensure_topology); nvcc cross-compiles sm_100a without a GPU."""
+    topo = (3, 7, 1)
+    assert not capi.has_topology(capi.TASK_REGRESSION, topo) or "reg[3,7,1]" in capi.build_info()
+    capi.ensure_topology(capi.TASK_REGRESSION, topo)
+    assert capi.has_topology(capi.TASK_REGRESSION, topo)
+    assert "reg[3,7,1]" in capi.build_info()
+    capi.ensure_topology(capi.TASK_REGRESSION, topo)                          # idempotent

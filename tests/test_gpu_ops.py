@@ -137,3 +137,38 @@ def test_swap_sweep_matches_reference_rule():
     assert sw.all() and src.tolist() == [1, 0]
     src, sw = capi.op_swap_sweep([1e6, -1e6], [0.0])
     assert not sw.any()
+
+
+def test_on_demand_topologies_match_oracle():
+    """Topologies outside csrc/ptfnn_topologies.h are compiled on first use (capi.ensure_topology): narrow,
+    two-units-per-lane and wide (team kernel, H = 100) hidden layers, regression and classification."""
+    rs = np.random.RandomState(17)
+    for task, topo in ((on.REGRESSION, (3, 7, 1)), (on.CLASSIFICATION, (6, 40, 4)), (on.CLASSIFICATION, (5, 100, 3))):
+        I, H, O = topo
+        n = 300
+        y = rs.rand(n, 1) if task == on.REGRESSION else rs.randint(0, O, size=(n, 1)).astype(float)
+        data = np.hstack([rs.randn(n, I) * 0.7, y])
+        w = rs.randn(on.num_params(topo)) * 0.4
+        lik, rm, acc, _ = capi.op_likelihood(task, topo, data, w, 0.4, 1.3)
+        l2, r2, a2 = oc.likelihood(task, topo, data, w, 0.4, 1.3)
+        assert lik == pytest.approx(l2, rel=RTOL), topo
+        w_gd = capi.op_langevin_gradient(task, topo, data, w, 0.05)
+        assert cm.relerr(w_gd, oc.langevin_gradient(task, topo, data, w, 0.05)) < RTOL, topo
+        # and a short chain against the oracle on the same draws
+        cfg = on.PTConfig(task=task, topology=topo, samples=12, swap_interval=4, use_langevin_gradients=True,
+                          l_prob=0.5, learn_rate=0.05)
+        temps = np.array([1.0, 1.4, 2.0])
+        draws = on.random_draws(cfg, 3, 9, common_random_numbers=True)
+        w0 = rs.randn(3, cfg.P) * 0.4
+        te = data[:97]
+        ref = oc.run_pt(cfg, data, te, temps, w0, draws)
+        from ptnn_b200.sampler import Sampler
+        with Sampler.from_oracle_config(cfg, temps, debug_traces=True) as s:
+            s.set_data(data, te)
+            s.init_chains(w0)
+            s.replay(draws)
+            t = s.traces()
+        diff = np.argwhere(t["accepted"] != ref.accepted)
+        i_star = int(diff[:, 1].min()) - 1 if diff.size else cfg.samples - 1
+        assert i_star >= 5, (topo, i_star)
+        assert cm.relerr(t["lik_prop"][:, 1:i_star + 2], ref.lik_prop[:, 1:i_star + 2]) < RTOL, topo
