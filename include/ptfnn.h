@@ -218,6 +218,13 @@ int ptfnn_op_likelihood(int32_t device, int32_t task, int32_t n_in, int32_t n_hi
                         const double *data, int32_t rows, int32_t n_cols, const double *w, double tau_sq,
                         double adapttemp, double *out3, double *fx /* [rows] or NULL */);
 /* ptReplica.prior_likelihood (R:215-221 / C:224-230) */
+/* Posterior-predictive forward passes in one batch: fx_all[n_samples][rows] for the weight vectors
+ * w_samples[n_samples][P]; sums3[n_samples][3] = per sample {sum of squared errors | sum log prob[label],
+ * sum (argmax - y)^2, #correct}.  This is what the reference allocates as fx_train_all / fx_test_all but
+ * returns as zeros (R:785-788, R:809-815). */
+int ptfnn_op_posterior_predictive(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
+                                  const double *data, int32_t rows, int32_t n_cols, const double *w_samples,
+                                  int32_t n_samples, double *fx_all, double *sums3 /* may be NULL */);
 int ptfnn_op_prior(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden, int32_t n_out,
                    const double *w, double sigma_squared, double nu_1, double nu_2, double tausq, double *out);
 /* ParallelTempering.swap_procedure applied as the sequential sweep of run_chains (R:659-690, R:741-748) */

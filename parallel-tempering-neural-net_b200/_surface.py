@@ -285,6 +285,8 @@ class ParallelTemperingBase:
         self.memoize_gradient = True
         self.write_files = True             # per-chain txt files of R:454-481
         self.results_from_files = True      # show_results() re-reads them (R:794-831); False = in-memory, full precision
+        self.posterior_predictive = False   # True: fx_train_all / fx_test_all hold the predictions of every posterior
+                                            # sample (one batched GPU pass) instead of the reference's zeros (R:785-788)
         self.last_sampler_seconds = None
         self._traces = None
 
@@ -445,6 +447,10 @@ class ParallelTemperingBase:
                 accept_list[i] = t["accept_list"][i]
                 rmse_test[i], rmse_train[i] = t["rmse_test"][i, burnin:], t["rmse_train"][i, burnin:]
                 acc_test[i], acc_train[i] = t["acc_test"][i, burnin:], t["acc_train"][i, burnin:]
+        if self.posterior_predictive:
+            for i in range(R):
+                fx_train_all[i] = capi.op_posterior_predictive(self.TASK, self.topology, self.traindata, pos_w[i], self.device)[0]
+                fx_test_all[i] = capi.op_posterior_predictive(self.TASK, self.topology, self.testdata, pos_w[i], self.device)[0]
         posterior = pos_w.transpose(2, 0, 1).reshape(self.num_param, -1)
         likelihood_vec = likelihood_rep.transpose(2, 0, 1).reshape(2, -1)
         rmse_train = rmse_train.reshape(R * (S - burnin), 1)

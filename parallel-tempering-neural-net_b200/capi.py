@@ -29,7 +29,7 @@ SYMBOLS = [
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
-    "ptfnn_op_swap_sweep",
+    "ptfnn_op_swap_sweep", "ptfnn_op_posterior_predictive",
 ]
 
 
@@ -226,6 +226,20 @@ def op_likelihood(task, topology, data, w, tau_sq=1.0, adapttemp=1.0, want_fx=Tr
     check(load().ptfnn_op_likelihood(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1], ptr(w),
                                      C.c_double(tau_sq), C.c_double(adapttemp), ptr(out), ptr(fx)))
     return float(out[0]), float(out[1]), float(out[2]), fx
+
+
+def op_posterior_predictive(task, topology, data, w_samples, device=0):
+    """Forward pass of every posterior sample in one batched launch -> (fx_all[n_samples, rows], sums[n_samples, 3]).
+    The reference returns these arrays as zeros (R:785-788)."""
+    I, H, O = topology
+    ensure_topology(task, topology)
+    data, w_samples = f64(data), f64(w_samples)
+    ns = w_samples.shape[0]
+    fx = np.empty((ns, data.shape[0]))
+    sums = np.empty((ns, 3))
+    check(load().ptfnn_op_posterior_predictive(device, task, I, H, O, ptr(data), data.shape[0], data.shape[1],
+                                               ptr(w_samples), ns, ptr(fx), ptr(sums)))
+    return fx, sums
 
 
 def op_prior(task, topology, w, sigma_squared=25.0, nu_1=0.0, nu_2=0.0, tausq=1.0, device=0):

@@ -886,7 +886,7 @@ struct OpData {
 };
 
 static int op_prepare(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
-                      const double *w, const KernelSet **ks, OpData &od) {
+                      const double *w, const KernelSet **ks, OpData &od, int batch = 1) {
     int rc = require_device(nullptr, device);
     if (rc) return rc;
     *ks = find_kernels(task, I, H, O);
@@ -902,10 +902,10 @@ static int op_prepare(int device, int task, int I, int H, int O, const double *d
         CU_TRY(nullptr, cudaMemcpy(od.y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice));
         od.rows = rows;
     }
-    std::vector<float> wf(P);
-    for (int j = 0; j < P; ++j) wf[j] = (float)w[j];
-    CU_TRY(nullptr, od.w.ensure(P));
-    CU_TRY(nullptr, cudaMemcpy(od.w.p, wf.data(), (size_t)P * 4, cudaMemcpyHostToDevice));
+    std::vector<float> wf((size_t)P * batch);
+    for (size_t j = 0; j < wf.size(); ++j) wf[j] = (float)w[j];
+    CU_TRY(nullptr, od.w.ensure(wf.size()));
+    CU_TRY(nullptr, cudaMemcpy(od.w.p, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
     return PTFNN_OK;
 }
 
@@ -922,16 +922,16 @@ static int pack_a_tiles(ptfnn_sampler *s, const KernelSet *ks, const float *x, i
 }
 
 static int op_forward(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
-                      const double *w, double *fx, double *prob, double sums[3]) {
+                      const double *w, double *fx, double *prob, double *sums /* [batch][3] */, int batch = 1) {
     const KernelSet *ks;
     OpData od;
-    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od);
+    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od, batch);
     if (rc) { od.release(); return rc; }
     const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
     DevBuf<float> d_fx, d_prob;
     DevBuf<double> d_sums;
-    CU_TRY(nullptr, d_fx.ensure(rows)); CU_TRY(nullptr, d_sums.ensure(3));
-    if (prob) CU_TRY(nullptr, d_prob.ensure((size_t)rows * O));
+    CU_TRY(nullptr, d_fx.ensure((size_t)rows * batch)); CU_TRY(nullptr, d_sums.ensure((size_t)3 * batch));
+    if (prob) CU_TRY(nullptr, d_prob.ensure((size_t)rows * O * batch));
     DataView v{od.x.p, od.y.p, rows};
     const float *wp = od.w.p; float *fxp = d_fx.p; float *pp = prob ? d_prob.p : nullptr; double *sp = d_sums.p;
     DevBuf<float> d_tiles;
@@ -942,26 +942,26 @@ static int op_forward(int device, int task, int I, int H, int O, const double *d
         const float *tp = d_tiles.p, *yp = od.y.p; int n = rows;
         void *args[] = {&wp, &tp, &yp, &n, &fxp, &pp, &sp};
         CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ks->tc_smem_bytes));
-        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd_tc, dim3(1), dim3(ks->NT), args, (size_t)ks->tc_smem_bytes, 0));
+        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd_tc, dim3(batch), dim3(ks->NT), args, (size_t)ks->tc_smem_bytes, 0));
     } else {
         void *args[] = {&wp, &v, &fxp, &pp, &sp};
         const size_t smem = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
         CU_TRY(nullptr, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd, dim3(1), dim3(ks->NT), args, smem, 0));
+        CU_TRY(nullptr, cudaLaunchKernel(ks->fwd, dim3(batch), dim3(ks->NT), args, smem, 0));
     }
     CU_TRY(nullptr, cudaDeviceSynchronize());
     d_tiles.release();
     if (fx) {
-        std::vector<float> t(rows);
-        CU_TRY(nullptr, cudaMemcpy(t.data(), d_fx.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
-        for (int r = 0; r < rows; ++r) fx[r] = t[r];
+        std::vector<float> t((size_t)rows * batch);
+        CU_TRY(nullptr, cudaMemcpy(t.data(), d_fx.p, t.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t r = 0; r < t.size(); ++r) fx[r] = t[r];
     }
     if (prob) {
-        std::vector<float> t((size_t)rows * O);
+        std::vector<float> t((size_t)rows * O * batch);
         CU_TRY(nullptr, cudaMemcpy(t.data(), d_prob.p, t.size() * 4, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < t.size(); ++k) prob[k] = t[k];
     }
-    if (sums) CU_TRY(nullptr, cudaMemcpy(sums, d_sums.p, 24, cudaMemcpyDeviceToHost));
+    if (sums) CU_TRY(nullptr, cudaMemcpy(sums, d_sums.p, (size_t)24 * batch, cudaMemcpyDeviceToHost));
     od.release(); d_fx.release(); d_prob.release(); d_sums.release();
     return PTFNN_OK;
 }
@@ -970,6 +970,20 @@ extern "C" int ptfnn_op_evaluate_proposal(int32_t device, int32_t task, int32_t 
                                           int32_t rows, int32_t n_cols, const double *w, double *fx, double *prob) {
     if (!data || !fx) return fail(nullptr, PTFNN_E_INVALID, "null argument");
     return op_forward(device, task, I, H, O, data, rows, n_cols, w, fx, task == kTaskCls ? prob : nullptr, nullptr);
+}
+
+// Posterior-predictive outputs: the reference allocates fx_train_all / fx_test_all
+// [samples, rows] but returns zeros (R:785-788, R:809-815 are commented out "for memory").  Here the forward
+// pass of every posterior sample runs as one batch (one CTA per weight vector; tcgen05 for wide nets).
+extern "C" int ptfnn_op_posterior_predictive(int32_t device, int32_t task, int32_t I, int32_t H, int32_t O, const double *data,
+                                             int32_t rows, int32_t n_cols, const double *w_samples, int32_t n_samples,
+                                             double *fx_all, double *sums3) {
+    if (!data || !w_samples || !fx_all || n_samples < 1) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    std::vector<double> sums((size_t)3 * n_samples);
+    int rc = op_forward(device, task, I, H, O, data, rows, n_cols, w_samples, fx_all, nullptr, sums.data(), n_samples);
+    if (rc) return rc;
+    if (sums3) memcpy(sums3, sums.data(), sums.size() * 8);
+    return PTFNN_OK;
 }
 
 // The scalar epilogue of likelihood_func (R:204-205 / C:222) on the device sums.

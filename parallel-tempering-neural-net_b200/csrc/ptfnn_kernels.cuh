@@ -1798,7 +1798,8 @@ __global__ void __launch_bounds__(NT) init_kernel(const InitParams p) {
 }
 
 // ==========================================================================================
-// single-operation kernels (one CTA)
+// single-operation kernels (one CTA per weight vector: blockIdx.x indexes a batch of them, e.g. the
+// posterior samples of ptfnn_op_posterior_predictive)
 // ==========================================================================================
 template <int I, int H, int O, int TASK, int NT>
 __global__ void __launch_bounds__(NT) op_forward_kernel(const float *w, DataView d, float *fx, float *prob,
@@ -1807,6 +1808,10 @@ __global__ void __launch_bounds__(NT) op_forward_kernel(const float *w, DataView
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_w = reinterpret_cast<float *>(smem_raw);
     double *s_red = reinterpret_cast<double *>(smem_raw + (((size_t)P * 4 + 15) & ~(size_t)15));
+    w += (size_t)blockIdx.x * P;
+    if (fx) fx += (size_t)blockIdx.x * d.n;
+    if (prob) prob += (size_t)blockIdx.x * d.n * O;
+    sums += (size_t)blockIdx.x * 3;
     for (int j = threadIdx.x; j < P; j += NT) s_w[j] = w[j];
     __syncthreads();
     double s[3] = {0.0, 0.0, 0.0};
@@ -1852,6 +1857,12 @@ __global__ void __launch_bounds__(NT) op_forward_tc_kernel(const float *w, const
     if constexpr (UseTc<I, H, O, NT>::value) {
         extern __shared__ __align__(128) unsigned char smem_raw[];
         __shared__ double s_red[3 * (NT / 32)];
+        __shared__ __align__(16) float s_tail[H * O + H + O + 4];  // [W2, B1, B2]: the epilogue reads W2 with 16-byte loads
+        constexpr int P = NetSizes<I, H, O>::P;
+        w += (size_t)blockIdx.x * P;
+        if (fx) fx += (size_t)blockIdx.x * n;
+        if (prob) prob += (size_t)blockIdx.x * n * O;
+        sums += (size_t)blockIdx.x * 3;
         tc::State st;
         tc::setup<I, H, O>(smem_raw, st);
         tc::build_b<I, H, O>(smem_raw, w, threadIdx.x, NT);
@@ -1859,7 +1870,10 @@ __global__ void __launch_bounds__(NT) op_forward_tc_kernel(const float *w, const
         __syncthreads();
         double s[3] = {0.0, 0.0, 0.0};
         int c = 0;
-        tc::lik_pass<I, H, O, TASK, NT, true>(smem_raw, st, tiles, y, n, w, s[0], s[1], c, fx, prob);
+        // (the rows of a batch of weight vectors are only 8-byte aligned for odd P: go through shared memory)
+        for (int j = threadIdx.x; j < H * O + H + O; j += NT) s_tail[j] = w[I * H + j];
+        __syncthreads();
+        tc::lik_pass<I, H, O, TASK, NT, true>(smem_raw, st, tiles, y, n, s_tail - I * H, s[0], s[1], c, fx, prob);
         s[2] = (double)c;
         block_sum<3, NT>(s, s_red);
         if (threadIdx.x == 0) { sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2]; }

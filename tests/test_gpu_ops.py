@@ -172,3 +172,25 @@ def test_on_demand_topologies_match_oracle():
         i_star = int(diff[:, 1].min()) - 1 if diff.size else cfg.samples - 1
         assert i_star >= 5, (topo, i_star)
         assert cm.relerr(t["lik_prop"][:, 1:i_star + 2], ref.lik_prop[:, 1:i_star + 2]) < RTOL, topo
+
+
+def test_posterior_predictive_batch_matches_oracle():
+    """ptfnn_op_posterior_predictive: the forward pass of a batch of weight vectors (what the reference leaves as
+    zeros in fx_train_all, R:785-788) -- CUDA-core path and the tcgen05 path of the wide-hidden net."""
+    rs = np.random.RandomState(23)
+    tr, _ = cm.dataset(on.REGRESSION, "Sunspot")
+    ws = rs.randn(7, 31) * 0.5
+    fx, sums = capi.op_posterior_predictive(capi.TASK_REGRESSION, (4, 5, 1), tr, ws)
+    for k in range(7):
+        assert cm.relerr(fx[k], oc.evaluate(on.REGRESSION, (4, 5, 1), tr, ws[k])) < RTOL
+        assert sums[k, 0] == pytest.approx(np.sum((fx[k] - tr[:, 4]) ** 2), rel=1e-5)
+    topo = (16, 256, 10)
+    data = np.hstack([rs.randn(200, 16), rs.randint(0, 10, size=(200, 1)).astype(float)])
+    ws = rs.randn(5, on.num_params(topo)) * 0.2
+    fx, sums = capi.op_posterior_predictive(capi.TASK_CLASSIFICATION, topo, data, ws)
+    for k in range(5):
+        ref_fx, ref_prob = oc.evaluate(on.CLASSIFICATION, topo, data, ws[k])
+        top2 = np.sort(ref_prob, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-5
+        assert np.array_equal(fx[k][clear], ref_fx[clear])
+        assert sums[k, 0] == pytest.approx(np.sum(np.log(ref_prob[np.arange(200), data[:, 16].astype(int)])), rel=RTOL)
