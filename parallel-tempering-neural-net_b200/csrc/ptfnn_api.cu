@@ -587,14 +587,23 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     // evaluate K consecutive steps speculatively (chain_kernel, "speculative windows").  cfg.speculation:
     // 0 = automatic, 1 = off, K > 1 = that depth (clamped to what is co-resident).
     int spec = 1;
-    if (!uses_tmem && c.n_hidden <= 64 && !external && R * 2 <= per_sm * s->num_sms) {
+    if (s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms) {
         int want = c.speculation;
         if (const char *e = getenv("PTFNN_SPEC")) want = atoi(e);
         if (want == 0) want = std::max(1, s->num_sms / R);    // one CTA per SM while the ladder is that small
         spec = std::max(1, std::min(std::min(want, kMaxSpec), per_sm * s->num_sms / R));
     }
     p.spec_k = spec; p.spec_bar = s->spec_bar.p; p.spec_flag = s->spec_flag.p;
-    if (spec > 1) grid = R * spec;
+    const void *chain_fn = s->ks->chain;
+    if (spec > 1) {
+        chain_fn = s->ks->chain_spec;
+        CU_TRY(s, cudaFuncSetAttribute(chain_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        int per_sm_spec = 0;
+        CU_TRY(s, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_spec, chain_fn, NT, L.total));
+        spec = std::max(1, std::min(spec, per_sm_spec * s->num_sms / R));
+        p.spec_k = spec;
+        if (spec > 1) grid = R * spec; else chain_fn = s->ks->chain;
+    }
     if (getenv("PTFNN_DEBUG")) {
         cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, s->ks->chain);
         int o2 = 0, o3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, s->ks->chain, NT, 90000); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, s->ks->chain, NT, 0);
@@ -606,7 +615,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     if (const char *e = getenv("PTFNN_LIK_TEAM_WARPS")) p.lik_team_warps = atoi(e);
     void *args[] = {&p};
     if (uses_tmem) CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
-    else CU_TRY(s, cudaLaunchCooperativeKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
+    else CU_TRY(s, cudaLaunchCooperativeKernel(chain_fn, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());
     s->step = end;
     if (external) {

@@ -339,12 +339,26 @@ __device__ __forceinline__ int swap_sweep_serial(int n, double *lh, int *src, ui
 // is known (either the original vector of slot k+1, or the vector that has been bubbling up), so
 // nothing but the bubbling vector's (lhood, origin) needs to be carried.  `lh_chunk(k)` returns the
 // ORIGINAL lhood of slot k; emit(slot, origin) reports final contents, decided(k, swapped) every pair.
-template <class LFn, class UFn, class Emit, class Decided>
+// The decision u < min(1, 0.5 exp(min(709, d))) is taken in the log domain, log(2u) < min(709, d), with
+// log(2u) precomputed by the whole CTA (`lu_of`): the sweep itself is sequential (pair k needs the outcome
+// of pair k-1) and an fp64 exp per pair made it ~0.2 us per rung -- 1.7 ms per round on an 8192-rung ladder.
+// Near a tie (and for u = 0 or a NaN difference) the reference's own expression decides, so the result is
+// the reference's in every case.
+__device__ __forceinline__ bool swap_decision(double cur_l, double nxt, float u, double lu) {
+    double d = nxt - cur_l;
+    if (d > 709.0) d = 709.0;
+    const double tol = 1e-12 * fmax(1.0, fabs(d));
+    if (lu < d - tol && lu > -1e300) return true;
+    if (lu > d + tol) return false;
+    return (double)u < swap_probability(cur_l, nxt);
+}
+
+template <class LFn, class UFn, class LUFn, class Emit, class Decided>
 __device__ __forceinline__ void swap_sweep_stream(int k_begin, int k_end, int n, double &cur_l, int &cur_src, int &ns,
-                                                  LFn lh_of, UFn u_of, Emit emit, Decided decided) {
+                                                  LFn lh_of, UFn u_of, LUFn lu_of, Emit emit, Decided decided) {
     for (int k = k_begin; k < k_end && k + 1 < n; ++k) {
         const double nxt = lh_of(k + 1);
-        const bool s = (double)u_of(k) < swap_probability(cur_l, nxt);
+        const bool s = swap_decision(cur_l, nxt, u_of(k), lu_of(k));
         if (s) { emit(k, k + 1); ++ns; }
         else { emit(k, cur_src); cur_l = nxt; cur_src = k + 1; }
         decided(k, s);

@@ -1198,7 +1198,7 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
     L.off_bar = take(8 * 4);
     const size_t tile_bytes = staged ? 0 : (size_t)2 * (kTileRows * IP * 4 + kTileRows * 4);
     L.off_tiles = tc ? L.off_lw + tc_alias_off : take(tile_bytes);
-    L.off_sweep = take(Rg > 1 ? (size_t)kSweepChunk * 8 : 0);   // one chunk of lhood fields for the streaming sweep
+    L.off_sweep = take(Rg > 1 ? (size_t)kSweepChunk * (8 + 8 + 4) : 0);   // one chunk of lhood fields, log(2u) and u for the streaming sweep
     L.off_team = tc ? L.off_tiles + ((tile_bytes + 15) & ~(size_t)15) : take((size_t)team_floats * 4);
     auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
     L.off_stage = take(staged ? ((size_t)n_train * IP + pad4(n_train) + (size_t)n_test * IP + pad4(n_test)) * 4 : 0);
@@ -1234,22 +1234,32 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
         const int r = slot - p.replica_offset;
         return apply && r >= 0 && r < p.R && (r % nblocks) == bid;
     };
+    double *s_lu = s_chunk + kSweepChunk;                          // log(2 u) of the chunk's pairs
+    float *s_u = reinterpret_cast<float *>(s_lu + kSweepChunk);    // their uniforms
     for (int base = 0; base <= last_needed; base += kSweepChunk - 1) {
-        // chunk holds original lhood of slots [base, base + kSweepChunk)
+        // chunk holds original lhood of slots [base, base + kSweepChunk) and the draws of pairs [base, ...)
         __syncthreads();
-        for (int k = tid; k < kSweepChunk && base + k < p.Rg; k += NT) s_chunk[k] = __ldcg(&L[base + k]);
+        for (int k = tid; k < kSweepChunk && base + k < p.Rg; k += NT) {
+            s_chunk[k] = __ldcg(&L[base + k]);
+            float u = 0.0f;
+            if (base + k < p.Rg - 1) {
+                if (ur) u = ur[base + k];
+                else {
+                    uint32_t c[4];
+                    philox_draw(p.seed, (uint32_t)round, (uint32_t)(base + k), 0u, kTagSwap, c);
+                    u = u01_open_right(c[0]);
+                }
+            }
+            s_u[k] = u;
+            s_lu[k] = log(2.0 * (double)u);
+        }
         __syncthreads();
         if (tid == 0) {
             if (base == 0) { cur_l = s_chunk[0]; cur_src = 0; }
             const int k_end = min(base + kSweepChunk - 1, last_needed + 1);
             swap_sweep_stream(
                 base, k_end, p.Rg, cur_l, cur_src, ns, [&](int k) { return s_chunk[k - base]; },
-                [&](int k) {
-                    if (ur) return ur[k];
-                    uint32_t c[4];
-                    philox_draw(p.seed, (uint32_t)round, (uint32_t)k, 0u, kTagSwap, c);
-                    return u01_open_right(c[0]);
-                },
+                [&](int k) { return s_u[k - base]; }, [&](int k) { return s_lu[k - base]; },
                 [&](int slot, int origin) { if (mine(slot)) p.swap_src[slot - p.replica_offset] = origin; },
                 [&](int k, bool sw) { if (lg_out) lg_out[k] = (uint8_t)sw; });
         }
@@ -1313,7 +1323,9 @@ __device__ __forceinline__ void peer_exchange_lhood(const ChainParams &p, int ro
     __syncthreads();
 }
 
-template <int I, int H, int O, int TASK, int NT, int MINB>
+// SPEC_T: the instantiation with speculative windows (small ladders); the plain one carries none of their
+// state (at 72 registers per thread for 1024 co-resident temperatures every live value counts).
+template <int I, int H, int O, int TASK, int NT, int MINB, bool SPEC_T = false>
 __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     constexpr int P = NetSizes<I, H, O>::P;
     constexpr int IP = NetSizes<I, H, O>::IP;
@@ -1408,8 +1420,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 
     const int nblocks = gridDim.x;
     // speculative windows: K CTAs per temperature (host guarantees gridDim.x == R * K and co-residency)
-    const int K = (!TEAM && p.spec_k > 1) ? p.spec_k : 1;
-    const bool SPEC = K > 1;
+    const int K = (SPEC_T && !TEAM && p.spec_k > 1) ? p.spec_k : 1;
+    const bool SPEC = SPEC_T && K > 1;
     const int kq = SPEC ? (int)blockIdx.x % K : 0;               // position inside the window
     const int vblock = SPEC ? (int)blockIdx.x / K : (int)blockIdx.x, nvb = SPEC ? nblocks / K : nblocks;
     int step = p.step_begin;

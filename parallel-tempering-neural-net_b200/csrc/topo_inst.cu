@@ -10,11 +10,22 @@
 
 using namespace ptfnn;
 
+// the chain kernel with speculative windows is only instantiated where it can be used (not for the team topologies)
+template <bool TEAM>
+struct SpecChain {
+    static const void *get() { return (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT, PTFNN_T_MINB, true>; }
+};
+template <>
+struct SpecChain<true> {
+    static const void *get() { return nullptr; }
+};
+
 const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
     constexpr bool kTc = UseTc<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_NT>::value;
     static const PtfnnKernelSet ks = {
         PTFNN_STR(PTFNN_T_NAME), PTFNN_T_TASK, PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_NT,
         (const void *)chain_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT, PTFNN_T_MINB>,
+        SpecChain<ptfnn::UseSgdTeam<PTFNN_T_H>::value>::get(),
         (const void *)init_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_forward_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
