@@ -88,6 +88,10 @@ struct DevBuf {
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }          // error paths (CU_TRY returns) do not leak device memory
 };
 
 struct ptfnn_sampler {
@@ -611,8 +615,6 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     }
     if (getenv("PTFNN_DEBUG")) fprintf(stderr, "[ptfnn] chain launch: smem %zu B, %d CTAs/SM, grid %d, threads %d\n", L.total, per_sm, grid, NT);
     // many temperatures per SM: keep the serial warps' sub-partitions quiet (see chain_kernel)
-    p.lik_team_warps = 0;
-    if (const char *e = getenv("PTFNN_LIK_TEAM_WARPS")) p.lik_team_warps = atoi(e);
     void *args[] = {&p};
     if (uses_tmem) CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
     else CU_TRY(s, cudaLaunchCooperativeKernel(chain_fn, dim3(grid), dim3(NT), args, L.total, s->stream));

@@ -1150,7 +1150,6 @@ struct ChainParams {
     int spec_k;
     GridBarrier *spec_bar;         // [R]         barrier of the CTAs of one temperature
     unsigned int *spec_flag;       // [R][spec_k] (window base + 1) << 1 | accepted
-    int lik_team_warps;            // warps per CTA that evaluate the likelihood while the serial warp runs (0 = all)
     // ---- multi-GPU ladder through peer memory (n_ranks > 1): every rank's pub_lhood / pub_rows / peer_flags
     //      are mapped into this process (CUDA IPC); entry q of the tables points at rank q's buffer
     int n_ranks, rank;
@@ -1573,17 +1572,14 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[k] = 0.0;
                 int c_tr = 0, c_te = 0;
-                if (lg && NW > 1 && !TEAM && p.lik_team_warps >= 0) {
+                if (lg && NW > 1 && !TEAM) {
+                    // (measured alternatives: fewer likelihood warps make that pass the critical path; running
+                    // the two one after the other costs the same as overlapping them -- DESIGN section 5)
                     if (is_sgd_warp) {
                         sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
-                    } else if (p.lik_team_warps <= 0 || lik_tid < 32 * p.lik_team_warps) {
-                        // The serial warp is latency-bound and has no issue priority: every additional
-                        // ready warp on its sub-partition delays each of its dependent instructions.
-                        // When many temperatures share an SM the likelihood (which has the whole SGD
-                        // epoch to finish) is therefore left to `lik_team_warps` warps per CTA.
-                        const int team = p.lik_team_warps <= 0 ? NT - 32 : 32 * p.lik_team_warps;
-                        lik_fast<I, H, O, TASK>(s_lw, s_prop, train, lik_tid, team, s[0], s[1], c_tr);
-                        lik_fast<I, H, O, TASK>(s_lw, s_prop, test, lik_tid, team, s[2], s[3], c_te);
+                    } else {
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, train, lik_tid, NT - 32, s[0], s[1], c_tr);
+                        lik_fast<I, H, O, TASK>(s_lw, s_prop, test, lik_tid, NT - 32, s[2], s[3], c_te);
                     }
                 } else {
                     if (lg) {
