@@ -1572,6 +1572,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[k] = 0.0;
                 int c_tr = 0, c_te = 0;
+                // The test-set pass only feeds rmse_test / acc_test, which are recorded on ACCEPTANCE (R:362,
+                // R:399-406): with `memo` (skip work whose result is provably unused, like the gradient memo) it
+                // runs after the MH decision, for accepted proposals only.  The overlapped pass below keeps it:
+                // there it hides behind the SGD epoch.
+                const bool lazy_test = p.memo != 0 && !(lg && NW > 1 && !TEAM);
                 if (lg && NW > 1 && !TEAM) {
                     // (measured alternatives: fewer likelihood warps make that pass the critical path; running
                     // the two one after the other costs the same as overlapping them -- DESIGN section 5)
@@ -1588,10 +1593,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                         __syncthreads();
                     }
                     if constexpr (TC) {
-                        tc_likelihood(s_prop, true, s[0], s[1], c_tr, s[2], s[3], c_te);
+                        tc_likelihood(s_prop, !lazy_test, s[0], s[1], c_tr, s[2], s[3], c_te);
                     } else {
                         lik_fast<I, H, O, TASK>(s_lw, s_prop, train, tid, NT, s[0], s[1], c_tr);
-                        lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, s[2], s[3], c_te);
+                        if (!lazy_test) lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, s[2], s[3], c_te);
                     }
                 }
                 __syncthreads();
@@ -1638,6 +1643,16 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 double mh = exp(a);
                 if (!(mh < 1.0)) mh = 1.0;     // min(1, .): overflow -> 1 (R:375); NaN -> 1 (Python min)
                 accept = (double)u < mh;                                              // R:395
+                if (lazy_test && accept) {                                            // R:362 for the proposals that need it
+                    double t[3] = {0.0, 0.0, 0.0};
+                    int ct = 0;
+                    if constexpr (TC) tc::lik_pass<I, H, O, TASK, NT, false>(s_tc, tcst, p.a_test, test.y, test.n, s_prop, t[0], t[1], ct, nullptr, nullptr);
+                    else lik_fast<I, H, O, TASK>(s_lw, s_prop, test, tid, NT, t[0], t[1], ct);
+                    t[2] = (double)ct;
+                    block_sum<3, NT>(t, s_red);
+                    if constexpr (TASK == kTaskReg) rmse_te = sqrt(t[0] / test.n);
+                    else { rmse_te = sqrt(t[1] / test.n); acc_te = 100.0 * (t[2] / test.n); }
+                }
                 // ---- traces of row i+1
                 const size_t ti = (size_t)r * p.S + (i + 1);
                 if (tid == 0) {
