@@ -1454,11 +1454,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
             auto store_state = [&]() {
                 for (int j = tid; j < P; j += NT) {
                     if constexpr (!TC) p.w[(size_t)r * P + j] = s_w[j];
-                    if constexpr (!TEAM) { if (p.memo) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
+                    if constexpr (!TEAM) { if (p.memo && gd_valid > 0) p.gd_cache[(size_t)r * P + j] = s_gd[j]; }
                 }
                 if (tid == 0) {
                     p.eta[r] = eta; p.tau[r] = tau; p.lik[r] = lik; p.prior[r] = prior_cur;
-                    p.n_acc[r] = n_acc; p.init_count[r] = init_count; p.gd_valid[r] = gd_valid;
+                    p.n_acc[r] = n_acc; p.init_count[r] = init_count; p.gd_valid[r] = gd_valid != 0;
                     p.last4[r * 4 + 0] = last_rtr; p.last4[r * 4 + 1] = last_rte;
                     p.last4[r * 4 + 2] = last_atr; p.last4[r * 4 + 3] = last_ate;
                 }
@@ -1490,6 +1490,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     }
                 }
                 const int i = ibase + kq;
+                const int gd_valid0 = gd_valid;      // langevin_gradient(w) known at the window base?
                 bool accept = false;
                 if (kq < W) {
                 // ---- a11: temperature schedule inside the chain (R:317-324)
@@ -1691,16 +1692,27 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 }   // kq < W
                 if (!SPEC) { ++ibase; continue; }
                 // ---- resolve the window
-                if (tid == 0) p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 1) | ((kq < W && accept) ? 1u : 0u);
+                // flag = (window base + 1) << 2 | computed langevin_gradient(w) of the base state << 1 | accepted
+                const bool made_gd = kq < W && !accept && p.memo && gd_valid && !gd_valid0;
+                if (tid == 0)
+                    p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 2) | (made_gd ? 2u : 0u) | ((kq < W && accept) ? 1u : 0u);
                 grid_barrier(&p.spec_bar[r], (unsigned int)K);
-                int kstar = W;
+                int kstar = W, kgd = W;
                 for (int q = 0; q < W; ++q) {
                     const unsigned int f = __ldcg(&p.spec_flag[r * K + q]);
-                    if ((f >> 1) == (unsigned int)(ibase + 1) && (f & 1u)) { kstar = q; break; }
+                    if ((f >> 2) != (unsigned int)(ibase + 1)) continue;
+                    if ((f & 2u) && kgd == W) kgd = q;
+                    if (f & 1u) { kstar = q; break; }
                 }
                 const int committed = min(kstar, W - 1);     // the last step of the window that stands
                 // its CTA holds exactly the chain's state after that step: the accepted vector, or (no
-                // acceptance) the unchanged state with the last proposed tau and any langevin_gradient(w) memo
+                // acceptance) the unchanged state with the last proposed tau.  Without an acceptance the memo
+                // langevin_gradient(w) stays valid for the next window: the first CTA that computed it stores it.
+                if (kstar == W && kgd < W) {
+                    if (kq == kgd && kq != committed)
+                        for (int j = tid; j < P; j += NT) p.gd_cache[(size_t)r * P + j] = s_gd[j];
+                    if (kq == committed && !gd_valid) gd_valid = -1;        // valid, but this CTA does not hold the vector
+                }
                 if (kq == committed) store_state();
                 grid_barrier(&p.spec_bar[r], (unsigned int)K);
                 ibase += committed + 1;
