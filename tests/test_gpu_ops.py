@@ -143,7 +143,8 @@ def test_on_demand_topologies_match_oracle():
     """Topologies outside csrc/ptfnn_topologies.h are compiled on first use (capi.ensure_topology): narrow,
     two-units-per-lane and wide (team kernel, H = 100) hidden layers, regression and classification."""
     rs = np.random.RandomState(17)
-    for task, topo in ((on.REGRESSION, (3, 7, 1)), (on.CLASSIFICATION, (6, 40, 4)), (on.CLASSIFICATION, (5, 100, 3))):
+    for task, topo in ((on.REGRESSION, (3, 7, 1)), (on.CLASSIFICATION, (6, 40, 4)), (on.CLASSIFICATION, (5, 100, 3)),
+                       (on.CLASSIFICATION, (51, 90, 2))):      # the last one: the shape of the reference's Bank set (C:958-971)
         I, H, O = topo
         n = 300
         y = rs.rand(n, 1) if task == on.REGRESSION else rs.randint(0, O, size=(n, 1)).astype(float)
