@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/ptfnn.h"
@@ -687,32 +688,58 @@ extern "C" int ptfnn_swap_uniforms(const ptfnn_sampler *s, int32_t round, float 
 // ------------------------------------------------------------------------------------------
 // traces
 // ------------------------------------------------------------------------------------------
-template <class T>
-static int fetch_rows(ptfnn_sampler *s, const T *dev, size_t row_elems, int first, int count, double *out) {
-    // dev is [R][S][row_elems]; copy rows [first, first+count) of every replica through the pinned staging
-    // buffer of the handle and widen to float64 (the reference's arrays are float64); large blocks are
-    // widened by a few host threads -- the traces of one swap interval of 1024 temperatures are 16 MB
+// One batch of device -> host trace copies: every requested array is copied (2-D, rows [first, first+count) of
+// every replica) into its own region of the handle's pinned staging buffer, ONE stream synchronisation,
+// then widened to the reference's float64 (large blocks by a few host threads: the traces of one swap
+// interval of 1024 temperatures are 16 MB).
+struct TraceFetch {
+    struct Item { const void *dev; size_t elem, row_elems; double *out; size_t off; bool is_int; };
+    std::vector<Item> items;
+    size_t bytes = 0;
+    template <class T>
+    void add(const T *dev, size_t row_elems, double *out, size_t R, int count) {
+        if (!out) return;
+        items.push_back({dev, sizeof(T), row_elems, out, bytes, std::is_integral<T>::value});
+        bytes += ((R * count * row_elems * sizeof(T)) + 255) & ~(size_t)255;
+    }
+};
+
+static int run_fetch(ptfnn_sampler *s, TraceFetch &f, int first, int count) {
+    if (f.items.empty()) return PTFNN_OK;
     const size_t R = s->cfg.n_replicas, S = s->cfg.samples;
-    const size_t n = R * count * row_elems, bytes = n * sizeof(T);
-    if (bytes > s->pinned_bytes) {
+    if (f.bytes > s->pinned_bytes) {
         if (s->pinned) cudaFreeHost(s->pinned);
         s->pinned = nullptr; s->pinned_bytes = 0;
-        CU_TRY(s, cudaHostAlloc(&s->pinned, bytes, cudaHostAllocDefault));
-        s->pinned_bytes = bytes;
+        CU_TRY(s, cudaHostAlloc(&s->pinned, f.bytes, cudaHostAllocDefault));
+        s->pinned_bytes = f.bytes;
     }
-    T *tmp = (T *)s->pinned;
-    CU_TRY(s, cudaMemcpy2DAsync(tmp, count * row_elems * sizeof(T), dev + (size_t)first * row_elems,
-                                S * row_elems * sizeof(T), count * row_elems * sizeof(T), R, cudaMemcpyDeviceToHost, s->stream));
+    char *base = (char *)s->pinned;
+    for (const auto &it : f.items) {
+        const size_t w = count * it.row_elems * it.elem;
+        CU_TRY(s, cudaMemcpy2DAsync(base + it.off, w, (const char *)it.dev + (size_t)first * it.row_elems * it.elem,
+                                    S * it.row_elems * it.elem, w, R, cudaMemcpyDeviceToHost, s->stream));
+    }
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthreads = n < (1u << 20) ? 1 : std::min<size_t>(std::min<unsigned>(hw, 8u), n >> 19);
-    auto widen = [tmp, out](size_t a, size_t b) { for (size_t i = a; i < b; ++i) out[i] = (double)tmp[i]; };
-    if (nthreads <= 1) { widen(0, n); return PTFNN_OK; }
-    std::vector<std::thread> th;
-    const size_t chunk = (n + nthreads - 1) / nthreads;
-    for (size_t k = 1; k < nthreads; ++k) th.emplace_back(widen, std::min(n, k * chunk), std::min(n, (k + 1) * chunk));
-    widen(0, std::min(n, chunk));
-    for (auto &t : th) t.join();
+    for (const auto &it : f.items) {
+        const size_t n = R * count * it.row_elems;
+        const char *src = base + it.off;
+        double *out = it.out;
+        const size_t elem = it.elem;
+        const bool is_int = it.is_int;
+        auto widen = [src, out, elem, is_int](size_t a, size_t b) {
+            if (elem == 8) { const double *t = (const double *)src; for (size_t i = a; i < b; ++i) out[i] = t[i]; }
+            else if (is_int) { const int *t = (const int *)src; for (size_t i = a; i < b; ++i) out[i] = (double)t[i]; }
+            else { const float *t = (const float *)src; for (size_t i = a; i < b; ++i) out[i] = (double)t[i]; }
+        };
+        const size_t nthreads = n < (1u << 20) ? 1 : std::min<size_t>(std::min<unsigned>(hw, 8u), n >> 19);
+        if (nthreads <= 1) { widen(0, n); continue; }
+        std::vector<std::thread> th;
+        const size_t chunk = (n + nthreads - 1) / nthreads;
+        for (size_t k = 1; k < nthreads; ++k) th.emplace_back(widen, std::min(n, k * chunk), std::min(n, (k + 1) * chunk));
+        widen(0, std::min(n, chunk));
+        for (auto &t : th) t.join();
+    }
     return PTFNN_OK;
 }
 
@@ -723,21 +750,25 @@ extern "C" int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, 
     CU_TRY(s, cudaSetDevice(s->cfg.device));
     int rc = sync_and_check(s);
     if (rc) return rc;
-    if (t->pos_w && (rc = fetch_rows(s, s->pos_w.p, s->P, first, count, t->pos_w))) return rc;
-    if (t->lik_prop && (rc = fetch_rows(s, s->lik_prop.p, 1, first, count, t->lik_prop))) return rc;
-    if (t->rmse_train && (rc = fetch_rows(s, s->rmse_tr.p, 1, first, count, t->rmse_train))) return rc;
-    if (t->rmse_test && (rc = fetch_rows(s, s->rmse_te.p, 1, first, count, t->rmse_test))) return rc;
-    if (t->acc_train && (rc = fetch_rows(s, s->acc_tr.p, 1, first, count, t->acc_train))) return rc;
-    if (t->acc_test && (rc = fetch_rows(s, s->acc_te.p, 1, first, count, t->acc_test))) return rc;
-    if (t->accept_list && (rc = fetch_rows(s, s->accept_list.p, 1, first, count, t->accept_list))) return rc;
-    if (t->prior_prop || t->diff_prop || t->mh_prob || t->accepted) {
-        if (!s->cfg.debug_traces) return fail(s, PTFNN_E_STATE, "debug traces were not enabled in the config");
-        if (t->prior_prop && (rc = fetch_rows(s, s->dbg_prior.p, 1, first, count, t->prior_prop))) return rc;
-        if (t->diff_prop && (rc = fetch_rows(s, s->dbg_diff.p, 1, first, count, t->diff_prop))) return rc;
-        if (t->mh_prob && (rc = fetch_rows(s, s->dbg_mh.p, 1, first, count, t->mh_prob))) return rc;
-        if (t->accepted)
-            CU_TRY(s, cudaMemcpy2D(t->accepted, count, s->dbg_acc.p + first, s->cfg.samples, count, s->cfg.n_replicas, cudaMemcpyDeviceToHost));
+    if ((t->prior_prop || t->diff_prop || t->mh_prob || t->accepted) && !s->cfg.debug_traces)
+        return fail(s, PTFNN_E_STATE, "debug traces were not enabled in the config");
+    const size_t R = s->cfg.n_replicas;
+    TraceFetch f;
+    f.add(s->pos_w.p, (size_t)s->P, t->pos_w, R, count);
+    f.add(s->lik_prop.p, 1, t->lik_prop, R, count);
+    f.add(s->rmse_tr.p, 1, t->rmse_train, R, count);
+    f.add(s->rmse_te.p, 1, t->rmse_test, R, count);
+    f.add(s->acc_tr.p, 1, t->acc_train, R, count);
+    f.add(s->acc_te.p, 1, t->acc_test, R, count);
+    f.add(s->accept_list.p, 1, t->accept_list, R, count);
+    if (s->cfg.debug_traces) {
+        f.add(s->dbg_prior.p, 1, t->prior_prop, R, count);
+        f.add(s->dbg_diff.p, 1, t->diff_prop, R, count);
+        f.add(s->dbg_mh.p, 1, t->mh_prob, R, count);
     }
+    if ((rc = run_fetch(s, f, first, count))) return rc;
+    if (t->accepted)
+        CU_TRY(s, cudaMemcpy2D(t->accepted, count, s->dbg_acc.p + first, s->cfg.samples, count, s->cfg.n_replicas, cudaMemcpyDeviceToHost));
     return PTFNN_OK;
 }
 
