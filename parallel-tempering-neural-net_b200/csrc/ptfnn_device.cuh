@@ -265,7 +265,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     return v;
 }
 
-__device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblocks) {
+__device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblocks, bool spin = false) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int gen = ld_acquire_u32(&b->generation);
@@ -277,7 +277,7 @@ __device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblock
         } else {
             const long long t0 = clock64();
             while (ld_acquire_u32(&b->generation) == gen) {
-                __nanosleep(32);
+                if (!spin) __nanosleep(32);          // small groups (speculative windows) poll without backing off
                 if (clock64() - t0 > kBarrierTimeoutCycles) { atomicExch(&b->failed, 1u); break; }   // never hang the device
             }
         }

@@ -1696,7 +1696,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 const bool made_gd = kq < W && !accept && p.memo && gd_valid && !gd_valid0;
                 if (tid == 0)
                     p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 2) | (made_gd ? 2u : 0u) | ((kq < W && accept) ? 1u : 0u);
-                grid_barrier(&p.spec_bar[r], (unsigned int)K);
+                grid_barrier(&p.spec_bar[r], (unsigned int)K, /*spin=*/true);
                 int kstar = W, kgd = W;
                 for (int q = 0; q < W; ++q) {
                     const unsigned int f = __ldcg(&p.spec_flag[r * K + q]);
@@ -1714,7 +1714,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     if (kq == committed && !gd_valid) gd_valid = -1;        // valid, but this CTA does not hold the vector
                 }
                 if (kq == committed) store_state();
-                grid_barrier(&p.spec_bar[r], (unsigned int)K);
+                grid_barrier(&p.spec_bar[r], (unsigned int)K, /*spin=*/true);
                 ibase += committed + 1;
             }
 
