@@ -306,6 +306,21 @@ def run_b200_arm(args, w, rank, world, local_rank):
     ip = (I + 3) & ~3
     h2d = sum((n * ip + ((n + 3) & ~3)) * 4 for n in (w["train"].shape[0], w["test"].shape[0]))
     e2e_value = units_per_step * K / e2e_s
+    # ---- (4) result pipeline on the device traces: burn-in slice -> pooled statistics, HBM-bound.
+    #          Event-timed inside the library on the handle's stream; L2 flushed before every call.
+    pipe = None
+    if rank == 0:
+        n_rows = smp.step
+        smp.trace_summary(1, n_rows)
+        got = []
+        for _ in range(3):
+            flush.fill_(1)
+            torch.cuda.synchronize(dev)
+            got.append(smp.trace_summary(1, n_rows))
+        ms = float(np.mean([g["kernel_ms"] for g in got]))
+        pipe = {"kernel": "trace_summary_kernel<2>", "bound": "hbm", "rows_pooled": int(got[0]["n"]),
+                "algorithmic_bytes_per_launch": int(got[0]["bytes_read"]), "launch_ms": ms,
+                "achieved": got[0]["bytes_read"] / (ms * 1e-3) / 1e9, "unit": "GB/s"}
     smp.close()
 
     if rank != 0:
@@ -382,11 +397,14 @@ def run_b200_arm(args, w, rank, world, local_rank):
                        "replicas_total": Rg, "replica_steps_per_bench_step": units_per_step,
                        "langevin_steps_in_timed_region": n_lg, "random_walk_steps_in_timed_region": n_rw,
                        "memoize_gradient": 0, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": "ladder partitioned over %d GPU(s), boundary swaps via NCCL" % world if world > 1 else "1 GPU, in-kernel swap round"},
+                       "parallelism": "ladder partitioned over %d GPU(s), swap rounds in-kernel over NVLink peer memory" % world if world > 1 else "1 GPU, in-kernel swap round"},
             "value_memoized": value_memo, "ms_per_step_memoized": total_ms_memo / K,
             "e2e": {"value": e2e_value, "unit": "replica-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": K, "clocks": clk, "roofline": roofline, "roofline_alt": roofline_alt,
             "cpu_baseline": cpu, "peaks_measured": peaks, "step_ms": ms_list}
+    if pipe:
+        pipe.update(peak=hbm_peak, frac=pipe["achieved"] / hbm_peak, peak_source=roofline_alt["hbm"]["peak_source"])
+        line["result_pipeline"] = pipe
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

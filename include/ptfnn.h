@@ -170,6 +170,23 @@ int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, const ptfnn
 int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total_swap_proposals,
                          uint8_t *swapped /* [max_rounds, n_replicas_global-1] or NULL */, int32_t max_rounds);
 
+/* ---- result pipeline on the device traces.  Pools rows [first, first+count) of every
+ * local replica -- the reference's burn-in slice, R:777, R:797-824 -- and reduces them on the device:
+ * what main() prints and appends to master_result_file.txt (R:1036-1052) without copying the traces
+ * to the host.  Each series is {mean, np.std (population), min, max}. */
+typedef struct ptfnn_summary {
+    int64_t n;             /* values pooled per series: n_replicas * count */
+    double rmse_train[4];  /* R:1036-1038 */
+    double rmse_test[4];   /* R:1040-1042 */
+    double acc_train[4];   /* C:1130-1136 */
+    double acc_test[4];
+    double *w_mean;        /* [P] posterior mean of every weight over the pooled rows, or NULL */
+    double *w_std;         /* [P] np.std of the same, or NULL (both or neither) */
+    double kernel_ms;      /* device time of the reductions (CUDA events on the handle's stream) */
+    int64_t bytes_read;    /* trace bytes those kernels read */
+} ptfnn_summary;
+int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t count, ptfnn_summary *out);
+
 /* ---- multi-GPU round (ladder partitioned over ranks).  Device pointers are owned by
  * the caller (torch tensors), so that NCCL can move them:
  *   lhood_local  [n_replicas]        float64  swap field of each local replica (R:430 / C:439)

@@ -288,6 +288,7 @@ class ParallelTemperingBase:
         self.posterior_predictive = False   # True: fx_train_all / fx_test_all hold the predictions of every posterior
                                             # sample (one batched GPU pass) instead of the reference's zeros (R:785-788)
         self.last_sampler_seconds = None
+        self.summary = None                 # device-reduced statistics of the last run (Sampler.trace_summary)
         self._traces = None
 
     def default_beta_ladder(self, ndim, ntemps, Tmax):
@@ -373,13 +374,14 @@ class ParallelTemperingBase:
             param1, param2 = param2, param1
         return param1, param2, swapped
 
-    def run_chains(self):
-        """R:694-771.  All replicas and every swap round run as ONE persistent kernel launch."""
+    def _run_sampler(self, want_traces):
+        """The sampling phase of run_chains (R:709-759): all replicas and every swap round are ONE persistent
+        kernel launch.  Also leaves the device-reduced result statistics in ``self.summary``."""
         import time
         if not self.chains:
             raise RuntimeError("initialize_chains(burn_in) must be called first")
-        open(self.path + '/num_exchange.txt', 'a').close()                        # R:704 (opened, never written)
         S = self.NumSamples
+        burnin = int(S * self.burn_in)
         seed = int(np.random.randint(0, 2 ** 31 - 1)) if self.seed is None else int(self.seed)
         l_prob = self.langevin_prob if self.TASK == REGRESSION else 0.5           # C:192
         t0 = time.perf_counter()
@@ -390,15 +392,23 @@ class ParallelTemperingBase:
             s.set_data(self.traindata, self.testdata)
             s.init_chains(np.stack([np.asarray(c.w, dtype=np.float64) for c in self.chains]))
             s.run()
-            t = s.traces()
+            self.summary = s.trace_summary(burnin, S - burnin) if S > burnin else None
+            t = s.traces() if want_traces else s.traces(first=S - 1, count=1, pos_w=False)
             st = s.get_state()
             ns, tot, _ = s.swap_stats()
         self.last_sampler_seconds = time.perf_counter() - t0
-        self._traces, self._state = t, st
         self.num_swap += ns
         self.total_swap_proposals += tot
         for k, c in enumerate(self.chains):
             c.w = st["w"][k]
+        return t, st
+
+    def run_chains(self):
+        """R:694-771."""
+        open(self.path + '/num_exchange.txt', 'a').close()                        # R:704 (opened, never written)
+        S = self.NumSamples
+        t, st = self._run_sampler(True)
+        self._traces, self._state = t, st
         if self.write_files:
             for k in range(self.num_chains):
                 _write_chain_files(self.path, self.temperatures[k], self.TASK, S, t, k, int(st["num_accepted"][k]))
@@ -408,6 +418,20 @@ class ParallelTemperingBase:
         swap_perc = self.num_swap * 100 / self.total_swap_proposals              # ZeroDivisionError if no round ran, as R:769
         return (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_vec, swap_perc,
                 accept_vec, accept)
+
+    def run_summary(self):
+        """Not in the reference: run_chains() for callers that only want what main() reports.
+        The burn-in slice is pooled and reduced on the device (R:777, R:1036-1044, C:1130-1136), so neither the
+        S x P traces nor any txt file leave the GPU.  -> dict with the series statistics
+        ({mean, std, min, max} of rmse_train / rmse_test / acc_train / acc_test), the posterior mean / std of
+        every weight, swap_perc (R:769) and accept_per (R:1009-1011)."""
+        S = self.NumSamples
+        t, st = self._run_sampler(False)
+        out = dict(self.summary)
+        out["swap_perc"] = self.num_swap * 100 / self.total_swap_proposals
+        out["accept_per"] = float(np.mean(t["accept_list"][:, -1] / S) * 100)     # Q16: the count BEFORE the last step
+        out["num_accepted"] = st["num_accepted"]
+        return out
 
     # -- R:775-871 / C:780-893
     def _lik_rows(self, burnin):

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ptfnn_abi_version", "ptfnn_build_info", "ptfnn_device_count", "ptfnn_default_config", "ptfnn_last_error",
     "ptfnn_create", "ptfnn_destroy", "ptfnn_set_stream", "ptfnn_set_data", "ptfnn_init_chains",
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
-    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats",
+    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
@@ -57,6 +57,12 @@ class Draws(C.Structure):
 class Traces(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("pos_w", "lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test",
                                           "accept_list", "prior_prop", "diff_prop", "mh_prob", "accepted")]
+
+
+class Summary(C.Structure):
+    _fields_ = [("n", C.c_int64), ("rmse_train", C.c_double * 4), ("rmse_test", C.c_double * 4),
+                ("acc_train", C.c_double * 4), ("acc_test", C.c_double * 4), ("w_mean", C.c_void_p),
+                ("w_std", C.c_void_p), ("kernel_ms", C.c_double), ("bytes_read", C.c_int64)]
 
 
 _lib = None

@@ -93,8 +93,9 @@ def load_problem(problem, data_root):
 
 
 def run_problem(problem, data_root, out_root, *, NumSample=50000, maxtemp=10, swap_ratio=0.02, num_chains=10,
-                burn_in=0.5, learn_rate=0.01, use_langevin_gradients=False, seed=None):
-    """One iteration of the reference's main() loop (C:901-1147) without the plots."""
+                burn_in=0.5, learn_rate=0.01, use_langevin_gradients=False, seed=None, results="host"):
+    """One iteration of the reference's main() loop (C:901-1147) without the plots.
+    results="device": the statistics of the row are reduced on the device traces (run_summary)."""
     name, traindata, testdata, topology = load_problem(problem, data_root)
     swap_interval = int(swap_ratio * (NumSample / num_chains))                   # C:1045
     run_nb = 0
@@ -109,16 +110,21 @@ def run_problem(problem, data_root, out_root, *, NumSample=50000, maxtemp=10, sw
     for d in RESULT_DIRS:
         pt.make_directory(path + d)
     pt.initialize_chains(burn_in)
-    (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_rep, swap_perc, accept_vec,
-     accept) = pt.run_chains()
-    list_end = accept_vec.shape[1]
-    accept_ratio = accept_vec[:, list_end - 1:list_end] / list_end
-    accept_per = np.mean(accept_ratio) * 100
+    if results == "device":
+        sm = pt.run_summary()
+        tr, te, swap_perc, accept_per = sm["acc_train"], sm["acc_test"], sm["swap_perc"], sm["accept_per"]
+        stats = [tr["mean"], tr["std"], tr["max"], te["mean"], te["std"], te["max"]]
+    else:
+        (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_rep, swap_perc, accept_vec,
+         accept) = pt.run_chains()
+        list_end = accept_vec.shape[1]
+        accept_ratio = accept_vec[:, list_end - 1:list_end] / list_end
+        accept_per = np.mean(accept_ratio) * 100
+        stats = [np.mean(acc_train), np.std(acc_train), np.amax(acc_train),
+                 np.mean(acc_test), np.std(acc_test), np.amax(acc_test)]
     timetotal = (time.time() - timer) / 60
-    allres = np.asarray([problem, NumSample, maxtemp, swap_interval, use_langevin_gradients, learn_rate,
-                         np.mean(acc_train), np.std(acc_train), np.amax(acc_train),
-                         np.mean(acc_test), np.std(acc_test), np.amax(acc_test),
-                         swap_perc, accept_per, timetotal])                     # C:1138
+    allres = np.asarray([problem, NumSample, maxtemp, swap_interval, use_langevin_gradients, learn_rate] + stats +
+                        [swap_perc, accept_per, timetotal])                     # C:1138
     xv = name + '_' + str(run_nb)
     for fn in (os.path.join(path, 'result.txt'), os.path.join(out_root, 'master_result_file.txt')):
         with open(fn, "a+") as f:

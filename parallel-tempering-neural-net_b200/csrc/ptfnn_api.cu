@@ -134,7 +134,7 @@ struct ptfnn_sampler {
     DevBuf<float> d_lx, d_z, d_zeta, d_u, d_uswap;   // replay staging
     DevBuf<int> d_src, smsp_load, swap_src;
     DevBuf<uint8_t> d_swapped;
-    DevBuf<double> d_scratch;
+    DevBuf<double> d_scratch, d_summary;
 
     void release_all() {
         if (pinned) cudaFreeHost(pinned);
@@ -153,7 +153,7 @@ struct ptfnn_sampler {
         }
         peer_flags.release(); spec_bar.release(); spec_flag.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
-        d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release();
+        d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release(); d_summary.release();
     }
 };
 
@@ -293,7 +293,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
         s->release_all(); delete s; cudaGetLastError(); return rc;                            \
     }
     ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(gd_cache, R * P); ALLOC(pgd_buf, cfg->n_hidden > 64 ? R * P : 1);
-    ALLOC(pos_w, R * S * P); ALLOC(pub_rows, 2 * R * (P + 1)); ALLOC(pub_lhood, 2 * (size_t)Rg);
+    ALLOC(pos_w, R * S * P + kSumTracePadFloats); ALLOC(pub_rows, 2 * R * (P + 1)); ALLOC(pub_lhood, 2 * (size_t)Rg);
     ALLOC(eta, R); ALLOC(tau, R); ALLOC(lik, R); ALLOC(prior, R); ALLOC(last4, R * 4); ALLOC(init_rmse, R * 2);
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
@@ -792,6 +792,78 @@ extern "C" int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t
         }
     }
     return PTFNN_OK;
+}
+
+// Result pipeline on the device traces (R:775-871 slicing, R:1036-1052 statistics).
+extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t count, ptfnn_summary *out) {
+    if (!s || !out) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    if (first < 0 || count < 1 || first + count > s->cfg.samples) return fail(s, PTFNN_E_INVALID, "rows [%d,%d) outside [0,%d)", first, first + count, s->cfg.samples);
+    if ((out->w_mean == nullptr) != (out->w_std == nullptr)) return fail(s, PTFNN_E_INVALID, "w_mean and w_std go together");
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    int rc = sync_and_check(s);
+    if (rc) return rc;
+    const int R = s->cfg.n_replicas, S = s->cfg.samples, P = s->P;
+    const bool moments = out->w_mean != nullptr;
+    const int cols = !moments || P <= kSumThreads ? 1 : P <= 2 * kSumThreads ? 2 : P <= 4 * kSumThreads ? 4 : 8;
+    const int ctiles = moments ? (P + kSumThreads * cols - 1) / (kSumThreads * cols) : 0;
+    int gx = std::max(1, std::min(R, s->num_sms));
+    if (moments) {                                                           // persistent: two blocks per SM over all planes
+        const int rpc = sum_rows_per_chunk(P, cols, ctiles == 1);
+        const long long items = (long long)R * ((count + rpc - 1) / rpc);
+        gx = (int)std::max<long long>(1, std::min<long long>(items, std::max(1, 2 * s->num_sms / ctiles)));
+    }
+    // layout of d_summary: stats[16] | acc[2P] | mean[P] | std[P] | part[4*gx*4] | ticket
+    const size_t need = 16 + 4 * (size_t)P + 16 * (size_t)gx + 1;
+    if (need > s->d_summary.n) {
+        CU_TRY(s, s->d_summary.ensure(need));
+        CU_TRY(s, cudaMemsetAsync(s->d_summary.p, 0, need * sizeof(double), s->stream));   // acc and ticket start at zero; the kernel leaves them so
+    }
+    double *d_stats = s->d_summary.p, *d_acc = d_stats + 16, *d_mean = d_acc + 2 * P, *d_std = d_mean + P, *d_part = d_std + P;
+    static bool smem_opted = false;
+    if (!smem_opted) {
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        smem_opted = true;
+    }
+    cudaEvent_t e0, e1;
+    CU_TRY(s, cudaEventCreate(&e0));
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return fail(s, PTFNN_E_CUDA, "cudaEventCreate"); }
+    auto done = [&](int code) { cudaEventDestroy(e0); cudaEventDestroy(e1); return code; };
+#define SUM_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return done(fail(s, PTFNN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_))); } while (0)
+    TraceSummaryArgs a;
+    a.pos_w = s->pos_w.p;
+    a.series[0] = s->rmse_tr.p; a.series[1] = s->rmse_te.p; a.series[2] = s->acc_tr.p; a.series[3] = s->acc_te.p;
+    a.R = R; a.S = S; a.P = P; a.first = first; a.count = count; a.ctiles = ctiles;
+    a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_part + 16 * (size_t)gx);
+    a.stats = d_stats; a.mean = d_mean; a.stdev = d_std;
+    const dim3 grid(gx, ctiles + 4);
+    const size_t smem = moments ? kSumSmemBytes : 0;
+    SUM_TRY(cudaEventRecord(e0, s->stream));
+    if (cols == 1) trace_summary_kernel<1><<<grid, kSumThreads, smem, s->stream>>>(a);
+    else if (cols == 2) trace_summary_kernel<2><<<grid, kSumThreads, smem, s->stream>>>(a);
+    else if (cols == 4) trace_summary_kernel<4><<<grid, kSumThreads, smem, s->stream>>>(a);
+    else trace_summary_kernel<8><<<grid, kSumThreads, smem, s->stream>>>(a);
+    SUM_TRY(cudaGetLastError());
+    SUM_TRY(cudaEventRecord(e1, s->stream));
+    double host[16];
+    SUM_TRY(cudaMemcpyAsync(host, d_stats, sizeof host, cudaMemcpyDeviceToHost, s->stream));
+    if (moments) {
+        SUM_TRY(cudaMemcpyAsync(out->w_mean, d_mean, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        SUM_TRY(cudaMemcpyAsync(out->w_std, d_std, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    SUM_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    SUM_TRY(cudaEventElapsedTime(&ms, e0, e1));
+#undef SUM_TRY
+    out->n = (int64_t)R * count;
+    memcpy(out->rmse_train, host, 32); memcpy(out->rmse_test, host + 4, 32);
+    memcpy(out->acc_train, host + 8, 32); memcpy(out->acc_test, host + 12, 32);
+    out->kernel_ms = ms;
+    out->bytes_read = (int64_t)R * count * (4 * 8 + (moments ? (int64_t)P * 4 : 0));
+    return done(PTFNN_OK);
 }
 
 // ------------------------------------------------------------------------------------------

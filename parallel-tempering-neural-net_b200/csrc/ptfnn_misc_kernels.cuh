@@ -76,6 +76,257 @@ __global__ void op_forward_row_kernel(int I, int H, int O, const float *x, const
     }
 }
 
+// ---- result pipeline on the device traces ----
+// The reference slices every trace at the burn-in row and pools chains x samples (R:775-871); its main()
+// then reports mean / np.std / min of the pooled RMSE columns (R:1036-1044).  trace_summary_kernel does
+// that reduction where the traces already are, in ONE launch, so a summary costs one read of the trace at
+// HBM speed instead of the device->host copy (and the txt round trip) of R x S x P values.
+//
+// Planes of the grid (blockIdx.y):
+//   [0, ctiles)        posterior moments: for every parameter p, sum and sum of squares of
+//                      (pos_w[r, first+i, p] - pivot[p]) over all local replicas r and rows i < count;
+//                      pivot[p] = pos_w[0, first, p] keeps the second moment free of cancellation (np.std is
+//                      two-pass).  HBM-bound: R*count*P floats read exactly once; fp64 sums.
+//                      Persistent blocks (2 per SM) stream the trace through a 3-stage ring of 32 KB shared-
+//                      memory buffers filled by 1-D TMA bulk copies (~190 KB in flight per SM, no registers
+//                      tied up by loads); the 256 threads then read a stage conflict-free with FIXED columns
+//                      per thread, so there is no index arithmetic per element.  The burn-in slice of one
+//                      replica is a contiguous span of count*P floats: when one column tile covers the row
+//                      (P <= 2048) a stage is one copy of as many whole rows as fit, and P < 256 packs
+//                      `groups` = 256/P adjacent rows into each pass of the block; wider nets tile the
+//                      columns by 2048 (one plane per tile) and a stage holds four row pieces.  Rows are not
+//                      16-byte aligned (P is odd as a rule): every copy starts at the aligned address below
+//                      its first element and the reader skips the `shift` floats in front.
+//   [ctiles, ctiles+4) the scalar series rmse_train, rmse_test, acc_train, acc_test (fp64 [R, S]): blocks
+//                      stride over the replicas and leave partial {sum, sum of squares, min, max}.
+// The last block to finish (ticket counter) folds everything into {mean, np.std, min, max} per series and
+// mean / np.std per parameter, then clears the accumulators for the next call.
+constexpr int kSumThreads = 256;
+constexpr int kSumStages = 3;
+constexpr int kSumMaxCols = 8;
+constexpr int kSumPad = 8;                                                       // slack per staged piece (alignment at both ends)
+constexpr int kSumStageFloats = 4 * (kSumThreads * kSumMaxCols + kSumPad);       // 8224 floats
+constexpr size_t kSumSmemBytes = (size_t)kSumStages * kSumStageFloats * sizeof(float) + kSumStages * sizeof(uint64_t);
+constexpr int kSumTracePadFloats = 4;    // the trace allocation ends with this much padding: aligned copies may run past the last row
+
+struct TraceSummaryArgs {
+    const float *pos_w;        // [R, S, P] (+ kSumTracePadFloats)
+    const double *series[4];   // [R, S] each
+    int R, S, P, first, count, ctiles;
+    double *acc;               // [2][P], zero on entry, zero on exit
+    double *part;              // [4][gridDim.x][4]
+    unsigned int *ticket;      // zero on entry, zero on exit
+    double *stats;             // out [4][4]
+    double *mean, *stdev;      // out [P] (ctiles > 0)
+};
+
+__device__ __forceinline__ const double *series_of(const TraceSummaryArgs &a, int k) {   // (no dynamic indexing of a kernel parameter)
+    return k == 0 ? a.series[0] : k == 1 ? a.series[1] : k == 2 ? a.series[2] : a.series[3];
+}
+
+__device__ __forceinline__ void fold4(double &s1, double &s2, double &lo, double &hi) {
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+}
+
+// rows of one stage: whole rows back to back, or row pieces at a fixed pitch
+__host__ __device__ inline int sum_rows_per_chunk(int P, int cols, bool whole) {
+    const int n = whole ? (kSumStageFloats - kSumPad) / P : kSumStageFloats / (kSumThreads * cols + kSumPad);
+    return n < 1 ? 1 : n;
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const TraceSummaryArgs a) {
+    extern __shared__ __align__(128) unsigned char sum_smem[];
+    __shared__ double s_fold[4][kSumThreads / 32];
+    __shared__ bool s_last;
+    const int P = a.P, count = a.count, tid = threadIdx.x;
+    if ((int)blockIdx.y < a.ctiles) {
+        constexpr int CW = kSumThreads * COLS, PITCH = CW + kSumPad;
+        float *stage = reinterpret_cast<float *>(sum_smem);
+        uint64_t *full = reinterpret_cast<uint64_t *>(sum_smem + (size_t)kSumStages * kSumStageFloats * sizeof(float));
+        const bool whole = a.ctiles == 1;
+        const int c0 = blockIdx.y * CW, cw = min(P - c0, CW);
+        const int width = min(cw, kSumThreads);
+        const int groups = whole ? kSumThreads / width : 1;
+        const int g = tid / width, c = tid - g * width;
+        const int rpc = sum_rows_per_chunk(P, COLS, whole);
+        const int chunks_per_rep = (count + rpc - 1) / rpc;
+        const int items = a.R * chunks_per_rep;
+        const int n_mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        double s1[COLS], s2[COLS], pivot[COLS];
+        bool live[COLS];
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+            live[k] = g < groups && c + k * kSumThreads < cw;
+            s1[k] = s2[k] = 0.0;
+            pivot[k] = live[k] ? (double)__ldg(a.pos_w + (size_t)a.first * P + c0 + c + k * kSumThreads) : 0.0;
+        }
+        auto locate = [&](int n, int &r, int &i0, int &nrows) {
+            const int t = blockIdx.x + n * gridDim.x;
+            r = t / chunks_per_rep;
+            i0 = (t - r * chunks_per_rep) * rpc;
+            nrows = min(rpc, count - i0);
+        };
+        auto issue = [&](int n) {                                   // one thread: fill stage n % kSumStages with item n
+            int r, i0, nrows;
+            locate(n, r, i0, nrows);
+            const int slot = n % kSumStages;
+            float *dst = stage + (size_t)slot * kSumStageFloats;
+            const size_t row0 = (size_t)r * a.S + a.first + i0;
+            if (whole) {
+                const size_t e0 = row0 * P, e1 = e0 + (size_t)nrows * P;
+                const size_t b0 = e0 & ~(size_t)3, b1 = (e1 + 3) & ~(size_t)3;
+                const uint32_t bytes = (uint32_t)(b1 - b0) * 4u;
+                mbar_arrive_expect_tx(&full[slot], bytes);
+                tma_load_1d(dst, a.pos_w + b0, bytes, &full[slot]);
+            } else {
+                uint32_t bytes = 0;
+                for (int i = 0; i < nrows; ++i) {
+                    const size_t e0 = (row0 + i) * P + c0, e1 = e0 + cw;
+                    bytes += (uint32_t)(((e1 + 3) & ~(size_t)3) - (e0 & ~(size_t)3)) * 4u;
+                }
+                mbar_arrive_expect_tx(&full[slot], bytes);
+                for (int i = 0; i < nrows; ++i) {
+                    const size_t e0 = (row0 + i) * P + c0, e1 = e0 + cw;
+                    const size_t b0 = e0 & ~(size_t)3, b1 = (e1 + 3) & ~(size_t)3;
+                    tma_load_1d(dst + (size_t)i * PITCH, a.pos_w + b0, (uint32_t)(b1 - b0) * 4u, &full[slot]);
+                }
+            }
+        };
+        if (tid == 0) {
+            for (int q = 0; q < kSumStages; ++q) mbar_init(&full[q], 1);
+            mbar_fence_init();
+            for (int n = 0; n < min(kSumStages, n_mine); ++n) issue(n);
+        }
+        __syncthreads();
+        for (int n = 0; n < n_mine; ++n) {
+            int r, i0, nrows;
+            locate(n, r, i0, nrows);
+            const int slot = n % kSumStages;
+            const float *src = stage + (size_t)slot * kSumStageFloats + c;
+            const size_t row0 = (size_t)r * a.S + a.first + i0;
+            mbar_wait(&full[slot], (uint32_t)(n / kSumStages) & 1u);
+            if (whole) {
+                const float *p = src + (int)((row0 * P) & 3) + g * P;           // row j*groups + g, columns c + 256k
+                const int stride = groups * P;
+                const int full_passes = nrows / groups;
+                int j = 0;
+                for (; j + 4 <= full_passes; j += 4) {
+                    float v[4][COLS];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < COLS; ++k) v[u][k] = live[k] ? p[(j + u) * stride + k * kSumThreads] : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < COLS; ++k) {
+                            const double d = (double)v[u][k] - pivot[k];
+                            s1[k] += d; s2[k] = fma(d, d, s2[k]);
+                        }
+                }
+                for (; j * groups + g < nrows; ++j)
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k)
+                        if (live[k]) {
+                            const double d = (double)p[j * stride + k * kSumThreads] - pivot[k];
+                            s1[k] += d; s2[k] = fma(d, d, s2[k]);
+                        }
+            } else {
+                for (int i = 0; i < nrows; ++i) {
+                    const float *p = src + (size_t)i * PITCH + (int)(((row0 + i) * P + c0) & 3);
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k)
+                        if (live[k]) {
+                            const double d = (double)p[k * kSumThreads] - pivot[k];
+                            s1[k] += d; s2[k] = fma(d, d, s2[k]);
+                        }
+                }
+            }
+            __syncthreads();                                            // the stage is drained: refill it
+            if (tid == 0 && n + kSumStages < n_mine) issue(n + kSumStages);
+        }
+        if (groups == 1) {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k)
+                if (live[k]) {
+                    atomicAdd(a.acc + c0 + c + k * kSumThreads, s1[k]);
+                    atomicAdd(a.acc + P + c0 + c + k * kSumThreads, s2[k]);
+                }
+        } else {                                                        // P < 256: fold the row groups first (COLS = 1)
+            double *red = reinterpret_cast<double *>(sum_smem);         // every copy has landed and been read
+            red[tid] = s1[0]; red[kSumThreads + tid] = s2[0];
+            __syncthreads();
+            if (g == 0) {
+                double x = 0.0, y = 0.0;
+                for (int gg = 0; gg < groups; ++gg) { x += red[gg * width + c]; y += red[kSumThreads + gg * width + c]; }
+                atomicAdd(a.acc + c, x);
+                atomicAdd(a.acc + P + c, y);
+            }
+        }
+    } else {
+        const int sidx = blockIdx.y - a.ctiles;
+        const double *x = series_of(a, sidx);
+        const double pivot = x[a.first];
+        double s1 = 0.0, s2 = 0.0, lo = pivot, hi = pivot;
+        for (int r = blockIdx.x; r < a.R; r += gridDim.x) {
+            const double *row = x + (size_t)r * a.S + a.first;
+            for (int i = tid; i < count; i += kSumThreads) {
+                const double v = __ldcs(row + i), d = v - pivot;
+                s1 += d; s2 = fma(d, d, s2);
+                lo = fmin(lo, v); hi = fmax(hi, v);
+            }
+        }
+        fold4(s1, s2, lo, hi);
+        const int warp = tid >> 5;
+        if ((tid & 31) == 0) { s_fold[0][warp] = s1; s_fold[1][warp] = s2; s_fold[2][warp] = lo; s_fold[3][warp] = hi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < kSumThreads / 32; ++k) {
+                s1 += s_fold[0][k]; s2 += s_fold[1][k]; lo = fmin(lo, s_fold[2][k]); hi = fmax(hi, s_fold[3][k]);
+            }
+            double *o = a.part + ((size_t)sidx * gridDim.x + blockIdx.x) * 4;
+            o[0] = s1; o[1] = s2; o[2] = lo; o[3] = hi;
+        }
+    }
+    // ---- the last block folds the partial results
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double n = (double)a.R * (double)count;
+    if (tid < 128) {
+        const int sidx = tid >> 5, lane = tid & 31;
+        const double pivot = series_of(a, sidx)[a.first];
+        double s1 = 0.0, s2 = 0.0, lo = pivot, hi = pivot;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const double *o = a.part + ((size_t)sidx * gridDim.x + b) * 4;
+            s1 += __ldcg(o); s2 += __ldcg(o + 1); lo = fmin(lo, __ldcg(o + 2)); hi = fmax(hi, __ldcg(o + 3));
+        }
+        fold4(s1, s2, lo, hi);
+        if (lane == 0) {
+            const double m = s1 / n, var = s2 / n - m * m;
+            double *o = a.stats + 4 * sidx;
+            o[0] = pivot + m; o[1] = sqrt(var > 0.0 ? var : 0.0); o[2] = lo; o[3] = hi;
+        }
+    }
+    if (a.ctiles > 0)
+        for (int p = tid; p < P; p += kSumThreads) {
+            const double m = __ldcg(a.acc + p) / n, var = __ldcg(a.acc + P + p) / n - m * m;
+            a.mean[p] = (double)a.pos_w[(size_t)a.first * P + p] + m;
+            a.stdev[p] = sqrt(var > 0.0 ? var : 0.0);
+            a.acc[p] = 0.0; a.acc[P + p] = 0.0;
+        }
+    if (tid == 0) *a.ticket = 0u;
+}
+
 // multi-GPU: install the rows selected by the sweep (R:435-437)
 __global__ void swap_apply_kernel(int R, int P, int replica_offset, const int *src, const float *rows_local,
                                   const float *rows_in, float *w, double *eta, int *gd_valid) {

@@ -68,9 +68,11 @@ PROBLEMS = {1: "Lazer", 2: "Sunspot", 3: "Mackey", 4: "Lorenz", 5: "Rossler", 6:
 
 def run_problem(problem, data_root, out_root, *, hidden=5, NumSample=100000, maxtemp=2, swap_ratio=0.01,
                 num_chains=10, burn_in=0.5, learn_rate=0.1, use_langevin_gradients=True, langevin_prob=0.5,
-                seed=None):
+                seed=None, results="host"):
     """One iteration of the reference's main() loop (R:879-1061) without the plots: runs the
-    sampler and appends the 15-number row to master_result_file.txt / result.txt."""
+    sampler and appends the 15-number row to master_result_file.txt / result.txt.
+    results="host": run_chains() as the reference does (per-chain txt files, the 11-tuple);
+    results="device": the statistics of the row are reduced on the device traces (run_summary)."""
     name = PROBLEMS[problem]
     traindata = np.loadtxt(os.path.join(data_root, "Data_OneStepAhead", name, "train.txt"))
     testdata = np.loadtxt(os.path.join(data_root, "Data_OneStepAhead", name, "test.txt"))
@@ -88,16 +90,21 @@ def run_problem(problem, data_root, out_root, *, hidden=5, NumSample=100000, max
     for d in RESULT_DIRS:
         pt.make_directory(path + d)
     pt.initialize_chains(burn_in)
-    (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_rep, swap_perc, accept_vec,
-     accept) = pt.run_chains()
-    list_end = accept_vec.shape[1]
-    accept_ratio = accept_vec[:, list_end - 1:list_end] / list_end               # R:1009-1011 (Q16)
-    accept_per = np.mean(accept_ratio) * 100
+    if results == "device":
+        sm = pt.run_summary()
+        tr, te, swap_perc, accept_per = sm["rmse_train"], sm["rmse_test"], sm["swap_perc"], sm["accept_per"]
+        stats = [tr["mean"], tr["std"], tr["min"], te["mean"], te["std"], te["min"]]
+    else:
+        (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_rep, swap_perc, accept_vec,
+         accept) = pt.run_chains()
+        list_end = accept_vec.shape[1]
+        accept_ratio = accept_vec[:, list_end - 1:list_end] / list_end           # R:1009-1011 (Q16)
+        accept_per = np.mean(accept_ratio) * 100
+        stats = [np.mean(rmse_train), np.std(rmse_train), np.amin(rmse_train),
+                 np.mean(rmse_test), np.std(rmse_test), np.amin(rmse_test)]
     timetotal = (time.time() - timer) / 60
-    allres = np.asarray([problem, NumSample, maxtemp, swap_interval, langevin_prob, learn_rate,
-                         np.mean(rmse_train), np.std(rmse_train), np.amin(rmse_train),
-                         np.mean(rmse_test), np.std(rmse_test), np.amin(rmse_test),
-                         swap_perc, accept_per, timetotal])                     # R:1052
+    allres = np.asarray([problem, NumSample, maxtemp, swap_interval, langevin_prob, learn_rate] + stats +
+                        [swap_perc, accept_per, timetotal])                     # R:1052
     xv = name + '_' + str(run_nb)
     for fn in (os.path.join(path, 'result.txt'), os.path.join(out_root, 'master_result_file.txt')):
         with open(fn, "a+") as f:

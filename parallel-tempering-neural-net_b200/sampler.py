@@ -194,6 +194,24 @@ class Sampler:
             out["accepted"] = out["accepted"].astype(bool)
         return out
 
+    def trace_summary(self, first=0, count=None, posterior=True):
+        """The reference's result statistics (R:1036-1044: mean / np.std / min of the pooled RMSE columns
+        after the burn-in slice, R:777) reduced on the device -- the traces are not copied to the host.
+        -> dict: n, rmse_train / rmse_test / acc_train / acc_test = {mean, std, min, max},
+        w_mean[P], w_std[P] (posterior moments of every weight), kernel_ms, bytes_read."""
+        count = self.S - first if count is None else count
+        sm = capi.Summary()
+        wm = ws = None
+        if posterior:
+            wm, ws = np.empty(self.P), np.empty(self.P)
+            sm.w_mean, sm.w_std = capi.ptr(wm), capi.ptr(ws)
+        self._ck(self._lib.ptfnn_trace_summary(self._h, int(first), int(count), C.byref(sm)))
+        out = {"n": sm.n, "kernel_ms": sm.kernel_ms, "bytes_read": sm.bytes_read, "w_mean": wm, "w_std": ws}
+        for k in ("rmse_train", "rmse_test", "acc_train", "acc_test"):
+            v = getattr(sm, k)
+            out[k] = {"mean": v[0], "std": v[1], "min": v[2], "max": v[3]}
+        return out
+
     def swap_stats(self, max_rounds=None):
         """-> (num_swap, total_swap_proposals, swapped[rounds, Rg-1])"""
         ns, tot = C.c_int64(), C.c_int64()
