@@ -107,7 +107,7 @@ struct ptfnn_sampler {
     void *pinned = nullptr;           // host staging buffer of get_traces (page-locked, grows on demand)
     size_t pinned_bytes = 0;
 
-    bool have_data = false, have_state = false;
+    bool have_data = false, have_state = false, summary_smem_opted = false;
     int n_train = 0, n_test = 0;
     int step = 0, rounds_done = 0;
     bool swap_pending = false, pending_final = false;
@@ -820,13 +820,12 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
         CU_TRY(s, cudaMemsetAsync(s->d_summary.p, 0, need * sizeof(double), s->stream));   // acc and ticket start at zero; the kernel leaves them so
     }
     double *d_stats = s->d_summary.p, *d_acc = d_stats + 16, *d_mean = d_acc + 2 * P, *d_std = d_mean + P, *d_part = d_std + P;
-    static bool smem_opted = false;
-    if (!smem_opted) {
+    if (!s->summary_smem_opted) {                                            // per device, so per handle
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
-        smem_opted = true;
+        s->summary_smem_opted = true;
     }
     cudaEvent_t e0, e1;
     CU_TRY(s, cudaEventCreate(&e0));
