@@ -34,6 +34,35 @@ def partition(n_global: int, world: int, rank: int):
     return rank * per, per
 
 
+SERIES = ("rmse_train", "rmse_test", "acc_train", "acc_test")
+
+
+def combine_summaries(parts):
+    """Pool the per-rank results of ``Sampler.trace_summary`` (each over that rank's block of the ladder)
+    into the statistics of the whole ladder: what the reference computes over all chains at once
+    (R:1036-1044).  Exact up to fp64 rounding: mean = sum n_k m_k / n, var = sum n_k (s_k^2 + (m_k - mean)^2) / n."""
+    parts = [p for p in parts if p is not None and p["n"] > 0]
+    n = float(sum(p["n"] for p in parts))
+    out = {"n": int(n)}
+
+    def pool(ms, ss):
+        ms, ss = np.asarray(ms, dtype=np.float64), np.asarray(ss, dtype=np.float64)
+        wts = np.asarray([p["n"] for p in parts], dtype=np.float64).reshape((-1,) + (1,) * (ms.ndim - 1)) / n
+        mean = (wts * ms).sum(axis=0)
+        var = (wts * (ss * ss + (ms - mean) ** 2)).sum(axis=0)
+        return mean, np.sqrt(var)
+
+    for k in SERIES:
+        mean, std = pool([p[k]["mean"] for p in parts], [p[k]["std"] for p in parts])
+        out[k] = {"mean": float(mean), "std": float(std), "min": min(p[k]["min"] for p in parts),
+                  "max": max(p[k]["max"] for p in parts)}
+    if all(p.get("w_mean") is not None for p in parts):
+        out["w_mean"], out["w_std"] = pool([p["w_mean"] for p in parts], [p["w_std"] for p in parts])
+    else:
+        out["w_mean"] = out["w_std"] = None
+    return out
+
+
 class GpuChains:
     """The local block of the ladder on this rank's GPU (libptfnn handle + torch swap buffers)."""
 
@@ -116,6 +145,16 @@ class PartitionedLadder:
                 req.wait()
         self.chains.swap_apply(src, rows_local, rows_in)
         return src
+
+    def summary(self, first=0, count=None, posterior=True):
+        """Result statistics of the WHOLE ladder: every rank reduces its own traces on its
+        GPU (Sampler.trace_summary), the few numbers per rank are all-gathered and pooled; identical on
+        every rank."""
+        mine = self.chains.s.trace_summary(first, count, posterior)
+        mine = {k: v for k, v in mine.items() if k not in ("kernel_ms", "bytes_read")}
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine, group=self.group)
+        return combine_summaries(parts)
 
     def run(self, n_steps=None, draws=None, u_swap=None):
         """Advance every rank's block by up to ``n_steps`` steps, completing the swap rounds that fall

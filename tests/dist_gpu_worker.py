@@ -45,6 +45,7 @@ def main():
         ladder.run(None)
     t = smp.traces()
     ns, tot, sw = smp.swap_stats()
+    pooled = ladder.summary(S // 2, S - S // 2)              # collective: every rank
     st = smp.get_state()
     pack = np.concatenate([t["pos_w"].reshape(n, -1), t["lik_prop"], t["accept_list"], st["w"], st["eta"][:, None]], axis=1)
     mine = torch.from_numpy(pack).cuda()
@@ -62,6 +63,7 @@ def main():
             else:
                 one.run()
             t1 = one.traces()
+            sm1 = one.trace_summary(S // 2, S - S // 2)
             ns1, tot1, sw1 = one.swap_stats()
             st1 = one.get_state()
         ref = np.concatenate([t1["pos_w"].reshape(Rg, -1), t1["lik_prop"], t1["accept_list"], st1["w"], st1["eta"][:, None]], axis=1)
@@ -70,6 +72,11 @@ def main():
         ok &= (ns, tot) == (ns1, tot1) and np.array_equal(sw, sw1)
         ok &= peer or int(moved.item()) > 0        # (the device-side exchange does not count rows on the host)
         ok &= bool(sw.any())
+        for k in ("rmse_train", "rmse_test"):
+            ok &= bool(np.allclose([pooled[k][q] for q in ("mean", "std", "min", "max")],
+                                   [sm1[k][q] for q in ("mean", "std", "min", "max")], rtol=1e-9, atol=1e-12))
+        ok &= bool(np.allclose(pooled["w_mean"], sm1["w_mean"], rtol=1e-9, atol=1e-12))
+        ok &= bool(np.allclose(pooled["w_std"], sm1["w_std"], rtol=1e-7, atol=1e-10)) and pooled["n"] == sm1["n"]
         print("DIST_GPU_RESULT mode=%s exchange=%s ok=%s world=%d swaps=%d/%d rows_moved=%d" % (mode, "peer" if peer else "host", ok, world, ns, tot, int(moved.item())))
     smp.close()
     dist.destroy_process_group()

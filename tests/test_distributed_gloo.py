@@ -8,7 +8,7 @@ import sys
 
 import pytest
 
-from ptnn_b200.distributed import partition
+from ptnn_b200.distributed import combine_summaries, partition
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -34,3 +34,27 @@ def test_partition_is_contiguous_and_even():
     assert [partition(1024, 8, r) for r in (0, 3, 7)] == [(0, 128), (384, 128), (896, 128)]
     with pytest.raises(ValueError):
         partition(10, 4, 0)
+
+
+def test_per_rank_summaries_pool_to_the_whole_ladder():
+    """combine_summaries (what PartitionedLadder.summary applies to the all-gathered per-rank results)
+    == the reference's statistics over all chains at once (R:1036-1044)."""
+    import numpy as np
+    rs = np.random.RandomState(2)
+    blocks = [rs.rand(n, 7) * (k + 1) + k for k, n in enumerate((40, 25, 1))]       # unequal blocks, one of a single row
+    names = ("rmse_train", "rmse_test", "acc_train", "acc_test")
+
+    def summarise(x):
+        d = {"n": len(x), "w_mean": x[:, 4:].mean(axis=0), "w_std": x[:, 4:].std(axis=0)}
+        for j, k in enumerate(names):
+            d[k] = {"mean": x[:, j].mean(), "std": x[:, j].std(), "min": x[:, j].min(), "max": x[:, j].max()}
+        return d
+
+    got, want = combine_summaries([summarise(b) for b in blocks] + [None]), summarise(np.vstack(blocks))
+    assert got["n"] == want["n"] == 66
+    for k in names:
+        assert np.allclose([got[k][q] for q in ("mean", "std", "min", "max")], [want[k][q] for q in ("mean", "std", "min", "max")], rtol=1e-12)
+    assert np.allclose(got["w_mean"], want["w_mean"], rtol=1e-12) and np.allclose(got["w_std"], want["w_std"], rtol=1e-12)
+    parts = [summarise(b) for b in blocks]
+    parts[1]["w_mean"] = parts[1]["w_std"] = None
+    assert combine_summaries(parts)["w_mean"] is None
