@@ -1,0 +1,125 @@
+"""GPU, BASELINE.json's full sizes (configs[3]: synthetic series, 4-64-1, 1024 temperatures, 29 998
+training rows; configs[4]: PenDigit-shaped, 16-256-10, 256 temperatures, 20 000 rows).
+
+The float64 oracle cannot run a 1024-temperature ladder in test time, so parity at these sizes is:
+
+  * sampled temperatures against the oracle: without a swap round inside the span a replica depends
+    only on its own temperature, start vector and draws, so the device run of the WHOLE ladder is
+    compared with the oracle run of a few of its temperatures (first, last, two in between) on the
+    full data set -- Langevin and random-walk steps alternating;
+  * size-independent properties of the whole ladder through swap rounds: one launch == the same steps
+    split over several launches, memoised langevin_gradient == recomputed, both bit for bit; swap
+    rounds only permute vectors (every carried trace row is some replica's earlier state or proposal);
+    the device-side summary == NumPy on the fetched traces.
+"""
+import numpy as np
+import pytest
+
+from oracle import ptfnn_c as oc
+from oracle import ptfnn_numpy as on
+from ptnn_b200 import datasets
+from ptnn_b200.sampler import Sampler, geometric_ladder
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+# fp32 online SGD over 20-30 thousand serial rows against the float64 oracle: measured worst relative error
+# 2.3e-5 (4-64-1, 29 998 rows) and 9.4e-5 (16-256-10, 20 000 rows) on log-likelihoods, weights and diff_prop / P
+RTOL_FULL = 3e-4
+
+_data = {}
+
+
+def _workload(name):
+    if name not in _data:
+        _data[name] = datasets.synthetic_timeseries() if name == "synth_ts" else datasets.synthetic_pendigit()
+    return _data[name]
+
+
+def _sampled_vs_oracle(name, task, topo, R, lr, pick, pattern):
+    tr, te = _workload(name)
+    S = len(pattern) + 1
+    cfg = on.PTConfig(task=task, topology=topo, samples=S, swap_interval=10 * S, use_langevin_gradients=True,
+                      l_prob=0.5, learn_rate=lr)
+    assert cfg.total_rounds() == 0
+    temps = geometric_ladder(R, 2)
+    draws = on.random_draws(cfg, R, 17, common_random_numbers=False)
+    draws.lx[:] = np.asarray(pattern)[None, :]                      # < 0.5: Langevin step, else random walk
+    draws.u[:] = draws.u * 0.5                                      # accept often, so later steps start from moved states
+    w0 = np.random.RandomState(8).randn(R, cfg.P) * (0.5 if topo[1] <= 64 else 0.2)
+    with Sampler.from_oracle_config(cfg, temps, debug_traces=True) as s:
+        s.set_data(tr, te)
+        s.init_chains(w0)
+        assert s.replay(draws) == S - 1
+        t = s.traces()
+    sub = on.Draws(lx=draws.lx[pick], z=draws.z[pick], z_eta=draws.z_eta[pick], u=draws.u[pick], u_swap=draws.u_swap[:, :len(pick) - 1])
+    ref = oc.run_pt(cfg, tr, te, temps[pick], w0[pick], sub)
+    worst = 0.0
+    for k, r in enumerate(pick):
+        acc, racc = t["accepted"][r], ref.accepted[k]
+        diff = np.flatnonzero(acc != racc)
+        i_star = int(diff[0]) - 1 if diff.size else S - 1          # steps < i_star replayed identically
+        if diff.size:                                               # only a documented near-tie may differ
+            c = int(diff[0])
+            lo, hi = sorted([t["mh_prob"][r, c], ref.mh_prob[k, c]])
+            assert lo - 1e-6 <= draws.u[r, c - 1] <= hi + 1e-6, (name, r, c, lo, hi, draws.u[r, c - 1])
+        rows = slice(1, i_star + 2)
+        e1 = cm.relerr(t["lik_prop"][r, rows], ref.lik_prop[k, rows])
+        e2 = cm.relerr(t["pos_w"][r, :i_star + 1], ref.pos_w[k, :i_star + 1])
+        e3 = float(np.max(np.abs(t["diff_prop"][r, rows] - ref.diff_prop[k, rows]))) / cfg.P
+        worst = max(worst, e1, e2, e3)
+        assert max(e1, e2, e3) < RTOL_FULL, (name, r, e1, e2, e3)
+        assert i_star >= (S - 1) // 2, (name, r, i_star)
+    assert t["accepted"].sum() > 0
+    return worst
+
+
+def test_synthetic_series_full_size_sampled_temperatures_match_oracle():
+    worst = _sampled_vs_oracle("synth_ts", on.REGRESSION, (4, 64, 1), 1024, 0.01, [0, 341, 682, 1023], [0.1, 0.9, 0.2, 0.8, 0.3])
+    print("worst relative error vs the float64 oracle: %.2e" % worst)
+
+
+def test_pendigit_full_size_sampled_temperatures_match_oracle():
+    worst = _sampled_vs_oracle("pendigit", on.CLASSIFICATION, (16, 256, 10), 256, 0.01, [0, 100, 255], [0.1, 0.9, 0.2])
+    print("worst relative error vs the float64 oracle: %.2e" % worst)
+
+
+def _run(name, task, topo, R, S, si, launches, memo, lr=0.01):
+    tr, te = _workload(name)
+    w0 = np.random.RandomState(5).randn(R, on.num_params(topo)) * 0.3
+    with Sampler(task, topo, geometric_ladder(R, 2), S, si, use_langevin_gradients=True, l_prob=0.5, learn_rate=lr,
+                 seed=31, common_random_numbers=False, memoize_gradient=memo, debug_traces=True) as s:
+        s.set_data(tr, te)
+        s.init_chains(w0)
+        for n in launches:
+            s.run(n)
+        assert s.step == S - 1
+        t = s.traces()
+        sm = s.trace_summary(1, S - 1)
+        return t, s.swap_stats(), s.get_state(), sm, w0
+
+
+def test_synthetic_series_full_size_ladder_properties():
+    R, S, si = 1024, 10, 3
+    base = _run("synth_ts", on.REGRESSION, (4, 64, 1), R, S, si, [S - 1], 0)
+    t, sw, st, sm, w0 = base
+    rounds = on.PTConfig(task=on.REGRESSION, topology=(4, 64, 1), samples=S, swap_interval=si).total_rounds()
+    assert rounds == 3 and sw[1] == rounds * (R - 1) and sw[0] > 0   # every pair of the ladder proposed in every round
+    for other in (_run("synth_ts", on.REGRESSION, (4, 64, 1), R, S, si, [2, 4, 3], 0),     # split over launches
+                  _run("synth_ts", on.REGRESSION, (4, 64, 1), R, S, si, [S - 1], 1)):      # memoised gradient
+        for k in t:
+            assert np.array_equal(other[0][k], t[k]), k
+        assert other[1][0] == sw[0] and np.array_equal(other[1][2], sw[2])
+        for k in ("w", "eta", "lik", "prior"):
+            assert np.array_equal(other[2][k], st[k]), k
+    # a swap round only moves vectors between temperatures: every final w is the start vector, an accepted
+    # proposal (a recorded trace row) of SOME temperature, bit for bit
+    rows = t["pos_w"].reshape(-1, t["pos_w"].shape[2]).astype(np.float32)
+    pool = {r.tobytes() for r in rows} | {r.astype(np.float32).tobytes() for r in w0}
+    assert all(w.astype(np.float32).tobytes() in pool for w in st["w"])
+    # device-side summary == NumPy on the fetched traces
+    for k in ("rmse_train", "rmse_test"):
+        x = t[k][:, 1:]
+        assert np.allclose([sm[k][q] for q in ("mean", "std", "min", "max")], [x.mean(), x.std(), x.min(), x.max()], rtol=1e-9)
+    pw = t["pos_w"][:, 1:].reshape(-1, rows.shape[1])
+    assert np.allclose(sm["w_mean"], pw.mean(axis=0), rtol=1e-9, atol=1e-12)
+    assert np.allclose(sm["w_std"], pw.std(axis=0), rtol=1e-7, atol=1e-10)
