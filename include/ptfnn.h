@@ -187,6 +187,14 @@ typedef struct ptfnn_summary {
 } ptfnn_summary;
 int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t count, ptfnn_summary *out);
 
+/* Host side of the same pipeline: byte-compatible replacements of the np.savetxt / np.loadtxt calls
+ * the reference spends its result phase in (R:454-481, R:794-831).  No device involved; thread-safe
+ * (one file per call).  fmt: one printf conversion, as np.savetxt's fmt ('%.18e', '%1.8f', ...).
+ * ptfnn_loadtxt: out == NULL reports the shape only; otherwise capacity >= rows*cols (file size / 2 always is). */
+int ptfnn_savetxt(const char *path, const double *data, int64_t rows, int64_t cols, int64_t row_stride,
+                  const char *fmt);
+int ptfnn_loadtxt(const char *path, double *out, int64_t capacity, int64_t *rows, int64_t *cols);
+
 /* ---- multi-GPU round (ladder partitioned over ranks).  Device pointers are owned by
  * the caller (torch tensors), so that NCCL can move them:
  *   lhood_local  [n_replicas]        float64  swap field of each local replica (R:430 / C:439)

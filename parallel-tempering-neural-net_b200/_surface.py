@@ -191,21 +191,33 @@ def _num_param(topology):
 
 
 def _write_chain_files(path, temperature, task, samples, t, k, num_accepted):
-    """Per-chain output files, names and formats of R:454-481 / C:465-492."""
+    """Per-chain output files, names and formats of R:454-481 / C:465-492.  capi.savetxt writes the bytes
+    np.savetxt would (these calls dominate run_chains() once sampling is fast)."""
     T = str(temperature)
-    np.savetxt(path + '/posterior/pos_w/' + 'chain_' + T + '.txt', t["pos_w"][k])
+    savetxt = capi.savetxt
+    savetxt(path + '/posterior/pos_w/' + 'chain_' + T + '.txt', t["pos_w"][k])
     fmt = '%1.8f' if task == REGRESSION else '%1.2f'                              # R:462-464 | C:473-475
-    np.savetxt(path + '/predictions/rmse_test_chain_' + T + '.txt', t["rmse_test"][k], fmt=fmt)
-    np.savetxt(path + '/predictions/rmse_train_chain_' + T + '.txt', t["rmse_train"][k], fmt=fmt)
-    np.savetxt(path + '/predictions/acc_test_chain_' + T + '.txt', t["acc_test"][k], fmt='%1.2f')
-    np.savetxt(path + '/predictions/acc_train_chain_' + T + '.txt', t["acc_train"][k], fmt='%1.2f')
+    savetxt(path + '/predictions/rmse_test_chain_' + T + '.txt', t["rmse_test"][k], fmt=fmt)
+    savetxt(path + '/predictions/rmse_train_chain_' + T + '.txt', t["rmse_train"][k], fmt=fmt)
+    savetxt(path + '/predictions/acc_test_chain_' + T + '.txt', t["acc_test"][k], fmt='%1.2f')
+    savetxt(path + '/predictions/acc_train_chain_' + T + '.txt', t["acc_train"][k], fmt='%1.2f')
     likeh = np.zeros((samples, 2))
     likeh[:, 0] = t["lik_prop"][k]
     likeh[0, :] = [-100, -100]                                                    # R:293
-    np.savetxt(path + '/posterior/pos_likelihood/chain_' + T + '.txt', likeh, fmt='%1.4f')
+    savetxt(path + '/posterior/pos_likelihood/chain_' + T + '.txt', likeh, fmt='%1.4f')
     accept_ratio = num_accepted / (samples * 1.0) * 100                           # R:447
-    np.savetxt(path + '/posterior/accept_list/chain_' + T + '_accept.txt', [accept_ratio], fmt='%1.4f')
-    np.savetxt(path + '/posterior/accept_list/chain_' + T + '.txt', t["accept_list"][k], fmt='%1.4f')
+    savetxt(path + '/posterior/accept_list/chain_' + T + '_accept.txt', [accept_ratio], fmt='%1.4f')
+    savetxt(path + '/posterior/accept_list/chain_' + T + '.txt', t["accept_list"][k], fmt='%1.4f')
+
+
+def _per_chain(fn, n):
+    """fn(k) for every chain, one thread each (the text conversion runs in the library, outside the GIL;
+    the reference gets the same parallelism from its one-process-per-replica layout)."""
+    if n <= 1:
+        return [fn(k) for k in range(n)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(n, os.cpu_count() or 4, 32)) as ex:
+        return list(ex.map(fn, range(n)))
 
 
 # ==========================================================================================
@@ -410,8 +422,8 @@ class ParallelTemperingBase:
         t, st = self._run_sampler(True)
         self._traces, self._state = t, st
         if self.write_files:
-            for k in range(self.num_chains):
-                _write_chain_files(self.path, self.temperatures[k], self.TASK, S, t, k, int(st["num_accepted"][k]))
+            _per_chain(lambda k: _write_chain_files(self.path, self.temperatures[k], self.TASK, S, t, k,
+                                                    int(st["num_accepted"][k])), self.num_chains)
         pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, likelihood_vec, accept_vec, accept = \
             self.show_results()
         print("NUMBER OF SWAPS =", self.num_swap)
@@ -453,24 +465,28 @@ class ParallelTemperingBase:
         acc_test = np.zeros((R, S - burnin))
         from_files = self.results_from_files and self.write_files
         t = self._traces
-        for i in range(R):
+        if not from_files and t is None:
+            raise RuntimeError("run_chains() has not produced traces yet")
+
+        def fill(i):
             T = str(self.temperatures[i])
-            if from_files:
-                pos_w[i, :, :] = np.loadtxt(self.path + '/posterior/pos_w/' + 'chain_' + T + '.txt')[burnin:, :]
-                likelihood_rep[i, :] = np.loadtxt(self.path + '/posterior/pos_likelihood/' + 'chain_' + T + '.txt')[self._lik_rows(burnin)]
-                accept_list[i, :] = np.loadtxt(self.path + '/posterior/accept_list/' + 'chain_' + T + '.txt')
-                rmse_test[i, :] = np.loadtxt(self.path + '/predictions/rmse_test_chain_' + T + '.txt')[burnin:]
-                rmse_train[i, :] = np.loadtxt(self.path + '/predictions/rmse_train_chain_' + T + '.txt')[burnin:]
-                acc_test[i, :] = np.loadtxt(self.path + '/predictions/acc_test_chain_' + T + '.txt')[burnin:]
-                acc_train[i, :] = np.loadtxt(self.path + '/predictions/acc_train_chain_' + T + '.txt')[burnin:]
+            if from_files:                                                        # R:794-831, read back as written
+                loadtxt = capi.loadtxt
+                pos_w[i, :, :] = loadtxt(self.path + '/posterior/pos_w/' + 'chain_' + T + '.txt')[burnin:, :]
+                likelihood_rep[i, :] = loadtxt(self.path + '/posterior/pos_likelihood/' + 'chain_' + T + '.txt')[self._lik_rows(burnin)]
+                accept_list[i, :] = loadtxt(self.path + '/posterior/accept_list/' + 'chain_' + T + '.txt')
+                rmse_test[i, :] = loadtxt(self.path + '/predictions/rmse_test_chain_' + T + '.txt')[burnin:]
+                rmse_train[i, :] = loadtxt(self.path + '/predictions/rmse_train_chain_' + T + '.txt')[burnin:]
+                acc_test[i, :] = loadtxt(self.path + '/predictions/acc_test_chain_' + T + '.txt')[burnin:]
+                acc_train[i, :] = loadtxt(self.path + '/predictions/acc_train_chain_' + T + '.txt')[burnin:]
             else:
-                if t is None:
-                    raise RuntimeError("run_chains() has not produced traces yet")
                 pos_w[i] = t["pos_w"][i, burnin:]
                 likelihood_rep[i, :, 0] = t["lik_prop"][i, self._lik_rows(burnin)]
                 accept_list[i] = t["accept_list"][i]
                 rmse_test[i], rmse_train[i] = t["rmse_test"][i, burnin:], t["rmse_train"][i, burnin:]
                 acc_test[i], acc_train[i] = t["acc_test"][i, burnin:], t["acc_train"][i, burnin:]
+
+        _per_chain(fill, R)
         if self.posterior_predictive:
             for i in range(R):
                 fx_train_all[i] = capi.op_posterior_predictive(self.TASK, self.topology, self.traindata, pos_w[i], self.device)[0]
@@ -483,9 +499,9 @@ class ParallelTemperingBase:
         acc_test = acc_test.reshape(R * (S - burnin), 1)
         accept_vec = accept_list
         accept = np.sum(accept_percent) / R                                       # always 0: never filled (R:780, R:860)
-        np.savetxt(self.path + '/likelihood.txt', likelihood_vec.T, fmt='%1.5f')
-        np.savetxt(self.path + '/accept_list.txt', accept_list, fmt='%1.2f')
-        np.savetxt(self.path + '/acceptpercent.txt', [accept], fmt='%1.2f')
+        capi.savetxt(self.path + '/likelihood.txt', likelihood_vec.T, fmt='%1.5f')
+        capi.savetxt(self.path + '/accept_list.txt', accept_list, fmt='%1.2f')
+        capi.savetxt(self.path + '/acceptpercent.txt', [accept], fmt='%1.2f')
         return (posterior, fx_train_all, fx_test_all, rmse_train, rmse_test, acc_train, acc_test, likelihood_vec.T,
                 accept_vec, accept)
 

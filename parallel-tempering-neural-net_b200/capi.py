@@ -29,7 +29,7 @@ SYMBOLS = [
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
-    "ptfnn_op_swap_sweep", "ptfnn_op_posterior_predictive",
+    "ptfnn_op_swap_sweep", "ptfnn_op_posterior_predictive", "ptfnn_savetxt", "ptfnn_loadtxt",
 ]
 
 
@@ -264,3 +264,39 @@ def op_swap_sweep(lhood, u_row, device=0):
     sw = np.zeros(max(n - 1, 1), dtype=np.uint8)
     check(load().ptfnn_op_swap_sweep(device, n, ptr(lhood), ptr(u_row), ptr(src), ptr(sw)))
     return src, sw[:n - 1].astype(bool)
+
+
+# ---- host side of the result pipeline (no device) ------------------------------------------------
+def savetxt(path, X, fmt='%.18e'):
+    """np.savetxt(path, X, fmt=fmt) for float arrays of 1 or 2 dimensions, byte for byte (R:454-481)."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 0:
+        X = X.reshape(1, 1)
+    elif X.ndim == 1:
+        X = X.reshape(-1, 1)
+    elif X.ndim != 2:
+        raise ValueError("Expected 1D or 2D array, got %dD array instead" % X.ndim)
+    X = np.ascontiguousarray(X)
+    rc = load().ptfnn_savetxt(os.fsencode(path), ptr(X), C.c_int64(X.shape[0]), C.c_int64(X.shape[1]),
+                              C.c_int64(X.shape[1]), fmt.encode())
+    if rc != OK:
+        raise OSError("ptfnn_savetxt(%r, fmt=%r) failed (%d)" % (path, fmt, rc))
+
+
+def loadtxt(path):
+    """np.loadtxt(path) for the files savetxt writes (R:794-831): (rows, cols) -> 2-D, one column -> 1-D."""
+    rows, cols = C.c_int64(), C.c_int64()
+    try:
+        cap = os.path.getsize(path) // 2 + 1            # a value takes at least a digit and a separator
+    except OSError as e:
+        raise OSError("ptfnn_loadtxt(%r): %s" % (path, e)) from None
+    flat = np.empty(cap)                                # (untouched pages cost nothing)
+    rc = load().ptfnn_loadtxt(os.fsencode(path), ptr(flat), C.c_int64(cap), C.byref(rows), C.byref(cols))
+    if rc != OK:
+        raise OSError("ptfnn_loadtxt(%r) failed (%d)" % (path, rc))
+    if rows.value == 0:
+        return np.empty(0)
+    out = flat[:rows.value * cols.value].reshape(rows.value, cols.value).copy()
+    if out.shape[1] == 1:
+        return out.reshape(()) if out.shape[0] == 1 else out[:, 0]
+    return out[0] if out.shape[0] == 1 else out
