@@ -262,6 +262,14 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     if (cfg->task == PTFNN_TASK_REGRESSION && cfg->n_out != 1)
         return fail(nullptr, PTFNN_E_UNSUPPORTED, "regression needs one output (the reference stores fx[i] = out, R:132)");
     if (cfg->n_replicas < 1 || cfg->samples < 2 || cfg->swap_interval < 1) return fail(nullptr, PTFNN_E_INVALID, "need n_replicas >= 1, samples >= 2, swap_interval >= 1");
+    if (cfg->swap_rule != PTFNN_SWAP_RULE_AUTO && cfg->swap_rule != PTFNN_SWAP_RULE_AFTER_I && cfg->swap_rule != PTFNN_SWAP_RULE_BEFORE_I1)
+        return fail(nullptr, PTFNN_E_INVALID, "bad swap_rule %d", cfg->swap_rule);
+    if (!(cfg->l_prob >= 0.0 && cfg->l_prob <= 1.0) || !std::isfinite(cfg->learn_rate) || !(cfg->step_w >= 0.0) || !(cfg->step_eta >= 0.0) ||
+        !(cfg->sigma_squared > 0.0) || !std::isfinite(cfg->nu_1) || !std::isfinite(cfg->nu_2) || !(cfg->pt_fraction >= 0.0))
+        return fail(nullptr, PTFNN_E_INVALID, "need 0 <= l_prob <= 1, finite learn_rate / nu, step_w >= 0, step_eta >= 0, sigma_squared > 0, pt_fraction >= 0");
+    for (int k = 0; k < cfg->n_replicas; ++k)
+        if (!(temperatures[k] > 0.0) || !std::isfinite(temperatures[k]))
+            return fail(nullptr, PTFNN_E_INVALID, "temperature %d = %g: the likelihood is divided by it (R:204), need a finite value > 0", k, temperatures[k]);
     const int Rg = cfg->n_replicas_global > 0 ? cfg->n_replicas_global : cfg->n_replicas;
     if (cfg->replica_offset < 0 || cfg->replica_offset + cfg->n_replicas > Rg) return fail(nullptr, PTFNN_E_INVALID, "replica_offset/n_replicas outside the ladder of %d", Rg);
     const KernelSet *ks = find_kernels(cfg->task, cfg->n_in, cfg->n_hidden, cfg->n_out);
@@ -283,6 +291,10 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     s->num_sms = prop.multiProcessorCount;
     s->regs_per_sm = prop.regsPerMultiprocessor; s->threads_per_sm = prop.maxThreadsPerMultiProcessor;
     s->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    if (prop.major != 10) {                                                   // the kernels are sm_100a code only
+        rc = fail(nullptr, PTFNN_E_UNSUPPORTED, "device %d (%s) is sm_%d%d: libptfnn is built for sm_100a (B200) only", cfg->device, prop.name, prop.major, prop.minor);
+        delete s; return rc;
+    }
     if (!prop.cooperativeLaunch) { rc = fail(nullptr, PTFNN_E_CUDA, "device lacks cooperative launch"); delete s; return rc; }
 
     const size_t R = cfg->n_replicas, S = cfg->samples, P = s->P;
@@ -343,11 +355,28 @@ static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP
     }
 }
 
+// Classification labels index the class probabilities (C:217 prob[i, int(y)]; C:73-75 one-hot target): the
+// reference raises IndexError for a label >= n_out and NumPy silently wraps a negative one; the device
+// would read past the outputs, so both are refused here.  -1: all labels are fine.
+static int first_bad_label(const double *data, int rows, int n_cols, int I, int O) {
+    for (int r = 0; r < rows; ++r) {
+        const double y = data[(size_t)r * n_cols + I];
+        if (!(y > -1.0 && y < (double)O)) return r;              // int(y) truncates towards zero, like the reference
+    }
+    return -1;
+}
+
 extern "C" int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_train, const double *test,
                               int32_t n_test, int32_t n_cols) {
     if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
     if (!train || !test || n_train < 1 || n_test < 1) return fail(s, PTFNN_E_INVALID, "empty dataset");
     if (n_cols < s->cfg.n_in + 1) return fail(s, PTFNN_E_INVALID, "n_cols %d < n_in + 1", n_cols);
+    if (s->cfg.task == PTFNN_TASK_CLASSIFICATION) {
+        int bad = first_bad_label(train, n_train, n_cols, s->cfg.n_in, s->cfg.n_out);
+        if (bad >= 0) return fail(s, PTFNN_E_INVALID, "train row %d: label %g outside [0, %d)", bad, train[(size_t)bad * n_cols + s->cfg.n_in], s->cfg.n_out);
+        bad = first_bad_label(test, n_test, n_cols, s->cfg.n_in, s->cfg.n_out);
+        if (bad >= 0) return fail(s, PTFNN_E_INVALID, "test row %d: label %g outside [0, %d)", bad, test[(size_t)bad * n_cols + s->cfg.n_in], s->cfg.n_out);
+    }
     CU_TRY(s, cudaSetDevice(s->cfg.device));
     std::vector<float> x, y;
     pack_dataset(train, n_train, n_cols, s->cfg.n_in, s->IP, x, y);
@@ -1001,7 +1030,7 @@ struct OpData {
 };
 
 static int op_prepare(int device, int task, int I, int H, int O, const double *data, int rows, int n_cols,
-                      const double *w, const KernelSet **ks, OpData &od, int batch = 1) {
+                      const double *w, const KernelSet **ks, OpData &od, int batch = 1, bool labels_used = true) {
     int rc = require_device(nullptr, device);
     if (rc) return rc;
     *ks = find_kernels(task, I, H, O);
@@ -1010,8 +1039,12 @@ static int op_prepare(int device, int task, int I, int H, int O, const double *d
     const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
     if (data) {
         if (rows < 1 || n_cols < I + 1) return fail(nullptr, PTFNN_E_INVALID, "bad data shape [%d,%d]", rows, n_cols);
+        const int bad = task == PTFNN_TASK_CLASSIFICATION ? first_bad_label(data, rows, n_cols, I, O) : -1;
+        if (bad >= 0 && labels_used) return fail(nullptr, PTFNN_E_INVALID, "row %d: label %g outside [0, %d)", bad, data[(size_t)bad * n_cols + I], O);
         std::vector<float> x, y;
         pack_dataset(data, rows, n_cols, I, IP, x, y);
+        if (bad >= 0)                                            // evaluate_proposal never looks at the labels (C:134-153): any valid class keeps the kernel in bounds
+            for (int r = 0; r < rows; ++r) y[r] = std::min(std::max(y[r], 0.0f), (float)(O - 1));
         CU_TRY(nullptr, od.x.ensure(x.size())); CU_TRY(nullptr, od.y.ensure(y.size()));
         CU_TRY(nullptr, cudaMemcpy(od.x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
         CU_TRY(nullptr, cudaMemcpy(od.y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice));
@@ -1040,7 +1073,7 @@ static int op_forward(int device, int task, int I, int H, int O, const double *d
                       const double *w, double *fx, double *prob, double *sums /* [batch][3] */, int batch = 1) {
     const KernelSet *ks;
     OpData od;
-    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od, batch);
+    int rc = op_prepare(device, task, I, H, O, data, rows, n_cols, w, &ks, od, batch, /*labels_used=*/sums != nullptr);
     if (rc) { od.release(); return rc; }
     const int P = I * H + H * O + H + O, IP = (I + 3) & ~3;
     DevBuf<float> d_fx, d_prob;

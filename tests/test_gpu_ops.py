@@ -195,3 +195,33 @@ def test_posterior_predictive_batch_matches_oracle():
         clear = (top2[:, 1] - top2[:, 0]) > 1e-5
         assert np.array_equal(fx[k][clear], ref_fx[clear])
         assert sums[k, 0] == pytest.approx(np.sum(np.log(ref_prob[np.arange(200), data[:, 16].astype(int)])), rel=RTOL)
+
+
+def test_class_labels_outside_the_outputs_are_refused_where_they_are_used():
+    """C:217 indexes prob[i, int(y)] and C:73-75 builds the one-hot target from the label: the reference raises
+    IndexError for a label >= n_out (and NumPy wraps a negative one).  The device refuses both instead of reading
+    out of bounds; evaluate_proposal never looks at the labels (C:134-153) and keeps working."""
+    from ptnn_b200.sampler import Sampler
+    rs = np.random.RandomState(9)
+    topo = (4, 12, 3)
+    good = np.hstack([rs.randn(20, 4), rs.randint(0, 3, size=(20, 1)).astype(float)])
+    w = rs.randn(on.num_params(topo)) * 0.3
+    for label in (3.0, -1.0, float("nan")):
+        bad = good.copy()
+        bad[7, 4] = label
+        for call in (lambda: capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, bad, w, 1.0, 1.0),
+                     lambda: capi.op_langevin_gradient(capi.TASK_CLASSIFICATION, topo, bad, w, 0.01)):
+            with pytest.raises(capi.PtfnnError) as e:
+                call()
+            assert e.value.code == capi.E_INVALID and "row 7" in str(e.value)
+        fx, prob = capi.op_evaluate_proposal(capi.TASK_CLASSIFICATION, topo, bad, w)
+        fx_ref, prob_ref = oc.evaluate(on.CLASSIFICATION, topo, good, w)
+        assert np.array_equal(fx, fx_ref) and cm.relerr(prob, prob_ref) < RTOL
+        with Sampler(capi.TASK_CLASSIFICATION, topo, [1.0, 2.0], 10, 5) as s:
+            with pytest.raises(capi.PtfnnError) as e:
+                s.set_data(good, bad)
+            assert e.value.code == capi.E_INVALID and "test row 7" in str(e.value)
+    frac = good.copy()
+    frac[:, 4] += 0.5                                            # int(y) truncates (C:74, C:217)
+    assert np.allclose(capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, frac, w, 1.0, 1.0)[0],
+                       capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, good, w, 1.0, 1.0)[0])
