@@ -181,7 +181,7 @@ def run_reference_arm(args, w):
         sample = "%d replica processes x %d steps per bench step (LG/RW alternating = l_prob 0.5), swap rounds included" % (n_procs, len(pattern))
     line = {"impl": "reference", "metric": "replica_mcmc_steps_per_sec", "value": value, "unit": "replica-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic" if w["name"] != "sunspot" else "Sunspot (reference dataset), random-init weights",
             "config": {"workload": w["desc"], "sampler": "Langevin PT, l_prob %.2f, lr %g, swap_interval %d, maxtemp %s" % (w["l_prob"], w["learn_rate"], w["swap_interval"], w["maxtemp"])},
             "cpu_baseline": {"value": value, "unit": "replica-steps/s", "cores": cores, "kind": "port", "sample": sample},
@@ -391,7 +391,7 @@ def run_b200_arm(args, w, rank, world, local_rank):
                "sample": "%d replica processes x %d steps (LG/RW alternating = l_prob 0.5) of the same workload, %.1f s wall" % (n_procs, len(pattern), wall)}
 
     line = {"metric": "replica_mcmc_steps_per_sec", "value": value, "unit": "replica-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if w["name"] != "sunspot" else "Sunspot (reference dataset), random-init weights",
             "config": {"workload": w["desc"], "sampler": "Langevin PT, l_prob %.2f, lr %g, swap_interval %d, maxtemp %s" % (w["l_prob"], w["learn_rate"], si, w["maxtemp"]),
                        "replicas_total": Rg, "replica_steps_per_bench_step": units_per_step,
@@ -418,6 +418,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="synth_ts", choices=["synth_ts", "sunspot", "pendigit"])
     ap.add_argument("--replicas-per-gpu", type=int, default=None)
+    ap.add_argument("--ladder-total", type=int, default=None,
+                    help="strong scaling: a fixed ladder of this many temperatures split over the GPUs "
+                         "(BASELINE configs[3] as worded: 1024 over 1/2/4/8); default is weak scaling, 1024 per GPU")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -427,7 +430,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    w = load_workload(args.workload, max(world, 1) if args.impl == "b200" else args.gpus, args.replicas_per_gpu)
+    n_dev = max(world, 1) if args.impl == "b200" else args.gpus
+    args.scaling = "weak"
+    if args.ladder_total:
+        if args.ladder_total % n_dev:
+            raise SystemExit("--ladder-total %d does not split evenly over %d GPUs" % (args.ladder_total, n_dev))
+        args.replicas_per_gpu, args.scaling = args.ladder_total // n_dev, "strong"
+    w = load_workload(args.workload, n_dev, args.replicas_per_gpu)
     if args.impl == "reference":
         if rank == 0:
             run_reference_arm(args, w)
