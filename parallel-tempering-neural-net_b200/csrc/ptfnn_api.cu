@@ -839,14 +839,15 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
     const bool moments = out->w_mean != nullptr;
     const int cols = !moments || P <= kSumThreads ? 1 : P <= 2 * kSumThreads ? 2 : P <= 4 * kSumThreads ? 4 : 8;
     const int ctiles = moments ? (P + kSumThreads * cols - 1) / (kSumThreads * cols) : 0;
-    int gx = std::max(1, std::min(R, s->num_sms));
-    if (moments) {                                                           // persistent: two blocks per SM over all planes
+    int mblocks = std::max(1, std::min(R, 2 * s->num_sms));                   // series only: one or two short blocks per SM
+    if (moments) {                                                           // persistent: two blocks per SM over all column tiles
         const int rpc = sum_rows_per_chunk(P, cols, ctiles == 1);
         const long long items = (long long)R * ((count + rpc - 1) / rpc);
-        gx = (int)std::max<long long>(1, std::min<long long>(items, std::max(1, 2 * s->num_sms / ctiles)));
+        mblocks = (int)std::max<long long>(1, std::min<long long>(items, std::max(1, 2 * s->num_sms / ctiles)));
     }
-    // layout of d_summary: stats[16] | acc[2P] | mean[P] | std[P] | part[4*gx*4] | ticket
-    const size_t need = 16 + 4 * (size_t)P + 16 * (size_t)gx + 1;
+    const int nblocks = moments ? ctiles * mblocks : mblocks;
+    // layout of d_summary: stats[16] | acc[2P] | mean[P] | std[P] | part[nblocks*16] | ticket
+    const size_t need = 16 + 4 * (size_t)P + 16 * (size_t)nblocks + 1;
     if (need > s->d_summary.n) {
         CU_TRY(s, s->d_summary.ensure(need));
         CU_TRY(s, cudaMemsetAsync(s->d_summary.p, 0, need * sizeof(double), s->stream));   // acc and ticket start at zero; the kernel leaves them so
@@ -868,9 +869,10 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
     a.pos_w = s->pos_w.p;
     a.series[0] = s->rmse_tr.p; a.series[1] = s->rmse_te.p; a.series[2] = s->acc_tr.p; a.series[3] = s->acc_te.p;
     a.R = R; a.S = S; a.P = P; a.first = first; a.count = count; a.ctiles = ctiles;
-    a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_part + 16 * (size_t)gx);
+    a.mblocks = mblocks;
+    a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_part + 16 * (size_t)nblocks);
     a.stats = d_stats; a.mean = d_mean; a.stdev = d_std;
-    const dim3 grid(gx, ctiles + 4);
+    const dim3 grid(nblocks);
     const size_t smem = moments ? kSumSmemBytes : 0;
     SUM_TRY(cudaEventRecord(e0, s->stream));
     if (cols == 1) trace_summary_kernel<1><<<grid, kSumThreads, smem, s->stream>>>(a);

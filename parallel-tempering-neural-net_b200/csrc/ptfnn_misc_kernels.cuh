@@ -82,9 +82,15 @@ __global__ void op_forward_row_kernel(int I, int H, int O, const float *x, const
 // that reduction where the traces already are, in ONE launch, so a summary costs one read of the trace at
 // HBM speed instead of the device->host copy (and the txt round trip) of R x S x P values.
 //
-// Planes of the grid (blockIdx.y):
-//   [0, ctiles)        posterior moments: for every parameter p, sum and sum of squares of
-//                      (pos_w[r, first+i, p] - pivot[p]) over all local replicas r and rows i < count;
+// Blocks of the (1-D) grid: ctiles planes of mblocks persistent blocks (or one or two short blocks per SM when only
+// the scalar series are wanted).  Every block does two things:
+//   the scalar series  rmse_train, rmse_test, acc_train, acc_test (fp64 [R, S]): the block strides over the
+//                      replicas, reads the four series side by side (four independent loads per thread and
+//                      step) and leaves its partial {sum, sum of squares, min, max} of each.  This is 32 bytes per
+//                      pooled row against 4P for the weights, folded into the streaming blocks so that it
+//                      costs neither extra waves of blocks behind them nor block slots in front of them;
+//   the posterior moments (plane = column tile)  -- for every parameter p, sum and sum of
+//                      squares of (pos_w[r, first+i, p] - pivot[p]) over all local replicas r and rows i < count;
 //                      pivot[p] = pos_w[0, first, p] keeps the second moment free of cancellation (np.std is
 //                      two-pass).  HBM-bound: R*count*P floats read exactly once; fp64 sums.
 //                      Persistent blocks (2 per SM) stream the trace through a 3-stage ring of 32 KB shared-
@@ -97,8 +103,6 @@ __global__ void op_forward_row_kernel(int I, int H, int O, const float *x, const
 //                      columns by 2048 (one plane per tile) and a stage holds four row pieces.  Rows are not
 //                      16-byte aligned (P is odd as a rule): every copy starts at the aligned address below
 //                      its first element and the reader skips the `shift` floats in front.
-//   [ctiles, ctiles+4) the scalar series rmse_train, rmse_test, acc_train, acc_test (fp64 [R, S]): blocks
-//                      stride over the replicas and leave partial {sum, sum of squares, min, max}.
 // The last block to finish (ticket counter) folds everything into {mean, np.std, min, max} per series and
 // mean / np.std per parameter, then clears the accumulators for the next call.
 constexpr int kSumThreads = 256;
@@ -113,8 +117,9 @@ struct TraceSummaryArgs {
     const float *pos_w;        // [R, S, P] (+ kSumTracePadFloats)
     const double *series[4];   // [R, S] each
     int R, S, P, first, count, ctiles;
+    int mblocks;               // blocks per column tile: gridDim.x = ctiles*mblocks (any number when ctiles == 0)
     double *acc;               // [2][P], zero on entry, zero on exit
-    double *part;              // [4][gridDim.x][4]
+    double *part;              // [gridDim.x][4 series][4]
     unsigned int *ticket;      // zero on entry, zero on exit
     double *stats;             // out [4][4]
     double *mean, *stdev;      // out [P] (ctiles > 0)
@@ -142,22 +147,23 @@ __host__ __device__ inline int sum_rows_per_chunk(int P, int cols, bool whole) {
 template <int COLS>
 __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const TraceSummaryArgs a) {
     extern __shared__ __align__(128) unsigned char sum_smem[];
-    __shared__ double s_fold[4][kSumThreads / 32];
+    __shared__ double s_fold[16][kSumThreads / 32];
     __shared__ bool s_last;
     const int P = a.P, count = a.count, tid = threadIdx.x;
-    if ((int)blockIdx.y < a.ctiles) {
+    if (a.ctiles > 0) {
+        const int plane = (int)blockIdx.x / a.mblocks, bx = (int)blockIdx.x - plane * a.mblocks, nbx = a.mblocks;
         constexpr int CW = kSumThreads * COLS, PITCH = CW + kSumPad;
         float *stage = reinterpret_cast<float *>(sum_smem);
         uint64_t *full = reinterpret_cast<uint64_t *>(sum_smem + (size_t)kSumStages * kSumStageFloats * sizeof(float));
         const bool whole = a.ctiles == 1;
-        const int c0 = blockIdx.y * CW, cw = min(P - c0, CW);
+        const int c0 = plane * CW, cw = min(P - c0, CW);
         const int width = min(cw, kSumThreads);
         const int groups = whole ? kSumThreads / width : 1;
         const int g = tid / width, c = tid - g * width;
         const int rpc = sum_rows_per_chunk(P, COLS, whole);
         const int chunks_per_rep = (count + rpc - 1) / rpc;
         const int items = a.R * chunks_per_rep;
-        const int n_mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int n_mine = bx < items ? (items - bx + nbx - 1) / nbx : 0;
         double s1[COLS], s2[COLS], pivot[COLS];
         bool live[COLS];
 #pragma unroll
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
             pivot[k] = live[k] ? (double)__ldg(a.pos_w + (size_t)a.first * P + c0 + c + k * kSumThreads) : 0.0;
         }
         auto locate = [&](int n, int &r, int &i0, int &nrows) {
-            const int t = blockIdx.x + n * gridDim.x;
+            const int t = bx + n * nbx;
             r = t / chunks_per_rep;
             i0 = (t - r * chunks_per_rep) * rpc;
             nrows = min(rpc, count - i0);
@@ -269,35 +275,45 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
                 atomicAdd(a.acc + P + c, y);
             }
         }
-    } else {
-        const int sidx = blockIdx.y - a.ctiles;
-        const double *x = series_of(a, sidx);
-        const double pivot = x[a.first];
-        double s1 = 0.0, s2 = 0.0, lo = pivot, hi = pivot;
+    }
+    {   // ---- the four scalar series, side by side
+        const double *x0 = a.series[0], *x1 = a.series[1], *x2 = a.series[2], *x3 = a.series[3];
+        double pv[4] = {x0[a.first], x1[a.first], x2[a.first], x3[a.first]};
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        double lo[4] = {pv[0], pv[1], pv[2], pv[3]}, hi[4] = {pv[0], pv[1], pv[2], pv[3]};
         for (int r = blockIdx.x; r < a.R; r += gridDim.x) {
-            const double *row = x + (size_t)r * a.S + a.first;
+            const size_t off = (size_t)r * a.S + a.first;
             for (int i = tid; i < count; i += kSumThreads) {
-                const double v = __ldcs(row + i), d = v - pivot;
-                s1 += d; s2 = fma(d, d, s2);
-                lo = fmin(lo, v); hi = fmax(hi, v);
+                const double v[4] = {__ldcs(x0 + off + i), __ldcs(x1 + off + i), __ldcs(x2 + off + i), __ldcs(x3 + off + i)};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double d = v[q] - pv[q];
+                    s1[q] += d; s2[q] = fma(d, d, s2[q]);
+                    lo[q] = fmin(lo[q], v[q]); hi[q] = fmax(hi[q], v[q]);
+                }
             }
         }
-        fold4(s1, s2, lo, hi);
         const int warp = tid >> 5;
-        if ((tid & 31) == 0) { s_fold[0][warp] = s1; s_fold[1][warp] = s2; s_fold[2][warp] = lo; s_fold[3][warp] = hi; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            fold4(s1[q], s2[q], lo[q], hi[q]);
+            if ((tid & 31) == 0) { s_fold[4 * q][warp] = s1[q]; s_fold[4 * q + 1][warp] = s2[q]; s_fold[4 * q + 2][warp] = lo[q]; s_fold[4 * q + 3][warp] = hi[q]; }
+        }
         __syncthreads();
-        if (tid == 0) {
-            for (int k = 1; k < kSumThreads / 32; ++k) {
-                s1 += s_fold[0][k]; s2 += s_fold[1][k]; lo = fmin(lo, s_fold[2][k]); hi = fmax(hi, s_fold[3][k]);
+        if (tid < 4) {
+            const int q = tid;
+            double t1 = 0.0, t2 = 0.0, tl = s_fold[4 * q + 2][0], th = s_fold[4 * q + 3][0];
+            for (int k = 0; k < kSumThreads / 32; ++k) {
+                t1 += s_fold[4 * q][k]; t2 += s_fold[4 * q + 1][k]; tl = fmin(tl, s_fold[4 * q + 2][k]); th = fmax(th, s_fold[4 * q + 3][k]);
             }
-            double *o = a.part + ((size_t)sidx * gridDim.x + blockIdx.x) * 4;
-            o[0] = s1; o[1] = s2; o[2] = lo; o[3] = hi;
+            double *o = a.part + ((size_t)blockIdx.x * 4 + q) * 4;
+            o[0] = t1; o[1] = t2; o[2] = tl; o[3] = th;
         }
     }
     // ---- the last block folds the partial results
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
         const double pivot = series_of(a, sidx)[a.first];
         double s1 = 0.0, s2 = 0.0, lo = pivot, hi = pivot;
         for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const double *o = a.part + ((size_t)sidx * gridDim.x + b) * 4;
+            const double *o = a.part + ((size_t)b * 4 + sidx) * 4;
             s1 += __ldcg(o); s2 += __ldcg(o + 1); lo = fmin(lo, __ldcg(o + 2)); hi = fmax(hi, __ldcg(o + 3));
         }
         fold4(s1, s2, lo, hi);
