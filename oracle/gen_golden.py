@@ -36,6 +36,12 @@ CASES = {
     "cls_iris_lg":     ("classification", "Iris", [4, 12, 3], 4, 10, 80, 8, True, 0.01, 0.5, 17),
     "cls_cancer_lg":   ("classification", "Cancer", [9, 12, 2], 3, 10, 40, 5, True, 0.01, 0.5, 19),
     "cls_ions_lg":     ("classification", "Ionosphere", [34, 50, 2], 2, 10, 25, 6, True, 0.01, 0.5, 23),
+    # the rest of the regression suite (BASELINE configs[1]) and random-walk classification
+    "reg_lorenz_lg":   ("regression", "Lorenz", [4, 5, 1], 5, 2, 60, 6, True, 0.1, 0.5, 29),       # 0.6*S = 36: the switch fires
+    "reg_henon_lg1":   ("regression", "Henon", [4, 5, 1], 3, 4, 45, 9, True, 0.01, 1.0, 31),       # every step Langevin
+    "reg_acfin_rw":    ("regression", "ACFinance", [4, 5, 1], 6, 2, 70, 10, False, 0.1, 0.5, 37),
+    "reg_rossler_lg":  ("regression", "Rossler", [4, 5, 1], 2, 5, 33, 4, True, 0.1, 0.5, 41),      # a round every 4 steps + the left-over one
+    "cls_iris_rw":     ("classification", "Iris", [4, 12, 3], 5, 10, 60, 5, False, 0.01, 0.5, 43),
 }
 
 
