@@ -60,20 +60,42 @@ class ParallelTempering(_s.ParallelTemperingBase):
                          self.wait_chain[i], self.event[i])
 
 
-def load_problem(problem, data_root):
-    """The dataset switch of C:909-1012 for the problems whose files ship with the reference."""
+def _zscore_and_split(features, classes, train_ratio=0.7, complementary_test_split=False):
+    """C:1001-1012 (``separate_flag``): z-score every feature column, then a random split drawn from the
+    global NumPy stream (np.random.seed() before the call makes it repeatable, as in the reference).
+    The training set is the first 70 % of a random permutation.  The reference's TEST set is
+    ``features[indices[k]:, :]`` with k = int(0.7 n) (C:1011-1012: the bracket closes after the index, so the
+    permutation's k-th ENTRY is used as the start of a plain slice): every row from that row number to the end
+    of the file, overlapping the training rows -- reproduced here (DESIGN quirk Q17).
+    ``complementary_test_split=True`` gives the split the line was presumably meant to be (the other 30 %)."""
+    features = np.array(features, dtype=np.float64)
+    for k in range(features.shape[1]):
+        features[:, k] = (features[:, k] - np.mean(features[:, k])) / np.std(features[:, k])
+    indices = np.random.permutation(features.shape[0])                            # C:1010
+    ntr = int(train_ratio * features.shape[0])
+    traindata = np.hstack([features[indices[:ntr], :], classes[indices[:ntr], :]])
+    if complementary_test_split:
+        testdata = np.hstack([features[indices[ntr:], :], classes[indices[ntr:], :]])
+    else:
+        testdata = np.hstack([features[indices[ntr]:, :], classes[indices[ntr]:, :]])
+    return traindata, testdata
+
+
+def load_problem(problem, data_root, complementary_test_split=False):
+    """The dataset switch of C:909-1012 for the problems whose files ship with the reference
+    (6 Bank needs DATA/Bank/bank-processed.csv and 8 Chess DATA/chess.csv, which the repository does not hold)."""
     base = os.path.join(data_root, "DATA")
+    if problem in (1, 2):                                                         # wine quality red / white, C:909-919, C:931-941
+        name = "winequality-red" if problem == 1 else "winequality-white"
+        data = np.genfromtxt(os.path.join(base, name + '.csv'), delimiter=';')[1:, :]     # first line: column labels
+        tr, te = _zscore_and_split(data[:, 0:11], data[:, 11].reshape(data.shape[0], 1),  # quality scores 3..9 index 10 outputs as they are
+                                   complementary_test_split=complementary_test_split)
+        return name, tr, te, [11, 50, 10]
     if problem == 3:                                                              # Iris, C:920-930
         data = np.genfromtxt(os.path.join(base, 'iris.csv'), delimiter=';')
-        classes = data[:, 4].reshape(data.shape[0], 1) - 1
-        features = data[:, 0:4]
-        for k in range(4):                                                        # C:1003-1007
-            features[:, k] = (features[:, k] - np.mean(features[:, k])) / np.std(features[:, k])
-        indices = np.random.permutation(features.shape[0])                        # C:1010
-        ntr = int(0.7 * features.shape[0])
-        traindata = np.hstack([features[indices[:ntr], :], classes[indices[:ntr], :]])
-        testdata = np.hstack([features[indices[ntr:], :], classes[indices[ntr:], :]])
-        return "iris", traindata, testdata, [4, 12, 3]
+        tr, te = _zscore_and_split(data[:, 0:4], data[:, 4].reshape(data.shape[0], 1) - 1,
+                                   complementary_test_split=complementary_test_split)
+        return "iris", tr, te, [4, 12, 3]
     if problem == 4:                                                              # Ionosphere, C:942-949
         tr = np.genfromtxt(os.path.join(base, 'Ions/Ions/ftrain.csv'), delimiter=',')[:, :-1]
         te = np.genfromtxt(os.path.join(base, 'Ions/Ions/ftest.csv'), delimiter=',')[:, :-1]

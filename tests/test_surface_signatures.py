@@ -84,3 +84,34 @@ def test_ladder_matches_reference_known_answer():
     assert pt.NumSamples == 100 and pt.num_param == 31
     with pytest.raises(ValueError):
         pt.default_beta_ladder(2, ntemps=10, Tmax=1)                              # R:544-545
+
+
+def test_classification_loaders_follow_the_reference_lines():
+    """load_problem == the reference's own preprocessing lines (C:909-930, C:1001-1012) executed here on its
+    data files, including the test-set slice quirk (DESIGN Q17).  Skipped where /root/reference is absent."""
+    import os
+    import numpy as np
+    root = "/root/reference/multicore-pt-classification"
+    if not os.path.isdir(os.path.join(root, "DATA")):
+        pytest.skip("reference data not present")
+    for problem, fname, ip, shift, skip in ((1, "winequality-red.csv", 11, 0, 1), (2, "winequality-white.csv", 11, 0, 1), (3, "iris.csv", 4, 1, 0)):
+        np.random.seed(5)
+        data = np.genfromtxt(os.path.join(root, "DATA", fname), delimiter=';')[skip:, :]
+        classes = data[:, ip].reshape(data.shape[0], 1) - shift
+        features = data[:, 0:ip]
+        for k in range(ip):                                                        # C:1003-1007
+            features[:, k] = (features[:, k] - np.mean(features[:, k])) / np.std(features[:, k])
+        indices = np.random.permutation(features.shape[0])
+        n = int(0.7 * features.shape[0])
+        traindata = np.hstack([features[indices[:n], :], classes[indices[:n], :]])
+        testdata = np.hstack([features[indices[n]:, :], classes[indices[n]:, :]])   # C:1012, as written
+        np.random.seed(5)
+        _, tr, te, topo = cls.load_problem(problem, root)
+        assert np.array_equal(tr, traindata) and np.array_equal(te, testdata) and topo[0] == ip
+        np.random.seed(5)
+        _, tr2, te2, _ = cls.load_problem(problem, root, complementary_test_split=True)
+        assert np.array_equal(tr2, traindata) and te2.shape[0] == features.shape[0] - n
+    for problem, shape in ((4, (245, 35)), (5, (489, 10)), (7, (7494, 17))):
+        assert cls.load_problem(problem, root)[1].shape == shape
+    with pytest.raises(ValueError):
+        cls.load_problem(6, root)                                                  # Bank: bank-processed.csv is not in the repository
