@@ -187,6 +187,16 @@ typedef struct ptfnn_summary {
 } ptfnn_summary;
 int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t count, ptfnn_summary *out);
 
+/* Posterior-predictive moments straight from the device traces (regression).  Every recorded
+ * weight vector of rows [first, first+count) of every local replica -- the pooled posterior the reference
+ * would have put into fx_train_all / fx_test_all (R:785-788, R:809-815, commented out "for memory") -- is run
+ * through the network on the train (which = 0) or test (which = 1) set in one batched pass, and the
+ * predictions are reduced over the samples on the device: mean[r] and std[r] (np.std) of fx[:, r] for every
+ * data row r.  Neither the weights nor the [samples, rows] prediction matrix leave the GPU.
+ * rmse_of_mean (optional): RMSE of the posterior-mean prediction against the targets. */
+int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count,
+                             double *mean /* [rows] */, double *std /* [rows] */, double *rmse_of_mean /* [1] or NULL */);
+
 /* Host side of the same pipeline: byte-compatible replacements of the np.savetxt / np.loadtxt calls
  * the reference spends its result phase in (R:454-481, R:794-831).  No device involved; thread-safe
  * (one file per call).  fmt: one printf conversion, as np.savetxt's fmt ('%.18e', '%1.8f', ...).

@@ -299,6 +299,9 @@ class ParallelTemperingBase:
         self.results_from_files = True      # show_results() re-reads them (R:794-831); False = in-memory, full precision
         self.posterior_predictive = False   # True: fx_train_all / fx_test_all hold the predictions of every posterior
                                             # sample (one batched GPU pass) instead of the reference's zeros (R:785-788)
+        self.predictive_moments = False     # True (regression): posterior-predictive mean / std of every train and test row over
+                                            # the pooled posterior, reduced on the device, left in self.predictive
+        self.predictive = None
         self.last_sampler_seconds = None
         self.summary = None                 # device-reduced statistics of the last run (Sampler.trace_summary)
         self._traces = None
@@ -405,6 +408,8 @@ class ParallelTemperingBase:
             s.init_chains(np.stack([np.asarray(c.w, dtype=np.float64) for c in self.chains]))
             s.run()
             self.summary = s.trace_summary(burnin, S - burnin) if S > burnin else None
+            if self.predictive_moments and self.TASK == REGRESSION and S > burnin:
+                self.predictive = {k: s.predictive_summary(k, burnin, S - burnin) for k in ("train", "test")}
             t = s.traces() if want_traces else s.traces(first=S - 1, count=1, pos_w=False)
             st = s.get_state()
             ns, tot, _ = s.swap_stats()

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ptfnn_abi_version", "ptfnn_build_info", "ptfnn_device_count", "ptfnn_default_config", "ptfnn_last_error",
     "ptfnn_create", "ptfnn_destroy", "ptfnn_set_stream", "ptfnn_set_data", "ptfnn_init_chains",
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
-    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary",
+    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary", "ptfnn_predictive_summary",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",

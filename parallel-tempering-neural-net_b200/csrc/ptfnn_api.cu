@@ -869,7 +869,7 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
     a.pos_w = s->pos_w.p;
     a.series[0] = s->rmse_tr.p; a.series[1] = s->rmse_te.p; a.series[2] = s->acc_tr.p; a.series[3] = s->acc_te.p;
     a.R = R; a.S = S; a.P = P; a.first = first; a.count = count; a.ctiles = ctiles;
-    a.mblocks = mblocks;
+    a.mblocks = mblocks; a.with_series = 1;
     a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_part + 16 * (size_t)nblocks);
     a.stats = d_stats; a.mean = d_mean; a.stdev = d_std;
     const dim3 grid(nblocks);
@@ -897,6 +897,82 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
     out->kernel_ms = ms;
     out->bytes_read = (int64_t)R * count * (4 * 8 + (moments ? (int64_t)P * 4 : 0));
     return done(PTFNN_OK);
+}
+
+// Posterior-predictive moments from the device traces: forward pass of every pooled posterior
+// sample (one CTA per recorded weight vector, read in place from pos_w), then the moments planes of
+// trace_summary_kernel over the [samples, rows] prediction matrix.
+extern "C" int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count,
+                                        double *mean, double *stdev, double *rmse_of_mean) {
+    if (!s || !mean || !stdev) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    if (s->cfg.task != PTFNN_TASK_REGRESSION) return fail(s, PTFNN_E_UNSUPPORTED, "predictive moments are defined for regression outputs (classification fx is a class index, C:148)");
+    if (which != 0 && which != 1) return fail(s, PTFNN_E_INVALID, "which = %d (0 train, 1 test)", which);
+    if (first < 0 || count < 1 || first + count > s->cfg.samples) return fail(s, PTFNN_E_INVALID, "rows [%d,%d) outside [0,%d)", first, first + count, s->cfg.samples);
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    int rc = sync_and_check(s);
+    if (rc) return rc;
+    const int R = s->cfg.n_replicas, S = s->cfg.samples, P = s->P;
+    const int N = which == 0 ? s->n_train : s->n_test;
+    const long long n = (long long)R * count;
+    if (n > 0x7fffffffLL || (double)n * N * 4.0 > 16e9) return fail(s, PTFNN_E_UNSUPPORTED, "%lld samples x %d rows of predictions exceed the 16 GB staging limit: summarise a shorter slice", n, N);
+    DevBuf<float> d_fx;
+    DevBuf<double> d_sums, d_out;
+    cudaError_t e;
+    if ((e = d_fx.ensure((size_t)n * N + kSumTracePadFloats)) != cudaSuccess || (e = d_sums.ensure((size_t)3 * n)) != cudaSuccess)
+        return fail(s, PTFNN_E_NOMEM, "cudaMalloc of the prediction matrix (%lld x %d): %s", n, N, cudaGetErrorString(e));
+    // ---- forward pass, one launch per replica (its slice of pos_w is a batch of `count` vectors at stride P)
+    const KernelSet *ks = s->ks;
+    const size_t smem_fwd = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
+    CU_TRY(s, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
+    DataView v = which == 0 ? view(s->train_x, s->train_y, s->n_train) : view(s->test_x, s->test_y, s->n_test);
+    for (int r = 0; r < R; ++r) {
+        const float *wp = s->pos_w.p + ((size_t)r * S + first) * P;
+        float *fxp = d_fx.p + (size_t)r * count * N, *pp = nullptr;
+        double *sp = d_sums.p + (size_t)3 * r * count;
+        void *args[] = {&wp, &v, &fxp, &pp, &sp};
+        CU_TRY(s, cudaLaunchKernel(ks->fwd, dim3(count), dim3(ks->NT), args, smem_fwd, s->stream));
+    }
+    // ---- moments over the samples for every data row
+    const int cols = N <= kSumThreads ? 1 : N <= 2 * kSumThreads ? 2 : N <= 4 * kSumThreads ? 4 : 8;
+    const int ctiles = (N + kSumThreads * cols - 1) / (kSumThreads * cols);
+    const int rpc = sum_rows_per_chunk(N, cols, ctiles == 1);
+    const long long items = (n + rpc - 1) / rpc;
+    const int mblocks = (int)std::max<long long>(1, std::min<long long>(items, std::max(1, 2 * s->num_sms / ctiles)));
+    const size_t need = 4 * (size_t)N + 2;
+    CU_TRY(s, d_out.ensure(need));
+    CU_TRY(s, cudaMemsetAsync(d_out.p, 0, need * sizeof(double), s->stream));
+    if (!s->summary_smem_opted) {
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
+        s->summary_smem_opted = true;
+    }
+    TraceSummaryArgs a;
+    memset(&a, 0, sizeof a);
+    a.pos_w = d_fx.p;
+    a.R = 1; a.S = (int)n; a.P = N; a.first = 0; a.count = (int)n; a.ctiles = ctiles; a.mblocks = mblocks; a.with_series = 0;
+    a.acc = d_out.p; a.mean = d_out.p + 2 * N; a.stdev = d_out.p + 3 * N;
+    a.ticket = reinterpret_cast<unsigned int *>(d_out.p + 4 * N);
+    a.part = nullptr; a.stats = nullptr;
+    const dim3 grid(ctiles * mblocks);
+    if (cols == 1) trace_summary_kernel<1><<<grid, kSumThreads, kSumSmemBytes, s->stream>>>(a);
+    else if (cols == 2) trace_summary_kernel<2><<<grid, kSumThreads, kSumSmemBytes, s->stream>>>(a);
+    else if (cols == 4) trace_summary_kernel<4><<<grid, kSumThreads, kSumSmemBytes, s->stream>>>(a);
+    else trace_summary_kernel<8><<<grid, kSumThreads, kSumSmemBytes, s->stream>>>(a);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaMemcpyAsync(mean, a.mean, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(stdev, a.stdev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    std::vector<float> y(rmse_of_mean ? (size_t)N : 0);
+    if (rmse_of_mean) CU_TRY(s, cudaMemcpyAsync(y.data(), which == 0 ? s->train_y.p : s->test_y.p, (size_t)N * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (rmse_of_mean) {
+        double acc = 0.0;
+        for (int r = 0; r < N; ++r) acc += (mean[r] - (double)y[r]) * (mean[r] - (double)y[r]);
+        *rmse_of_mean = std::sqrt(acc / N);
+    }
+    return PTFNN_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -118,6 +118,7 @@ struct TraceSummaryArgs {
     const double *series[4];   // [R, S] each
     int R, S, P, first, count, ctiles;
     int mblocks;               // blocks per column tile: gridDim.x = ctiles*mblocks (any number when ctiles == 0)
+    int with_series;           // 0: moments only (the matrix is not a trace: ptfnn_predictive_summary)
     double *acc;               // [2][P], zero on entry, zero on exit
     double *part;              // [gridDim.x][4 series][4]
     unsigned int *ticket;      // zero on entry, zero on exit
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
             }
         }
     }
-    {   // ---- the four scalar series, side by side
+    if (a.with_series) {   // ---- the four scalar series, side by side
         const double *x0 = a.series[0], *x1 = a.series[1], *x2 = a.series[2], *x3 = a.series[3];
         double pv[4] = {x0[a.first], x1[a.first], x2[a.first], x3[a.first]};
         double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
     if (!s_last) return;
     __threadfence();
     const double n = (double)a.R * (double)count;
-    if (tid < 128) {
+    if (tid < 128 && a.with_series) {
         const int sidx = tid >> 5, lane = tid & 31;
         const double pivot = series_of(a, sidx)[a.first];
         double s1 = 0.0, s2 = 0.0, lo = pivot, hi = pivot;

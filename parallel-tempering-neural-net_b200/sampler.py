@@ -212,6 +212,18 @@ class Sampler:
             out[k] = {"mean": v[0], "std": v[1], "min": v[2], "max": v[3]}
         return out
 
+    def predictive_summary(self, which="test", first=0, count=None):
+        """Posterior-predictive mean and std of every data row over the pooled posterior samples (rows
+        [first, first+count) of every chain's pos_w), computed from the device traces: what np.mean / np.std
+        over the fx_*_all arrays the reference comments out (R:785-788, R:809-815) would give.  Regression.
+        -> dict(mean[rows], std[rows], rmse_of_mean)"""
+        count = self.S - first if count is None else count
+        rows = self.n_train if which == "train" else self.n_test
+        mean, std, rm = np.empty(rows), np.empty(rows), C.c_double()
+        self._ck(self._lib.ptfnn_predictive_summary(self._h, 0 if which == "train" else 1, int(first), int(count),
+                                                    capi.ptr(mean), capi.ptr(std), C.byref(rm)))
+        return {"mean": mean, "std": std, "rmse_of_mean": rm.value}
+
     def swap_stats(self, max_rounds=None):
         """-> (num_swap, total_swap_proposals, swapped[rounds, Rg-1])"""
         ns, tot = C.c_int64(), C.c_int64()

@@ -117,3 +117,49 @@ def test_run_problem_with_device_results(tmp_path):
                                         swap_ratio=0.05, seed=21, results=mode)
         assert len(open(out / "master_result_file.txt").read().split()) == 16            # 15 numbers + run name (R:1052-1061)
     assert np.allclose(rows["host"][:14], rows["device"][:14], rtol=1e-4, atol=1e-7)   # host row: statistics of the %1.8f txt files
+
+
+@pytest.mark.parametrize("ds,topo,R,S,first,count", [("Sunspot", (4, 5, 1), 4, 40, 20, 20), ("Lazer", (4, 10, 1), 3, 25, 3, 17),
+                                                   ("Mackey", (4, 64, 1), 2, 12, 6, 6)])
+def test_predictive_moments_from_device_traces_match_oracle(ds, topo, R, S, first, count):
+    """ptfnn_predictive_summary == np.mean / np.std over the per-sample predictions the float64 oracle computes for
+    every recorded weight vector of the slice (what fx_train_all / fx_test_all would hold, R:785-788, R:809-815)."""
+    from oracle import ptfnn_c as oc
+    tr, te = cm.dataset(on.REGRESSION, ds)
+    P = topo[0] * topo[1] + topo[1] * topo[2] + topo[1] + topo[2]
+    w0 = np.random.RandomState(4).randn(R, P) * 0.5
+    with Sampler(on.REGRESSION, topo, geometric_ladder(R, 3), S, 5, learn_rate=0.05, l_prob=0.5, seed=3) as s:
+        s.set_data(tr, te)
+        s.init_chains(w0)
+        s.run()
+        got = {k: s.predictive_summary(k, first, count) for k in ("train", "test")}
+        pw = s.traces()["pos_w"][:, first:first + count].reshape(-1, P)
+    for k, data in (("train", tr), ("test", te)):
+        fx = np.stack([oc.evaluate(on.REGRESSION, topo, data, w) for w in pw])
+        assert np.allclose(got[k]["mean"], fx.mean(axis=0), rtol=1e-4, atol=1e-6)
+        assert np.allclose(got[k]["std"], fx.std(axis=0), rtol=1e-3, atol=1e-6)
+        assert got[k]["rmse_of_mean"] == pytest.approx(np.sqrt(np.mean((fx.mean(axis=0) - data[:, -1]) ** 2)), rel=1e-4)
+
+
+def test_predictive_moments_are_regression_only():
+    from ptnn_b200.capi import PtfnnError
+    tr, te = cm.dataset(on.CLASSIFICATION, "Iris")
+    with Sampler(on.CLASSIFICATION, (4, 12, 3), geometric_ladder(2, 2), 10, 5) as s:
+        s.set_data(tr, te)
+        s.init_chains(np.zeros((2, 99)))
+        with pytest.raises(PtfnnError) as e:
+            s.predictive_summary("test", 0, 5)
+        assert e.value.code == -4                                   # PTFNN_E_UNSUPPORTED
+
+
+def test_run_chains_predictive_moments_agree_with_the_per_sample_predictions(tmp_path):
+    """Two routes to SURVEY 8(f).2 on the same run: pt.posterior_predictive fills fx_train_all / fx_test_all
+    (one batched pass, arrays on the host); pt.predictive_moments reduces the same predictions on the device."""
+    pt = _pt(reg, on.REGRESSION, "Sunspot", (4, 5, 1), tmp_path, 4, 60, 10, 2, write_files=False, results_from_files=False,
+             posterior_predictive=True, predictive_moments=True)
+    res = pt.run_chains()
+    for k, fx_all, data in (("train", res[1], pt.traindata), ("test", res[2], pt.testdata)):
+        fx = fx_all.reshape(-1, data.shape[0])
+        assert fx.shape[0] == 4 * 30 and np.any(fx != 0)
+        assert np.allclose(pt.predictive[k]["mean"], fx.mean(axis=0), rtol=1e-6, atol=1e-9)
+        assert np.allclose(pt.predictive[k]["std"], fx.std(axis=0), rtol=1e-5, atol=1e-9)
