@@ -846,13 +846,14 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
         mblocks = (int)std::max<long long>(1, std::min<long long>(items, std::max(1, 2 * s->num_sms / ctiles)));
     }
     const int nblocks = moments ? ctiles * mblocks : mblocks;
-    // layout of d_summary: stats[16] | acc[2P] | mean[P] | std[P] | part[nblocks*16] | ticket
-    const size_t need = 16 + 4 * (size_t)P + 16 * (size_t)nblocks + 1;
+    // layout of d_summary: stats[16] | ticket | acc[2P] | mean[P] | std[P] | part[nblocks*16]
+    // (the ticket and the accumulators sit at offsets that do not depend on the grid: they are zero between calls)
+    const size_t need = 17 + 4 * (size_t)P + 16 * (size_t)nblocks;
     if (need > s->d_summary.n) {
         CU_TRY(s, s->d_summary.ensure(need));
         CU_TRY(s, cudaMemsetAsync(s->d_summary.p, 0, need * sizeof(double), s->stream));   // acc and ticket start at zero; the kernel leaves them so
     }
-    double *d_stats = s->d_summary.p, *d_acc = d_stats + 16, *d_mean = d_acc + 2 * P, *d_std = d_mean + P, *d_part = d_std + P;
+    double *d_stats = s->d_summary.p, *d_ticket = d_stats + 16, *d_acc = d_ticket + 1, *d_mean = d_acc + 2 * P, *d_std = d_mean + P, *d_part = d_std + P;
     if (!s->summary_smem_opted) {                                            // per device, so per handle
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
         CU_TRY(s, cudaFuncSetAttribute(trace_summary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumSmemBytes));
@@ -870,7 +871,7 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
     a.series[0] = s->rmse_tr.p; a.series[1] = s->rmse_te.p; a.series[2] = s->acc_tr.p; a.series[3] = s->acc_te.p;
     a.R = R; a.S = S; a.P = P; a.first = first; a.count = count; a.ctiles = ctiles;
     a.mblocks = mblocks; a.with_series = 1;
-    a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_part + 16 * (size_t)nblocks);
+    a.acc = d_acc; a.part = d_part; a.ticket = reinterpret_cast<unsigned int *>(d_ticket);
     a.stats = d_stats; a.mean = d_mean; a.stdev = d_std;
     const dim3 grid(nblocks);
     const size_t smem = moments ? kSumSmemBytes : 0;

@@ -49,9 +49,16 @@ def test_trace_summary_matches_numpy_on_the_traces(task, ds, topo, R, S, first, 
         s.run()
         sm = s.trace_summary(first, count)
         t = s.traces()
+        # the same handle again with other grids and slices: series only, a one-row slice, the whole trace
         sm2 = s.trace_summary(first, count, posterior=False)
+        sm3 = s.trace_summary(S - 1, 1)
+        sm4 = s.trace_summary(0, S, posterior=False)
+        sm5 = s.trace_summary(0, S)
     _check(sm, t, first, count)
-    assert sm2["w_mean"] is None and sm2["rmse_test"] == sm["rmse_test"]
+    assert sm2["w_mean"] is None and sm2["rmse_test"] == sm["rmse_test"] and sm2["acc_train"] == sm["acc_train"]
+    _check(sm3, t, S - 1, 1)
+    _check(sm5, t, 0, S)
+    assert sm4["rmse_train"] == sm5["rmse_train"] and sm4["n"] == R * S
     assert sm["bytes_read"] == R * count * (32 + 4 * P) and sm["kernel_ms"] > 0
 
 
