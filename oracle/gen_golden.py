@@ -42,6 +42,7 @@ CASES = {
     "reg_acfin_rw":    ("regression", "ACFinance", [4, 5, 1], 6, 2, 70, 10, False, 0.1, 0.5, 37),
     "reg_rossler_lg":  ("regression", "Rossler", [4, 5, 1], 2, 5, 33, 4, True, 0.1, 0.5, 41),      # a round every 4 steps + the left-over one
     "cls_iris_rw":     ("classification", "Iris", [4, 12, 3], 5, 10, 60, 5, False, 0.01, 0.5, 43),
+    "cls_pendigit_lg": ("classification", "PenDigit", [16, 30, 10], 3, 10, 20, 4, True, 0.01, 0.5, 47),   # ten classes, the reference's own data
 }
 
 
@@ -197,7 +198,7 @@ def generate_datasets():
     for n in rh.REG_DATASETS:
         tr, te = rh.load_regression_dataset(n)
         d["reg_%s_train" % n], d["reg_%s_test" % n] = tr, te
-    for n in ("Iris", "Cancer", "Ionosphere"):
+    for n in ("Iris", "Cancer", "Ionosphere", "PenDigit"):
         tr, te, topo = rh.load_classification_dataset(n, split_seed=0)
         d["cls_%s_train" % n], d["cls_%s_test" % n], d["cls_%s_topology" % n] = tr, te, np.array(topo)
     np.savez_compressed(os.path.join(GOLDEN, "datasets.npz"), **d)

@@ -302,6 +302,13 @@ def load_classification_dataset(name: str, split_seed: int = 0):
         tr = _np.hstack([features[idx[:ntr], :], classes[idx[:ntr], :]])
         te = _np.hstack([features[idx[ntr:], :], classes[idx[ntr:], :]])
         return tr, te, [4, 12, 3]
+    if name == "PenDigit":        # C:972-986 (per-split z-score of the 16 features); first 1500 / 600 rows to keep the fixture small
+        tr = _np.genfromtxt(os.path.join(base, "PenDigit/train.csv"), delimiter=",")
+        te = _np.genfromtxt(os.path.join(base, "PenDigit/test.csv"), delimiter=",")
+        for k in range(16):
+            tr[:, k] = (tr[:, k] - _np.mean(tr[:, k])) / _np.std(tr[:, k])
+            te[:, k] = (te[:, k] - _np.mean(te[:, k])) / _np.std(te[:, k])
+        return tr[:1500].copy(), te[:600].copy(), [16, 30, 10]
     raise KeyError(name)
 
 

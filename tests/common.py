@@ -7,7 +7,7 @@ from oracle import ptfnn_numpy as on
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["reg_sunspot_lg", "reg_lazer_rw", "reg_mackey_h10", "cls_iris_lg", "cls_cancer_lg", "cls_ions_lg",
-         "reg_lorenz_lg", "reg_henon_lg1", "reg_acfin_rw", "reg_rossler_lg", "cls_iris_rw"]
+         "reg_lorenz_lg", "reg_henon_lg1", "reg_acfin_rw", "reg_rossler_lg", "cls_iris_rw", "cls_pendigit_lg"]
 REG_DATASETS = ["Lazer", "Sunspot", "Mackey", "Lorenz", "Rossler", "Henon", "ACFinance"]
 CLS_DATASETS = ["Iris", "Cancer", "Ionosphere"]
 
