@@ -651,11 +651,12 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         int sraw[OPW];
 #pragma unroll
         for (int j = 0; j < OPW; ++j) {
-            float a0 = 0.0f, a1 = 0.0f;
+            float2 a = make_float2(0.0f, 0.0f);               // even / odd hidden units: two chains in one FFMA2 stream
 #pragma unroll
-            for (int m = 0; m + 1 < HC; m += 2) { a0 = fmaf(hv[m], w2c[j][m], a0); a1 = fmaf(hv[m + 1], w2c[j][m + 1], a1); }
-            if (HC & 1) a0 = fmaf(hv[HC - 1], w2c[j][HC - 1], a0);
-            sraw[j] = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(a0 + a1, fscale, kMagic)));
+            for (int m = 0; m + 1 < HC; m += 2)
+                a = __ffma2_rn(make_float2(hv[m], hv[m + 1]), make_float2(w2c[j][m], w2c[j][m + 1]), a);
+            if (HC & 1) a.x = fmaf(hv[HC - 1], w2c[j][HC - 1], a.x);
+            sraw[j] = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(a.x + a.y, fscale, kMagic)));
         }
 #pragma unroll
         for (int j = 0; j < OPW; ++j) {
@@ -675,8 +676,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         // ---- column-view updates and this thread's look-ahead (off the chain)
 #pragma unroll
         for (int j = 0; j < OPW; ++j) {
-#pragma unroll
-            for (int m = 0; m < HC; ++m) w2c[j][m] = fmaf(lo_j[j], hv[m], w2c[j][m]);   // R:67-69 (column view)
+            vfma_s<HC>(w2c[j], hv, lo_j[j], w2c[j]);                                  // R:67-69 (column view), FFMA2
             b2[j] -= lo_j[j];                                                         // R:70-71
             b2l[j] = kL2E * b2[j];
         }
