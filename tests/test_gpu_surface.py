@@ -180,3 +180,31 @@ def test_swap_procedure_object_api():
     assert (pt.num_swap, pt.total_swap_proposals) == (1, 1)
     a, b, swapped = pt.swap_procedure(Q(p2), Q(p1))                                   # l2 - l1 = -100 -> p ~ 0
     assert not swapped and (pt.num_swap, pt.total_swap_proposals) == (1, 2)
+
+
+def test_integration_md_binding_stub_runs():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (section 2) is executable as printed: it is
+    extracted from the document and driven with a minimal stand-in for ParallelTempering."""
+    import re
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "def run_chains(self)" in b]
+    assert len(blocks) == 1
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)                                      # the stub opens the library by its path inside the repository
+    try:
+        exec(compile(blocks[0], "INTEGRATION.md", "exec"), ns)
+        tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+        R, S = 4, 60
+        rs = np.random.RandomState(1)
+        pt = types.SimpleNamespace(topology=[4, 5, 1], num_chains=R, NumSamples=S, swap_interval=10, use_langevin_gradients=True,
+                                   langevin_prob=0.5, learn_rate=0.1, temperatures=list(on.geometric_ladder(R, 2)),
+                                   traindata=tr, testdata=te, num_param=31, num_swap=0, total_swap_proposals=0,
+                                   chains=[types.SimpleNamespace(w=rs.randn(31)) for _ in range(R)])
+        np.random.seed(3)
+        ns["run_chains"](pt)
+    finally:
+        os.chdir(cwd)
+    assert pt.total_swap_proposals == 6 * (R - 1) and 0 <= pt.num_swap <= pt.total_swap_proposals   # S/swap_interval rounds (Q9)
