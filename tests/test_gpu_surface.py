@@ -208,3 +208,25 @@ def test_integration_md_binding_stub_runs():
     finally:
         os.chdir(cwd)
     assert pt.total_swap_proposals == 6 * (R - 1) and 0 <= pt.num_swap <= pt.total_swap_proposals   # S/swap_interval rounds (Q9)
+
+
+def test_classification_cli_like_run_sh(tmp_path, monkeypatch):
+    """`python pt_classification.py <swap_ratio>` (run.sh:8-11, C:1039) through ptnn_b200.classification.main on an
+    iris.csv laid out like the reference's DATA/iris.csv (';' separated, labels 1..3): default NumSample 50 000,
+    10 chains, the result row appended to master_result_file.txt (C:1138-1146)."""
+    tr, te = cm.dataset(on.CLASSIFICATION, "Iris")
+    data = np.vstack([tr, te])
+    data[:, 4] += 1
+    os.makedirs(tmp_path / "root" / "DATA")
+    np.savetxt(tmp_path / "root" / "DATA" / "iris.csv", data, delimiter=";")
+    monkeypatch.setenv("PT_DATA_ROOT", str(tmp_path / "root"))
+    monkeypatch.setenv("PT_OUT_ROOT", str(tmp_path / "out"))
+    np.random.seed(0)
+    cls.main(["0.02", "3"])
+    row = open(tmp_path / "out" / "master_result_file.txt").read().split()
+    assert len(row) == 16 and row[-1] == "iris_0"
+    vals = [float(v) for v in row[:15]]
+    assert vals[0] == 3 and vals[1] == 50000 and vals[3] == 100                       # problem, NumSample, swap_interval = 0.02 * 50000 / 10
+    assert 50.0 < vals[6] <= 100.0 and 50.0 < vals[9] <= 100.0                        # mean train / test accuracy of the pooled posterior
+    files = [f for _, _, fs in os.walk(tmp_path / "out" / "iris_0") for f in fs]
+    assert len(files) == 10 * 8 + 5                                                   # 8 files per chain + 4 aggregates + result.txt
