@@ -123,3 +123,33 @@ def test_ladder_and_swap_rule():
         a, b = on.swap_sweep(lh, u)
         c, d = oc.swap_sweep(lh, u)
         assert a == c.tolist() and b == d.tolist()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_oracle_equals_numpy_oracle_on_random_configurations(seed):
+    """The C restatement (used for full-size replays) against the NumPy one (bit-identical to the reference on the
+    golden runs) outside the golden set: random topologies, ladders, swap cadences, Langevin probabilities and data,
+    including a round on the last step, 0.6*S integral or not, and both tasks."""
+    rs = np.random.RandomState(100 + seed)
+    task = on.REGRESSION if seed % 2 == 0 else on.CLASSIFICATION
+    I, H = int(rs.randint(1, 7)), int(rs.randint(1, 12))
+    O = 1 if task == on.REGRESSION else int(rs.randint(2, 5))
+    R, S, si = int(rs.randint(1, 5)), int(rs.choice([10, 15, 17, 20])), int(rs.randint(1, 7))
+    cfg = on.PTConfig(task=task, topology=(I, H, O), samples=S, swap_interval=si, use_langevin_gradients=bool(seed % 3),
+                      l_prob=float(rs.choice([0.3, 0.5, 1.0])), learn_rate=float(rs.choice([0.01, 0.1])))
+
+    def data(n):
+        x = rs.rand(n, I) if task == on.REGRESSION else rs.randn(n, I)
+        y = rs.rand(n, 1) if task == on.REGRESSION else rs.randint(0, O, size=(n, 1)).astype(float)
+        return np.hstack([x, y])
+
+    tr, te = data(int(rs.randint(3, 40))), data(int(rs.randint(2, 25)))
+    temps = on.geometric_ladder(R, float(rs.choice([2, 5, 10]))) if R > 1 else np.ones(1)
+    w0 = rs.randn(R, cfg.P) * 0.7
+    draws = on.random_draws(cfg, R, seed, common_random_numbers=bool(seed % 2))
+    a = on.run_pt(cfg, tr, te, temps, w0, draws)
+    b = oc.run_pt(cfg, tr, te, temps, w0, draws)
+    assert np.array_equal(a.accepted, b.accepted) and np.array_equal(a.swapped, b.swapped)
+    assert (a.num_swap, a.total_swap_proposals) == (b.num_swap, b.total_swap_proposals)
+    for k in ("pos_w", "lik_prop", "prior_prop", "diff_prop", "mh_prob", "rmse_train", "rmse_test", "acc_train", "acc_test", "accept_list"):
+        assert cm.relerr(getattr(a, k), getattr(b, k)) < 1e-9, k
