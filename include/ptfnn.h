@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PTFNN_ABI_VERSION 1
+#define PTFNN_ABI_VERSION 2
 
 #define PTFNN_OK 0
 #define PTFNN_E_INVALID (-1)     /* bad argument / shape */
@@ -44,6 +44,12 @@ extern "C" {
 #define PTFNN_SWAP_RULE_AUTO (-1)
 #define PTFNN_SWAP_RULE_AFTER_I 0   /* R:427  swap when i % s == 0 and i != 0 */
 #define PTFNN_SWAP_RULE_BEFORE_I1 1 /* C:438  swap when (i+1) % s == 0 */
+
+/* The swap PROBABILITY.  The reference's scripts use R:674 / C:683; its drafts carry a temperature-aware
+ * ratio rule (Misc/ldpt_fnn_multi_fixed.py:520) that no published result uses -- opt-in, single GPU, and
+ * outside replay parity. */
+#define PTFNN_SWAP_KIND_REFERENCE 0          /* min(1, 0.5 exp(min(709, lhood2 - lhood1))) */
+#define PTFNN_SWAP_KIND_RATIO_TEMPERATURE 1  /* (lhood1 / (lhood2 or 1)) * (1/T1 * 1/T2) */
 
 typedef struct ptfnn_sampler ptfnn_sampler;
 
@@ -65,11 +71,16 @@ typedef struct ptfnn_config {
     int32_t memoize_gradient;       /* 1 = reuse langevin_gradient(w) while w is unchanged
                                        (bit-identical results) */
     int32_t device;                 /* CUDA ordinal */
-    int32_t threads_per_block;      /* 0 = auto */
+    int32_t barrier_timeout_ms;     /* limit on time WITHOUT PROGRESS in a device-side wait (swap-round grid
+                                     * barrier, peer flags); 0 = 20 000.  A wait that gives up ends the launch,
+                                     * leaves state and traces untouched and makes every later call on the
+                                     * handle fail with PTFNN_E_CUDA until ptfnn_init_chains */
     int32_t debug_traces;           /* 1 = also record prior_prop / diff_prop / mh_prob / accepted */
     int32_t speculation;            /* small ladders: CTAs per temperature that evaluate consecutive steps
                                      * speculatively (results are those of the sequential chain, bit for bit);
                                      * 0 = automatic, 1 = off, K = that depth */
+    int32_t swap_kind;              /* PTFNN_SWAP_KIND_* */
+    int32_t reserved0;              /* 0 */
     uint64_t seed;                  /* Philox key (free-running mode) */
     double l_prob;                  /* langevin_prob, R:174 (C:192 fixes 0.5) */
     double learn_rate;              /* R:172 */
@@ -196,6 +207,12 @@ int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t count, ptfnn_su
  * rmse_of_mean (optional): RMSE of the posterior-mean prediction against the targets. */
 int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count,
                              double *mean /* [rows] */, double *std /* [rows] */, double *rmse_of_mean /* [1] or NULL */);
+/* Percentile bands of the same posterior-predictive distribution (the 5 % - 95 % uncertainty band the
+ * reference's drafts plot from fx_*_all): lo[r] = np.percentile(fx[:, r], q_lo), hi[r] = np.percentile(fx[:, r],
+ * q_hi) with NumPy's default linear interpolation, for every data row r, by an exact radix select over the
+ * [samples, rows] prediction matrix on the device.  q in percent, 0 <= q_lo <= q_hi <= 100. */
+int ptfnn_predictive_bands(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count, double q_lo, double q_hi,
+                           double *lo /* [rows] */, double *hi /* [rows] */);
 
 /* Host side of the same pipeline: byte-compatible replacements of the np.savetxt / np.loadtxt calls
  * the reference spends its result phase in (R:454-481, R:794-831).  No device involved; thread-safe
@@ -208,7 +225,8 @@ int ptfnn_loadtxt(const char *path, double *out, int64_t capacity, int64_t *rows
 /* ---- multi-GPU round (ladder partitioned over ranks).  Device pointers are owned by
  * the caller (torch tensors), so that NCCL can move them:
  *   lhood_local  [n_replicas]        float64  swap field of each local replica (R:430 / C:439)
- *   rows_local   [n_replicas, P+1]   float32  (w, eta) of each local replica
+ *   rows_local   [n_replicas, P+2]   float32  (w, eta) of each local replica; the two words behind the P weights
+ *                                             are the bit pattern of the float64 eta (R:430 moves the float64)
  * After all-gathering lhood over ranks, ptfnn_swap_plan runs the reference's sequential sweep
  * (R:741-748) with the same device code every rank and returns src[k] = ladder slot whose vector
  * ends up in slot k.  Rows whose source is remote are received into rows_in (same shape as
@@ -218,7 +236,10 @@ int ptfnn_loadtxt(const char *path, double *out, int64_t capacity, int64_t *rows
  * all ranks are exchanged by the caller (e.g. torch.distributed.all_gather_object) and handed to
  * ptfnn_peer_connect.  Afterwards ptfnn_run / ptfnn_replay advance through swap rounds like the
  * single-GPU kernel does; every rank must request the same number of steps.  Replaces the reference's
- * parameter queues and events between processes (R:427-437, R:730-752). */
+ * parameter queues and events between processes (R:427-437, R:730-752).
+ * ptfnn_init_chains may be called again on connected handles (the arrival flags count across runs); the
+ * caller must put a barrier between the ranks before the first step of the new run, so that no rank
+ * publishes into a window a slower rank is still reading. */
 #define PTFNN_PEER_HANDLE_BYTES 64
 int ptfnn_peer_export(ptfnn_sampler *s, void *handles /* [3][PTFNN_PEER_HANDLE_BYTES] */);
 int ptfnn_peer_connect(ptfnn_sampler *s, int32_t n_ranks, int32_t rank,
@@ -265,6 +286,9 @@ int ptfnn_op_prior(int32_t device, int32_t task, int32_t n_in, int32_t n_hidden,
 /* ParallelTempering.swap_procedure applied as the sequential sweep of run_chains (R:659-690, R:741-748) */
 int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row,
                         int32_t *src, uint8_t *swapped);
+/* the same sweep under PTFNN_SWAP_KIND_*; temperature [n] travels with the vectors (may be NULL for kind 0) */
+int ptfnn_op_swap_sweep_kind(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t swap_kind,
+                             const double *temperature, int32_t *src, uint8_t *swapped);
 
 #ifdef __cplusplus
 }

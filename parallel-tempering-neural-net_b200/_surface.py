@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import capi
-from .sampler import Sampler
+from .sampler import Sampler, geometric_betas
 
 REGRESSION, CLASSIFICATION = capi.TASK_REGRESSION, capi.TASK_CLASSIFICATION
 
@@ -301,13 +301,22 @@ class ParallelTemperingBase:
                                             # sample (one batched GPU pass) instead of the reference's zeros (R:785-788)
         self.predictive_moments = False     # True (regression): posterior-predictive mean / std of every train and test row over
                                             # the pooled posterior, reduced on the device, left in self.predictive
+        self.predictive_bands = None        # e.g. (5, 95): with predictive_moments, also np.percentile bands of the same predictions
         self.predictive = None
+        self.swap_kind = 0                  # 0: the swap probability of R:674; 1: the drafts' temperature-aware rule
+                                            # (Misc/ldpt_fnn_multi_fixed.py:520) -- opt-in, outside replay parity
         self.last_sampler_seconds = None
         self.summary = None                 # device-reduced statistics of the last run (Sampler.trace_summary)
         self._traces = None
 
     def default_beta_ladder(self, ndim, ntemps, Tmax):
-        """R:529-613 (after ptemcee).  Only the geometric spacing is reachable from assign_temperatures."""
+        """Inverse temperatures of the ladder (R:529-613).  For every argument list the reference's version
+        survives, its result is the geometric spacing logspace(0, -log10(Tmax), ntemps) (R:607): it rejects
+        bad arguments first (R:538-547), then iterates ``range(Tmax)`` over a step that divides by
+        ``ntemps - 1`` (R:570-579) -- so a non-integer Tmax (None and inf included) is a TypeError and a
+        one-rung ladder a ZeroDivisionError -- and the ptemcee step size it derives from ``ndim`` is never
+        used once both ntemps and Tmax are given.  Same checks, same errors, same numbers here."""
+        import operator
         if type(ndim) != int or ndim < 1:
             raise ValueError('Invalid number of dimensions specified.')
         if ntemps is None and Tmax is None:
@@ -316,33 +325,12 @@ class ParallelTemperingBase:
             raise ValueError('``Tmax`` must be greater than 1.')
         if ntemps is not None and (type(ntemps) != int or ntemps < 1):
             raise ValueError('Invalid number of temperatures specified.')
-        maxtemp, numchain = Tmax, ntemps
-        b = [maxtemp]
-        last = maxtemp
-        for _ in range(maxtemp):                                                 # R:576: maxtemp must be an int
-            last = last * (numchain ** (-1 / (numchain - 1)))
-            b.append(last)
-        tstep = np.array(b)
-        if ndim > tstep.shape[0]:
-            tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
-        else:
-            tstep = tstep[ndim - 1]
-        appendInf = False
-        if Tmax == np.inf:
-            appendInf = True
-            Tmax = None
-            ntemps = ntemps - 1
-        if ntemps is not None:
-            if Tmax is None:
-                Tmax = tstep ** (ntemps - 1)
-        else:
-            if Tmax is None:
-                raise ValueError('Must specify at least one of ``ntemps'' and finite ``Tmax``.')
-            ntemps = int(np.log(Tmax) / np.log(tstep) + 2)
-        betas = np.logspace(0, -np.log10(Tmax), ntemps)                            # R:607
-        if appendInf:
-            betas = np.concatenate((betas, [0]))
-        return betas
+        operator.index(Tmax)                       # R:576 range(maxtemp): TypeError unless an integer
+        if ntemps is None:
+            raise TypeError("unsupported operand type(s) for ** or pow(): 'NoneType' and 'float'")   # R:577
+        if ntemps == 1:
+            raise ZeroDivisionError('division by zero')                                            # R:577
+        return geometric_betas(ntemps, Tmax)
 
     def assign_temperatures(self):
         if self.geometric is True:                                                # R:624-628
@@ -403,13 +391,14 @@ class ParallelTemperingBase:
         with Sampler(self.TASK, self.topology, self.temperatures, S, self.swap_interval,
                      use_langevin_gradients=self.use_langevin_gradients, l_prob=l_prob, learn_rate=self.learn_rate,
                      seed=seed, common_random_numbers=self.common_random_numbers,
-                     memoize_gradient=self.memoize_gradient, device=self.device) as s:
+                     memoize_gradient=self.memoize_gradient, device=self.device, swap_kind=self.swap_kind) as s:
             s.set_data(self.traindata, self.testdata)
             s.init_chains(np.stack([np.asarray(c.w, dtype=np.float64) for c in self.chains]))
             s.run()
             self.summary = s.trace_summary(burnin, S - burnin) if S > burnin else None
             if self.predictive_moments and self.TASK == REGRESSION and S > burnin:
-                self.predictive = {k: s.predictive_summary(k, burnin, S - burnin) for k in ("train", "test")}
+                self.predictive = {k: s.predictive_summary(k, burnin, S - burnin, bands=self.predictive_bands)
+                                   for k in ("train", "test")}
             t = s.traces() if want_traces else s.traces(first=S - 1, count=1, pos_w=False)
             st = s.get_state()
             ns, tot, _ = s.swap_stats()

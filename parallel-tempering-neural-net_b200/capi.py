@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libptfnn.so")
 OK, E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4, -5
 TASK_REGRESSION, TASK_CLASSIFICATION = 0, 1
 SWAP_RULE_AUTO, SWAP_RULE_AFTER_I, SWAP_RULE_BEFORE_I1 = -1, 0, 1
-ABI_VERSION = 1
+SWAP_KIND_REFERENCE, SWAP_KIND_RATIO_TEMPERATURE = 0, 1      # R:674 | Misc/ldpt_fnn_multi_fixed.py:520 (opt-in)
+ABI_VERSION = 2
 PEER_HANDLE_BYTES = 64       # cudaIpcMemHandle_t
 
 # every symbol include/ptfnn.h declares (tests/test_capi_symbols.py checks the header against this)
@@ -25,11 +26,11 @@ SYMBOLS = [
     "ptfnn_abi_version", "ptfnn_build_info", "ptfnn_device_count", "ptfnn_default_config", "ptfnn_last_error",
     "ptfnn_create", "ptfnn_destroy", "ptfnn_set_stream", "ptfnn_set_data", "ptfnn_init_chains",
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
-    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary", "ptfnn_predictive_summary",
+    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary", "ptfnn_predictive_summary", "ptfnn_predictive_bands",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
-    "ptfnn_op_swap_sweep", "ptfnn_op_posterior_predictive", "ptfnn_savetxt", "ptfnn_loadtxt",
+    "ptfnn_op_swap_sweep", "ptfnn_op_swap_sweep_kind", "ptfnn_op_posterior_predictive", "ptfnn_savetxt", "ptfnn_loadtxt",
 ]
 
 
@@ -43,7 +44,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "task", "n_in", "n_hidden", "n_out", "n_replicas", "n_replicas_global", "replica_offset",
         "samples", "swap_interval", "swap_rule", "use_langevin_gradients", "common_random_numbers",
-        "memoize_gradient", "device", "threads_per_block", "debug_traces", "speculation")] + \
+        "memoize_gradient", "device", "barrier_timeout_ms", "debug_traces", "speculation", "swap_kind", "reserved0")] + \
         [("seed", C.c_uint64)] + \
         [(n, C.c_double) for n in ("l_prob", "learn_rate", "step_w", "step_eta", "sigma_squared", "nu_1", "nu_2",
                                    "pt_fraction")]
@@ -115,6 +116,7 @@ def ensure_topology(task, topology, verbose=False):
     the library.  Needs nvcc; hidden layers wider than 256 units are not supported."""
     import hashlib
     import subprocess
+    import uuid
     task = int(task)
     I, H, O = (int(x) for x in topology)
     lib = load()
@@ -136,12 +138,15 @@ def ensure_topology(task, topology, verbose=False):
         h.update(open(f, "rb").read())
     so = os.path.join(out_dir, "libptfnn_topo_%s_%s.so" % (name, h.hexdigest()[:12]))
     if not os.path.exists(so):
+        # a name of its own per process: the ranks of a multi-GPU launch may all compile the same new topology at once,
+        # and os.replace() must publish a complete file whichever of them finishes first
+        tmp = "%s.%d.%s.tmp" % (so, os.getpid(), uuid.uuid4().hex[:8])
         nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-cudart", "shared", "-DPTFNN_T_STANDALONE",
                "-DPTFNN_T_NAME=%s" % name, "-DPTFNN_T_TASK=%d" % task, "-DPTFNN_T_I=%d" % I, "-DPTFNN_T_H=%d" % H,
                "-DPTFNN_T_O=%d" % O, "-DPTFNN_T_NT=%d" % nt, "-DPTFNN_T_MINB=%d" % minb,
-               os.path.join(csrc, "topo_inst.cu"), "-o", so + ".tmp"]
+               os.path.join(csrc, "topo_inst.cu"), "-o", tmp]
         if verbose:
             print("[ptfnn] compiling a specialisation for topology [%d,%d,%d]: %s" % (I, H, O, " ".join(cmd)), file=sys.stderr)
         try:
@@ -150,8 +155,10 @@ def ensure_topology(task, topology, verbose=False):
             raise PtfnnError(E_UNSUPPORTED, "topology [%d,%d,%d] is not built into libptfnn.so and nvcc is not available "
                                             "to compile it (%s)" % (I, H, O, e))
         if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
             raise PtfnnError(E_UNSUPPORTED, "compiling topology [%d,%d,%d] failed:\n%s" % (I, H, O, r.stderr[-2000:]))
-        os.replace(so + ".tmp", so)
+        os.replace(tmp, so)
     tl = C.CDLL(so)
     tl.ptfnn_topology_kernels.restype = C.c_void_p
     check(lib.ptfnn_register_kernels(C.c_void_p(tl.ptfnn_topology_kernels()), int(tl.ptfnn_topology_registry_version())))
@@ -257,12 +264,15 @@ def op_prior(task, topology, w, sigma_squared=25.0, nu_1=0.0, nu_2=0.0, tausq=1.
     return out.value
 
 
-def op_swap_sweep(lhood, u_row, device=0):
+def op_swap_sweep(lhood, u_row, device=0, swap_kind=SWAP_KIND_REFERENCE, temperatures=None):
+    """The coordinator's sequential sweep (R:741-748) over the lhood fields -> (src, swapped).
+    swap_kind: the reference's rule (R:674) or the drafts' temperature-aware one (needs ``temperatures``)."""
     lhood, u_row = f64(lhood), f32(u_row)
     n = lhood.shape[0]
     src = np.zeros(n, dtype=np.int32)
     sw = np.zeros(max(n - 1, 1), dtype=np.uint8)
-    check(load().ptfnn_op_swap_sweep(device, n, ptr(lhood), ptr(u_row), ptr(src), ptr(sw)))
+    t = None if temperatures is None else f64(temperatures)
+    check(load().ptfnn_op_swap_sweep_kind(device, n, ptr(lhood), ptr(u_row), int(swap_kind), ptr(t), ptr(src), ptr(sw)))
     return src, sw[:n - 1].astype(bool)
 
 

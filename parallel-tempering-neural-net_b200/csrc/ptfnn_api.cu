@@ -101,8 +101,13 @@ struct ptfnn_sampler {
     int P = 0, IP = 0;
     int swap_rule = 0;
     cudaStream_t stream = nullptr;
-    int num_sms = 0, regs_per_sm = 0, threads_per_sm = 0;
+    int num_sms = 0, regs_per_sm = 0, threads_per_sm = 0, clock_khz = 0;
     size_t smem_per_sm = 0;
+    bool device_failed = false;       // a device-side wait gave up: sticky until ptfnn_init_chains
+    unsigned int peer_round_base = 0; // flag domain of the peer hand-shake: grows with every ptfnn_init_chains
+    int verified_grid = 0;            // TMEM kernels: CTAs proven co-resident by the probe launch ...
+    size_t verified_smem = 0;         // ... for this much dynamic shared memory
+    DevBuf<unsigned int> probe_count;
     std::string err;
     void *pinned = nullptr;           // host staging buffer of get_traces (page-locked, grows on demand)
     size_t pinned_bytes = 0;
@@ -126,7 +131,7 @@ struct ptfnn_sampler {
     DevBuf<GridBarrier> barrier, spec_bar;            // spec_bar: one per temperature (speculative windows)
     DevBuf<unsigned int> spec_flag;
     // multi-GPU ladder through peer memory (ptfnn_peer_connect)
-    DevBuf<unsigned int> peer_flags;                  // [kMaxPeers] rounds published by each rank
+    DevBuf<unsigned int> peer_flags;                  // [kMaxPeers] rounds published by each rank, [kMaxPeers] = this rank's heartbeat
     int n_ranks = 1, rank = 0;
     void *peer_lhood[kMaxPeers] = {}, *peer_rows[kMaxPeers] = {}, *peer_flag_ptr[kMaxPeers] = {};
     bool peer_opened[kMaxPeers][3] = {};
@@ -151,7 +156,7 @@ struct ptfnn_sampler {
             if (peer_opened[q][2]) cudaIpcCloseMemHandle(peer_flag_ptr[q]);
             peer_opened[q][0] = peer_opened[q][1] = peer_opened[q][2] = false;
         }
-        peer_flags.release(); spec_bar.release(); spec_flag.release();
+        peer_flags.release(); spec_bar.release(); spec_flag.release(); probe_count.release();
         barrier.release(); swap_counters.release(); d_lx.release(); d_z.release(); d_zeta.release();
         d_u.release(); d_uswap.release(); d_src.release(); smsp_load.release(); swap_src.release(); d_swapped.release(); d_scratch.release(); d_summary.release();
     }
@@ -238,6 +243,8 @@ extern "C" void ptfnn_default_config(ptfnn_config *c) {
     c->sigma_squared = 25.0;  // R:273
     c->nu_1 = 0.0; c->nu_2 = 0.0;
     c->pt_fraction = 0.6;     // R:301
+    c->barrier_timeout_ms = 0;
+    c->swap_kind = PTFNN_SWAP_KIND_REFERENCE;
 }
 
 extern "C" const char *ptfnn_last_error(const ptfnn_sampler *s) { return s ? s->err.c_str() : g_last_error.c_str(); }
@@ -264,6 +271,9 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     if (cfg->n_replicas < 1 || cfg->samples < 2 || cfg->swap_interval < 1) return fail(nullptr, PTFNN_E_INVALID, "need n_replicas >= 1, samples >= 2, swap_interval >= 1");
     if (cfg->swap_rule != PTFNN_SWAP_RULE_AUTO && cfg->swap_rule != PTFNN_SWAP_RULE_AFTER_I && cfg->swap_rule != PTFNN_SWAP_RULE_BEFORE_I1)
         return fail(nullptr, PTFNN_E_INVALID, "bad swap_rule %d", cfg->swap_rule);
+    if (cfg->swap_kind != PTFNN_SWAP_KIND_REFERENCE && cfg->swap_kind != PTFNN_SWAP_KIND_RATIO_TEMPERATURE)
+        return fail(nullptr, PTFNN_E_INVALID, "bad swap_kind %d", cfg->swap_kind);
+    if (cfg->barrier_timeout_ms < 0) return fail(nullptr, PTFNN_E_INVALID, "barrier_timeout_ms %d < 0", cfg->barrier_timeout_ms);
     if (!(cfg->l_prob >= 0.0 && cfg->l_prob <= 1.0) || !std::isfinite(cfg->learn_rate) || !(cfg->step_w >= 0.0) || !(cfg->step_eta >= 0.0) ||
         !(cfg->sigma_squared > 0.0) || !std::isfinite(cfg->nu_1) || !std::isfinite(cfg->nu_2) || !(cfg->pt_fraction >= 0.0))
         return fail(nullptr, PTFNN_E_INVALID, "need 0 <= l_prob <= 1, finite learn_rate / nu, step_w >= 0, step_eta >= 0, sigma_squared > 0, pt_fraction >= 0");
@@ -272,6 +282,8 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
             return fail(nullptr, PTFNN_E_INVALID, "temperature %d = %g: the likelihood is divided by it (R:204), need a finite value > 0", k, temperatures[k]);
     const int Rg = cfg->n_replicas_global > 0 ? cfg->n_replicas_global : cfg->n_replicas;
     if (cfg->replica_offset < 0 || cfg->replica_offset + cfg->n_replicas > Rg) return fail(nullptr, PTFNN_E_INVALID, "replica_offset/n_replicas outside the ladder of %d", Rg);
+    if (cfg->swap_kind != PTFNN_SWAP_KIND_REFERENCE && Rg != cfg->n_replicas)
+        return fail(nullptr, PTFNN_E_UNSUPPORTED, "swap_kind %d (the drafts' temperature-aware rule) is a single-GPU option", cfg->swap_kind);
     const KernelSet *ks = find_kernels(cfg->task, cfg->n_in, cfg->n_hidden, cfg->n_out);
     if (!ks) return fail(nullptr, PTFNN_E_UNSUPPORTED, "no sm_100a specialisation for %s topology [%d,%d,%d]; built: %s", cfg->task == kTaskReg ? "regression" : "classification", cfg->n_in, cfg->n_hidden, cfg->n_out, supported_list().c_str());
     int rc = require_device(nullptr, cfg->device);
@@ -291,6 +303,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     s->num_sms = prop.multiProcessorCount;
     s->regs_per_sm = prop.regsPerMultiprocessor; s->threads_per_sm = prop.maxThreadsPerMultiProcessor;
     s->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    s->clock_khz = prop.clockRate;
     if (prop.major != 10) {                                                   // the kernels are sm_100a code only
         rc = fail(nullptr, PTFNN_E_UNSUPPORTED, "device %d (%s) is sm_%d%d: libptfnn is built for sm_100a (B200) only", cfg->device, prop.name, prop.major, prop.minor);
         delete s; return rc;
@@ -305,17 +318,18 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
         s->release_all(); delete s; cudaGetLastError(); return rc;                            \
     }
     ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(gd_cache, R * P); ALLOC(pgd_buf, cfg->n_hidden > 64 ? R * P : 1);
-    ALLOC(pos_w, R * S * P + kSumTracePadFloats); ALLOC(pub_rows, 2 * R * (P + 1)); ALLOC(pub_lhood, 2 * (size_t)Rg);
+    ALLOC(pos_w, R * S * P + kSumTracePadFloats); ALLOC(pub_rows, 2 * R * (P + kRowTail)); ALLOC(pub_lhood, 2 * (size_t)Rg);
     ALLOC(eta, R); ALLOC(tau, R); ALLOC(lik, R); ALLOC(prior, R); ALLOC(last4, R * 4); ALLOC(init_rmse, R * 2);
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
-    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, kMaxPeers); ALLOC(spec_bar, R); ALLOC(spec_flag, R * kMaxSpec);
+    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, 2 * kMaxPeers); ALLOC(probe_count, 2); ALLOC(spec_bar, R); ALLOC(spec_flag, R * kMaxSpec);
     ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(swap_src, R); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(s->barrier.p, 0, sizeof(GridBarrier));
-    cudaMemset(s->peer_flags.p, 0, kMaxPeers * sizeof(unsigned int));
+    cudaMemset(s->peer_flags.p, 0, 2 * kMaxPeers * sizeof(unsigned int));
+    cudaMemset(s->probe_count.p, 0, 2 * sizeof(unsigned int));
     cudaMemset(s->spec_bar.p, 0, R * sizeof(GridBarrier));
     cudaMemset(s->spec_flag.p, 0, R * kMaxSpec * sizeof(unsigned int));
     cudaMemset(s->smsp_load.p, 0, s->smsp_load.n * sizeof(int));
@@ -343,6 +357,10 @@ extern "C" int ptfnn_set_stream(ptfnn_sampler *s, void *cuda_stream) {
 }
 
 static int pack_a_tiles(ptfnn_sampler *s, const KernelSet *ks, const float *x, int rows, int IP, DevBuf<float> &tiles, cudaStream_t st);
+static int sync_and_check(ptfnn_sampler *s);
+static const char *kDeviceFailedMsg = "a device-side wait of an earlier launch timed out (swap-round grid barrier or peer flags: the "
+                                      "temperatures of one launch were not co-resident, or a peer rank never arrived); chain state and "
+                                      "traces were left untouched -- call ptfnn_init_chains to start over";
 
 // row-major float64 [rows, n_cols] -> padded float32 X [rows][IP] + y [pad4(rows)]
 static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP, std::vector<float> &x,
@@ -455,6 +473,11 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     CU_TRY(s, cudaFuncSetAttribute(s->ks->init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(s, cudaLaunchKernel(s->ks->init, dim3((unsigned)R), dim3(s->ks->NT), args, smem, s->stream));
     CU_TRY(s, cudaGetLastError());
+    // The peer arrival flags are written remotely and never reset: a re-initialised handle moves to a fresh
+    // range of the flag domain instead (same arithmetic on every rank), so that the counts of the previous
+    // run are not taken for "already published".
+    if (s->have_state) s->peer_round_base += (unsigned int)h_total_rounds(s) + 2u;
+    s->device_failed = false;
     s->step = 0; s->rounds_done = 0; s->swap_pending = false; s->pending_final = false;
     s->host_num_swap = 0; s->host_total_prop = 0; s->host_swap_log.clear(); s->host_swap_log_round.clear();
     s->have_state = true;
@@ -486,7 +509,7 @@ extern "C" int ptfnn_get_state(ptfnn_sampler *s, double *w, double *eta, double 
     if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
     CU_TRY(s, cudaSetDevice(s->cfg.device));
     const size_t R = s->cfg.n_replicas, P = s->P;
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    { const int rc = sync_and_check(s); if (rc) return rc; }
     if (w) {
         std::vector<float> tmp(R * P);
         CU_TRY(s, cudaMemcpy(tmp.data(), s->w.p, R * P * 4, cudaMemcpyDeviceToHost));
@@ -516,6 +539,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     if (steps_done) *steps_done = 0;
     if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
     if (s->swap_pending) return fail(s, PTFNN_E_STATE, "a swap round is pending: finish it with ptfnn_swap_plan/apply");
+    if (s->device_failed) return fail(s, PTFNN_E_CUDA, "%s", kDeviceFailedMsg);
     CU_TRY(s, cudaSetDevice(s->cfg.device));
     const ptfnn_config &c = s->cfg;
     const int R = c.n_replicas, Rg = c.n_replicas_global, S = c.samples, P = s->P;
@@ -566,6 +590,11 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     }
     p.swap_src = s->swap_src.p;
     p.P = P;
+    p.peer_round_base = s->peer_round_base;
+    p.heartbeat = s->peer_flags.p + kMaxPeers;
+    p.wait_limit = (long long)(c.barrier_timeout_ms > 0 ? c.barrier_timeout_ms : 20000) * (long long)std::max(s->clock_khz, 1);
+    p.probe = 0; p.probe_count = s->probe_count.p;
+    p.swap_kind = c.swap_kind; p.temperature_global = s->temperature.p;   // swap_kind != 0 is single-GPU: the local ladder is the ladder
 
     if (d) {
         if (d->n < n) return fail(s, PTFNN_E_INVALID, "draws cover %d steps, need %d", d->n, n);
@@ -590,7 +619,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
 
     const size_t stage_bytes = ((size_t)s->n_train * s->IP + ((s->n_train + 3) & ~3) + (size_t)s->n_test * s->IP + ((s->n_test + 3) & ~3)) * 4;
     p.staged = stage_bytes <= kStageLimitBytes ? 1 : 0;
-    const int NT = c.threads_per_block > 0 ? s->ks->NT : s->ks->NT;
+    const int NT = s->ks->NT;
     const int team_floats = c.n_hidden > 64 ? team_smem_floats(c.n_hidden, c.n_out) : 0;   // mirrors UseSgdTeam<H>
     const int lik_floats = c.n_hidden * ((c.n_in + 1 + c.n_out + 3) & ~3);   // mirrors LikLayout<I, O>::LW
     const ChainSmem L = chain_smem_layout(P, s->IP, NT, external ? 1 : Rg, p.staged != 0, s->n_train, s->n_test, team_floats, lik_floats, team_floats == 0,
@@ -605,25 +634,48 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     if (uses_tmem) {
         // The occupancy calculator answers 1 for every kernel that executes tcgen05.alloc, although the
         // hardware co-schedules CTAs as long as their TMEM columns fit (tools/occ_probe.cu: two CTAs of
-        // 256 columns per SM).  Count the resources ourselves; such kernels are launched without the
-        // cooperative-launch check (the grid barrier has a time-out instead of a co-residency proof).
+        // 256 columns per SM), so such kernels cannot be launched cooperatively.  The estimate below
+        // (registers / shared memory / threads / TMEM columns) is only the starting point: co-residency is
+        // MEASURED by a probe launch of the real kernel with the real launch configuration, and the grid is
+        // clamped to the number of CTAs that were resident together (other contexts on the GPU, driver-
+        // reserved shared memory and allocation granularities are then accounted for by construction).
         cudaFuncAttributes fa;
         CU_TRY(s, cudaFuncGetAttributes(&fa, s->ks->chain));
         const int regs = ((fa.numRegs + 7) / 8) * 8;
         const int by_regs = s->regs_per_sm / std::max(1, regs * NT);
         const int by_smem = (int)(s->smem_per_sm / (L.total + fa.sharedSizeBytes + 1024));
         const int by_thr = s->threads_per_sm / NT;
-        const int by_tmem = 512 / c.n_hidden;
+        const int by_tmem = 512 / std::max(32, s->ks->tmem_cols);
         per_sm = std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_thr, by_tmem)));
+        const int want = std::min(R, per_sm * s->num_sms);
+        if (s->verified_grid < 1 || s->verified_smem != L.total || s->verified_grid > want) {
+            int try_grid = want, proven = 0;
+            for (int attempt = 0; attempt < 4 && try_grid >= 1; ++attempt) {
+                CU_TRY(s, cudaMemsetAsync(s->probe_count.p, 0, 2 * sizeof(unsigned int), s->stream));
+                ChainParams pp = p;
+                pp.probe = 1;
+                void *pargs[] = {&pp};
+                CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(try_grid), dim3(NT), pargs, L.total, s->stream));
+                unsigned int seen[2] = {0, 0};
+                CU_TRY(s, cudaMemcpyAsync(seen, s->probe_count.p, sizeof seen, cudaMemcpyDeviceToHost, s->stream));
+                CU_TRY(s, cudaStreamSynchronize(s->stream));
+                if ((int)seen[1] >= try_grid) { proven = try_grid; break; }
+                // fewer CTAs than asked were resident together: whole CTAs per SM, one less than the estimate
+                try_grid = std::min((int)seen[1], (try_grid > s->num_sms ? (try_grid - 1) / s->num_sms : 0) * s->num_sms);
+                if (try_grid < 1) try_grid = std::min((int)seen[1], s->num_sms);
+            }
+            if (proven < 1) return fail(s, PTFNN_E_CUDA, "the chain kernel's CTAs are not co-resident on device %d even at one per SM (another context holding the GPU?)", c.device);
+            s->verified_grid = proven; s->verified_smem = L.total;
+        }
+        per_sm = std::max(1, s->verified_grid / s->num_sms);
     }
-    int grid = std::min(R, per_sm * s->num_sms);
+    int grid = uses_tmem ? std::min(R, s->verified_grid) : std::min(R, per_sm * s->num_sms);
     // Small ladders leave most of the GPU idle (10 temperatures = 10 of 148 SMs): K CTAs per temperature
     // evaluate K consecutive steps speculatively (chain_kernel, "speculative windows").  cfg.speculation:
     // 0 = automatic, 1 = off, K > 1 = that depth (clamped to what is co-resident).
     int spec = 1;
     if (s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms) {
         int want = c.speculation;
-        if (const char *e = getenv("PTFNN_SPEC")) want = atoi(e);
         // automatic: one CTA per SM while the ladder is that small -- for Langevin runs only (a random-walk step is
         // shorter than the two group barriers of a window: measured 7 us per step against 4 us sequentially)
         // (Deeper automatic windows -- every co-resident CTA slot -- were measured on the 4-64-1 ladder at 512 / 256 /
@@ -643,12 +695,6 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
         p.spec_k = spec;
         if (spec > 1) grid = R * spec; else chain_fn = s->ks->chain;
     }
-    if (getenv("PTFNN_DEBUG")) {
-        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, s->ks->chain);
-        int o2 = 0, o3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, s->ks->chain, NT, 90000); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, s->ks->chain, NT, 0);
-        fprintf(stderr, "[ptfnn] regs %d static smem %zu local %zu maxdyn %d; occ@90000=%d occ@0=%d\n", fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, o2, o3);
-    }
-    if (getenv("PTFNN_DEBUG")) fprintf(stderr, "[ptfnn] chain launch: smem %zu B, %d CTAs/SM, grid %d, threads %d\n", L.total, per_sm, grid, NT);
     // many temperatures per SM: keep the serial warps' sub-partitions quiet (see chain_kernel)
     void *args[] = {&p};
     if (uses_tmem) CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
@@ -678,12 +724,13 @@ extern "C" int ptfnn_replay(ptfnn_sampler *s, const ptfnn_draws *d, int32_t *ste
 // stream synchronisation + the device-side failure flag of the grid barrier
 static int sync_and_check(ptfnn_sampler *s) {
     CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->device_failed) return fail(s, PTFNN_E_CUDA, "%s", kDeviceFailedMsg);
     GridBarrier b;
     CU_TRY(s, cudaMemcpy(&b, s->barrier.p, sizeof b, cudaMemcpyDeviceToHost));
     std::vector<GridBarrier> sb(s->cfg.n_replicas);
     CU_TRY(s, cudaMemcpy(sb.data(), s->spec_bar.p, sb.size() * sizeof(GridBarrier), cudaMemcpyDeviceToHost));
     for (const GridBarrier &g : sb) b.failed |= g.failed;
-    if (b.failed) return fail(s, PTFNN_E_CUDA, "swap-round grid barrier timed out: the temperatures of one launch were not co-resident on the device");
+    if (b.failed) { s->device_failed = true; return fail(s, PTFNN_E_CUDA, "%s", kDeviceFailedMsg); }
     return PTFNN_OK;
 }
 
@@ -809,7 +856,7 @@ extern "C" int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, 
 extern "C" int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total, uint8_t *swapped, int32_t max_rounds) {
     if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
     CU_TRY(s, cudaSetDevice(s->cfg.device));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    { const int rc = sync_and_check(s); if (rc) return rc; }
     long long c[2] = {0, 0};
     CU_TRY(s, cudaMemcpy(c, s->swap_counters.p, 16, cudaMemcpyDeviceToHost));
     if (num_swap) *num_swap = c[0] + s->host_num_swap;
@@ -903,9 +950,10 @@ extern "C" int ptfnn_trace_summary(ptfnn_sampler *s, int32_t first, int32_t coun
 // Posterior-predictive moments from the device traces: forward pass of every pooled posterior
 // sample (one CTA per recorded weight vector, read in place from pos_w), then the moments planes of
 // trace_summary_kernel over the [samples, rows] prediction matrix.
-extern "C" int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count,
-                                        double *mean, double *stdev, double *rmse_of_mean) {
-    if (!s || !mean || !stdev) return fail(s, PTFNN_E_INVALID, "null argument");
+// The [samples, rows] prediction matrix of rows [first, first+count) of every local replica's pos_w: one launch of
+// the forward kernel per replica (its slice of pos_w is a batch of `count` weight vectors at stride P).
+static int predictive_matrix(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count, DevBuf<float> &d_fx, DevBuf<double> &d_sums,
+                             long long *n_out, int *N_out) {
     if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
     if (s->cfg.task != PTFNN_TASK_REGRESSION) return fail(s, PTFNN_E_UNSUPPORTED, "predictive moments are defined for regression outputs (classification fx is a class index, C:148)");
     if (which != 0 && which != 1) return fail(s, PTFNN_E_INVALID, "which = %d (0 train, 1 test)", which);
@@ -917,12 +965,9 @@ extern "C" int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t
     const int N = which == 0 ? s->n_train : s->n_test;
     const long long n = (long long)R * count;
     if (n > 0x7fffffffLL || (double)n * N * 4.0 > 16e9) return fail(s, PTFNN_E_UNSUPPORTED, "%lld samples x %d rows of predictions exceed the 16 GB staging limit: summarise a shorter slice", n, N);
-    DevBuf<float> d_fx;
-    DevBuf<double> d_sums, d_out;
     cudaError_t e;
     if ((e = d_fx.ensure((size_t)n * N + kSumTracePadFloats)) != cudaSuccess || (e = d_sums.ensure((size_t)3 * n)) != cudaSuccess)
         return fail(s, PTFNN_E_NOMEM, "cudaMalloc of the prediction matrix (%lld x %d): %s", n, N, cudaGetErrorString(e));
-    // ---- forward pass, one launch per replica (its slice of pos_w is a batch of `count` vectors at stride P)
     const KernelSet *ks = s->ks;
     const size_t smem_fwd = (((size_t)P * 4 + 15) & ~(size_t)15) + 8 * (ks->NT / 32) * 8 + 64;
     CU_TRY(s, cudaFuncSetAttribute(ks->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
@@ -934,6 +979,49 @@ extern "C" int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t
         void *args[] = {&wp, &v, &fxp, &pp, &sp};
         CU_TRY(s, cudaLaunchKernel(ks->fwd, dim3(count), dim3(ks->NT), args, smem_fwd, s->stream));
     }
+    *n_out = n; *N_out = N;
+    return PTFNN_OK;
+}
+
+// Percentile bands of the posterior-predictive distribution: np.percentile(fx_all, [q_lo, q_hi], axis=0)
+// over the prediction matrix, on the device (quantile_bands_kernel).
+extern "C" int ptfnn_predictive_bands(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count, double q_lo, double q_hi,
+                                      double *lo, double *hi) {
+    if (!s || !lo || !hi) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!(q_lo >= 0.0 && q_lo <= q_hi && q_hi <= 100.0)) return fail(s, PTFNN_E_INVALID, "need 0 <= q_lo <= q_hi <= 100 (percent), got %g, %g", q_lo, q_hi);
+    DevBuf<float> d_fx;
+    DevBuf<double> d_sums, d_out;
+    long long n = 0;
+    int N = 0;
+    int rc = predictive_matrix(s, which, first, count, d_fx, d_sums, &n, &N);
+    if (rc) return rc;
+    CU_TRY(s, d_out.ensure((size_t)2 * N));
+    auto split = [&](double q, long long *k, double *f) {          // np.percentile, method 'linear': virtual index q/100 (n-1)
+        const double idx = q / 100.0 * (double)(n - 1);
+        long long kk = (long long)std::floor(idx);
+        if (kk > n - 1) kk = n - 1;
+        *k = kk; *f = kk >= n - 1 ? 0.0 : idx - (double)kk;
+    };
+    long long k0, k1;
+    double f0, f1;
+    split(q_lo, &k0, &f0); split(q_hi, &k1, &f1);
+    quantile_bands_kernel<<<(N + kQCols - 1) / kQCols, kQThreads, 0, s->stream>>>(d_fx.p, n, N, k0, f0, k1, f1, d_out.p, d_out.p + N);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaMemcpyAsync(lo, d_out.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(hi, d_out.p + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_predictive_summary(ptfnn_sampler *s, int32_t which, int32_t first, int32_t count,
+                                        double *mean, double *stdev, double *rmse_of_mean) {
+    if (!s || !mean || !stdev) return fail(s, PTFNN_E_INVALID, "null argument");
+    DevBuf<float> d_fx;
+    DevBuf<double> d_sums, d_out;
+    long long n = 0;
+    int N = 0;
+    int rc = predictive_matrix(s, which, first, count, d_fx, d_sums, &n, &N);
+    if (rc) return rc;
     // ---- moments over the samples for every data row
     const int cols = N <= kSumThreads ? 1 : N <= 2 * kSumThreads ? 2 : N <= 4 * kSumThreads ? 4 : 8;
     const int ctiles = (N + kSumThreads * cols - 1) / (kSumThreads * cols);
@@ -990,6 +1078,7 @@ extern "C" int ptfnn_swap_export(ptfnn_sampler *s, void *lhood_local_dev, void *
     if (!s || !lhood_local_dev) return fail(s, PTFNN_E_INVALID, "null argument");
     if (!s->swap_pending) return fail(s, PTFNN_E_STATE, "no swap round pending");
     CU_TRY(s, cudaSetDevice(s->cfg.device));
+    if (s->device_failed) return fail(s, PTFNN_E_CUDA, "%s", kDeviceFailedMsg);
     const size_t R = s->cfg.n_replicas, P = s->P;
     const int parity = s->rounds_done & 1;
     if (s->pending_final) {
@@ -999,20 +1088,21 @@ extern "C" int ptfnn_swap_export(ptfnn_sampler *s, void *lhood_local_dev, void *
         CU_TRY(s, cudaMemcpyAsync(lhood_local_dev, s->pub_lhood.p + (size_t)parity * s->cfg.n_replicas_global + s->cfg.replica_offset,
                                   R * 8, cudaMemcpyDeviceToDevice, s->stream));
         if (rows_local_dev)
-            CU_TRY(s, cudaMemcpyAsync(rows_local_dev, s->pub_rows.p + (size_t)parity * R * (P + 1), R * (P + 1) * 4, cudaMemcpyDeviceToDevice, s->stream));
+            CU_TRY(s, cudaMemcpyAsync(rows_local_dev, s->pub_rows.p + (size_t)parity * R * (P + kRowTail), R * (P + kRowTail) * 4, cudaMemcpyDeviceToDevice, s->stream));
     }
     return PTFNN_OK;
 }
 
 static int run_sweep(ptfnn_sampler *s, cudaStream_t st, int n, const double *lhood_dev, const float *u_host, int *d_src,
-                     uint8_t *d_swapped, DevBuf<float> &d_u, int32_t *src, uint8_t *swapped, int *ns_out) {
+                     uint8_t *d_swapped, DevBuf<float> &d_u, int32_t *src, uint8_t *swapped, int *ns_out,
+                     int kind = PTFNN_SWAP_KIND_REFERENCE, const double *temperature_dev = nullptr) {
     CU_TRY(s, d_u.ensure(std::max(n - 1, 1)));
     if (n > 1) CU_TRY(s, cudaMemcpyAsync(d_u.p, u_host, (size_t)(n - 1) * 4, cudaMemcpyHostToDevice, st));
     DevBuf<int> d_ns;
     CU_TRY(s, d_ns.ensure(1));
     const size_t smem = (size_t)n * 12;
     if (smem > 48 * 1024) CU_TRY(s, cudaFuncSetAttribute((const void *)op_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    op_sweep_kernel<<<1, 128, smem, st>>>(n, lhood_dev, d_u.p, d_src, d_swapped, d_ns.p);
+    op_sweep_kernel<<<1, 128, smem, st>>>(n, lhood_dev, d_u.p, d_src, d_swapped, d_ns.p, kind, temperature_dev);
     CU_TRY(s, cudaGetLastError());
     CU_TRY(s, cudaMemcpyAsync(src, d_src, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (n > 1 && swapped) CU_TRY(s, cudaMemcpyAsync(swapped, d_swapped, (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
@@ -1341,14 +1431,25 @@ extern "C" int ptfnn_op_forward_pass(int32_t device, int32_t I, int32_t H, int32
     return PTFNN_OK;
 }
 
-extern "C" int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t *src, uint8_t *swapped) {
+extern "C" int ptfnn_op_swap_sweep_kind(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t swap_kind,
+                                        const double *temperature, int32_t *src, uint8_t *swapped) {
     if (n < 1 || !lhood || !src || (n > 1 && !u_row)) return fail(nullptr, PTFNN_E_INVALID, "bad argument");
+    if (swap_kind != PTFNN_SWAP_KIND_REFERENCE && swap_kind != PTFNN_SWAP_KIND_RATIO_TEMPERATURE) return fail(nullptr, PTFNN_E_INVALID, "bad swap_kind %d", swap_kind);
+    if (swap_kind != PTFNN_SWAP_KIND_REFERENCE && !temperature) return fail(nullptr, PTFNN_E_INVALID, "swap_kind %d needs the temperatures", swap_kind);
     int rc = require_device(nullptr, device);
     if (rc) return rc;
-    DevBuf<double> dl; DevBuf<int> ds; DevBuf<uint8_t> dsw; DevBuf<float> du;
+    DevBuf<double> dl, dt; DevBuf<int> ds; DevBuf<uint8_t> dsw; DevBuf<float> du;
     CU_TRY(nullptr, dl.ensure(n)); CU_TRY(nullptr, ds.ensure(n)); CU_TRY(nullptr, dsw.ensure(std::max(n - 1, 1)));
     CU_TRY(nullptr, cudaMemcpy(dl.p, lhood, (size_t)n * 8, cudaMemcpyHostToDevice));
-    rc = run_sweep(nullptr, 0, n, dl.p, u_row, ds.p, dsw.p, du, src, swapped, nullptr);
-    dl.release(); ds.release(); dsw.release(); du.release();
+    if (temperature) {
+        CU_TRY(nullptr, dt.ensure(n));
+        CU_TRY(nullptr, cudaMemcpy(dt.p, temperature, (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    rc = run_sweep(nullptr, 0, n, dl.p, u_row, ds.p, dsw.p, du, src, swapped, nullptr, swap_kind, temperature ? dt.p : nullptr);
+    dl.release(); dt.release(); ds.release(); dsw.release(); du.release();
     return rc;
+}
+
+extern "C" int ptfnn_op_swap_sweep(int32_t device, int32_t n, const double *lhood, const float *u_row, int32_t *src, uint8_t *swapped) {
+    return ptfnn_op_swap_sweep_kind(device, n, lhood, u_row, PTFNN_SWAP_KIND_REFERENCE, nullptr, src, swapped);
 }

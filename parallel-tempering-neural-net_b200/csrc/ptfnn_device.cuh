@@ -257,15 +257,48 @@ struct GridBarrier {
     unsigned int failed;      // set when a CTA gave up waiting (the grid was not co-resident): reported by the host
     unsigned int pad;
 };
-constexpr long long kBarrierTimeoutCycles = 1ll << 35;   // ~17 s: far above any legitimate skew between CTAs
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
-__device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblocks, bool spin = false) {
+// A wait that cannot hang the device.  The limit counts time WITHOUT PROGRESS, not waiting time: every CTA
+// bumps a heartbeat word after each MCMC step, and a waiter restarts its clock whenever the heartbeat it
+// watches has moved (legitimate skew -- a CTA that owns one more replica segment than its neighbours, a peer
+// rank that started late -- is progress, a grid that is not co-resident is not).  `limit` comes from the
+// configuration (ptfnn_config::barrier_timeout_ms).
+struct WaitClock {
+    long long t0, limit;
+    const unsigned int *beat;
+    unsigned int last;
+    __device__ __forceinline__ WaitClock(const unsigned int *heartbeat, long long limit_cycles) {
+        t0 = clock64(); limit = limit_cycles; beat = heartbeat;
+        last = heartbeat ? ld_relaxed_u32(heartbeat) : 0u;
+    }
+    // true: give up
+    __device__ __forceinline__ bool expired() {
+        const long long now = clock64();
+        if (now - t0 <= limit) return false;
+        if (beat) {
+            const unsigned int b = ld_relaxed_u32(beat);
+            if (b != last) { last = b; t0 = now; return false; }
+        }
+        return true;
+    }
+};
+
+// Returns false -- in EVERY thread of the CTA -- when this barrier (or an earlier one) timed out: the caller
+// must leave the kernel without touching chain state, traces or the swap window.
+__device__ __forceinline__ bool grid_barrier(GridBarrier *b, unsigned int nblocks, long long limit_cycles,
+                                             const unsigned int *heartbeat, bool spin = false) {
+    int bad = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int gen = ld_acquire_u32(&b->generation);
@@ -275,15 +308,16 @@ __device__ __forceinline__ void grid_barrier(GridBarrier *b, unsigned int nblock
             __threadfence();
             atomicAdd(&b->generation, 1u);
         } else {
-            const long long t0 = clock64();
+            WaitClock wc(heartbeat, limit_cycles);
             while (ld_acquire_u32(&b->generation) == gen) {
                 if (!spin) __nanosleep(32);          // small groups (speculative windows) poll without backing off
-                if (clock64() - t0 > kBarrierTimeoutCycles) { atomicExch(&b->failed, 1u); break; }   // never hang the device
+                if (ld_relaxed_u32(&b->failed) || wc.expired()) { atomicExch(&b->failed, 1u); break; }   // never hang the device
             }
         }
         __threadfence();
+        bad = (int)ld_relaxed_u32(&b->failed);
     }
-    __syncthreads();
+    return __syncthreads_or(bad) == 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -303,6 +337,20 @@ __device__ __forceinline__ float ld_sys_f32(const float *p) {      // never serv
     asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int ld_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// eta crosses the swap window as the bit pattern of the float64 (the reference moves the float64, R:430-437)
+__device__ __forceinline__ void put_f64_words(float *two_words, double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    unsigned int *t = reinterpret_cast<unsigned int *>(two_words);
+    t[0] = (unsigned int)b; t[1] = (unsigned int)(b >> 32);
+}
+__device__ __forceinline__ double f64_from_words(unsigned int lo, unsigned int hi) {
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
 __device__ __forceinline__ double ld_sys_f64(const double *p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -320,11 +368,23 @@ __device__ __forceinline__ double swap_probability(double l1, double l2) {
     return p < 1.0 ? p : 1.0;  // NaN -> 1, like Python's min(1, nan)
 }
 
-template <class UFn>
-__device__ __forceinline__ int swap_sweep_serial(int n, double *lh, int *src, uint8_t *swapped_out, UFn u_of) {
+// Opt-in swap rule of the reference's drafts (Misc/ldpt_fnn_multi_fixed.py:520):
+//     swap_proposal = (lhood1 / (1 if lhood2 == 0 else lhood2)) * (1/T1 * 1/T2),   swap when u < swap_proposal
+// with T1, T2 the temperature fields that travel with the two vectors.  Not used by any published result
+// of the reference and excluded from replay parity; kSwapKindReference is R:674.
+constexpr int kSwapKindReference = 0;
+constexpr int kSwapKindRatioTemp = 1;
+__device__ __forceinline__ double swap_probability_ratio(double l1, double l2, double t1, double t2) {
+    return (l1 / (l2 == 0.0 ? 1.0 : l2)) * (1.0 / t1 * 1.0 / t2);
+}
+
+template <class UFn, class TFn>
+__device__ __forceinline__ int swap_sweep_serial(int n, double *lh, int *src, uint8_t *swapped_out, UFn u_of, int kind, TFn t_of) {
     int ns = 0;
     for (int k = 0; k + 1 < n; ++k) {
-        const bool s = (double)u_of(k) < swap_probability(lh[k], lh[k + 1]);
+        const double pr = kind == kSwapKindReference ? swap_probability(lh[k], lh[k + 1])
+                                                     : swap_probability_ratio(lh[k], lh[k + 1], t_of(src[k]), t_of(src[k + 1]));
+        const bool s = (double)u_of(k) < pr;
         if (s) {
             const double t = lh[k]; lh[k] = lh[k + 1]; lh[k + 1] = t;
             const int ti = src[k]; src[k] = src[k + 1]; src[k + 1] = ti;
@@ -353,12 +413,14 @@ __device__ __forceinline__ bool swap_decision(double cur_l, double nxt, float u,
     return (double)u < swap_probability(cur_l, nxt);
 }
 
-template <class LFn, class UFn, class LUFn, class Emit, class Decided>
+template <class LFn, class UFn, class LUFn, class Emit, class Decided, class TFn>
 __device__ __forceinline__ void swap_sweep_stream(int k_begin, int k_end, int n, double &cur_l, int &cur_src, int &ns,
-                                                  LFn lh_of, UFn u_of, LUFn lu_of, Emit emit, Decided decided) {
+                                                  LFn lh_of, UFn u_of, LUFn lu_of, Emit emit, Decided decided,
+                                                  int kind, TFn t_of) {
     for (int k = k_begin; k < k_end && k + 1 < n; ++k) {
         const double nxt = lh_of(k + 1);
-        const bool s = swap_decision(cur_l, nxt, u_of(k), lu_of(k));
+        const bool s = kind == kSwapKindReference ? swap_decision(cur_l, nxt, u_of(k), lu_of(k))
+                                                  : (double)u_of(k) < swap_probability_ratio(cur_l, nxt, t_of(cur_src), t_of(k + 1));
         if (s) { emit(k, k + 1); ++ns; }
         else { emit(k, cur_src); cur_l = nxt; cur_src = k + 1; }
         decided(k, s);

@@ -1137,7 +1137,7 @@ struct ChainParams {
     // ---- replay draws
     const float *lx, *z, *z_eta, *u, *u_swap;
     // ---- swap round
-    float *pub_rows;               // [2][R][P+1]   (w, eta) published at the hand-shake (R:430-431)
+    float *pub_rows;               // [2][R][P+2]   (w, eta) published at the hand-shake (R:430-431); eta = the fp64 bit pattern in two words
     double *pub_lhood;             // [2][Rg]       lhood field (R:430 / C:439)
     GridBarrier *barrier;
     long long *swap_counters;      // {num_swap, total_swap_proposals}  (R:680-688)
@@ -1154,10 +1154,24 @@ struct ChainParams {
     //      are mapped into this process (CUDA IPC); entry q of the tables points at rank q's buffer
     int n_ranks, rank;
     double *peer_lhood[kMaxPeers];         // rank q's pub_lhood  [2][Rg]
-    const float *peer_rows[kMaxPeers];     // rank q's pub_rows   [2][R][P+1]
-    unsigned int *peer_flags[kMaxPeers];   // rank q's arrival flags [kMaxPeers]; flags[j] = rounds published by rank j
+    const float *peer_rows[kMaxPeers];     // rank q's pub_rows   [2][R][P+2]
+    unsigned int *peer_flags[kMaxPeers];   // rank q's arrival flags [kMaxPeers] + heartbeat; flags[j] = peer_round_base + rounds published by rank j
+    unsigned int peer_round_base;  // grows with every ptfnn_init_chains: the flag domain is never reset (a re-initialised
+                                   // handle must not see the previous run's counts as "already published")
     int *smsp_load;                // [num_SMs] ticket counter used to spread serial (SGD) warps over the SM sub-partitions
+    // ---- liveness: every wait has a limit on time WITHOUT progress (WaitClock); a failed wait ends the kernel
+    long long wait_limit;          // cycles
+    unsigned int *heartbeat;       // this rank's progress word (= peer_flags[rank] + kMaxPeers): bumped after every MCMC step
+    // ---- co-residency probe (kernels that allocate TMEM are launched without the cooperative-launch proof):
+    //      probe = 1: every CTA sets itself up as for a real launch, arrives on probe_count[0], waits (bounded) for
+    //      the whole grid and leaves; the host reads how many arrived TOGETHER (probe_count[1] = max seen)
+    int probe;
+    unsigned int *probe_count;
+    // ---- opt-in swap rule of the reference's drafts; 0 = the reference's rule (R:674)
+    int swap_kind;
+    const double *temperature_global;   // [Rg] (swap_kind != 0 only)
 };
+constexpr int kRowTail = 2;        // words behind the P weights of a published row: eta as raw fp64 bits (R:430 moves the float64)
 
 __device__ __forceinline__ bool swap_due(int rule, int s, int i) {
     return rule == 0 ? (i % s == 0 && i != 0) : ((i + 1) % s == 0);                // R:427 | C:438
@@ -1260,7 +1274,8 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
                 base, k_end, p.Rg, cur_l, cur_src, ns, [&](int k) { return s_chunk[k - base]; },
                 [&](int k) { return s_u[k - base]; }, [&](int k) { return s_lu[k - base]; },
                 [&](int slot, int origin) { if (mine(slot)) p.swap_src[slot - p.replica_offset] = origin; },
-                [&](int k, bool sw) { if (lg_out) lg_out[k] = (uint8_t)sw; });
+                [&](int k, bool sw) { if (lg_out) lg_out[k] = (uint8_t)sw; },
+                p.swap_kind, [&](int slot) { return p.temperature_global[slot]; });
         }
     }
     if (tid == 0) {
@@ -1275,13 +1290,21 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
             const int q = p.n_ranks > 1 ? gsrc / p.R : 0;     // equal contiguous blocks: owner rank of that slot
             const int lsrc = gsrc - q * p.R - (p.n_ranks > 1 ? 0 : p.replica_offset);
             if (p.n_ranks > 1 && q != p.rank) {               // the row lives on another GPU: pull it over NVLink
-                const float *row = p.peer_rows[q] + ((size_t)parity * p.R + lsrc) * (P + 1);
+                const float *row = p.peer_rows[q] + ((size_t)parity * p.R + lsrc) * (P + kRowTail);
                 for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = ld_sys_f32(&row[j]);
-                if (tid == 0) { p.eta[r] = (double)ld_sys_f32(&row[P]); p.gd_valid[r] = 0; }
+                if (tid == 0) {
+                    const unsigned int *t = reinterpret_cast<const unsigned int *>(row + P);
+                    p.eta[r] = f64_from_words(ld_sys_u32(&t[0]), ld_sys_u32(&t[1]));
+                    p.gd_valid[r] = 0;
+                }
             } else {
-                const float *row = p.pub_rows + ((size_t)parity * p.R + lsrc) * (P + 1);
+                const float *row = p.pub_rows + ((size_t)parity * p.R + lsrc) * (P + kRowTail);
                 for (int j = tid; j < P; j += NT) p.w[(size_t)r * P + j] = __ldcg(&row[j]);
-                if (tid == 0) { p.eta[r] = (double)__ldcg(&row[P]); p.gd_valid[r] = 0; }
+                if (tid == 0) {
+                    const unsigned int *t = reinterpret_cast<const unsigned int *>(row + P);
+                    p.eta[r] = f64_from_words(__ldcg(&t[0]), __ldcg(&t[1]));
+                    p.gd_valid[r] = 0;
+                }
             }
         }
     }
@@ -1294,9 +1317,11 @@ __device__ __forceinline__ void chain_sweep(const ChainParams &p, int round, int
 // temperature over NVLink), raises its flag on every peer, and every CTA waits until the flags of all
 // ranks have reached this round.  The sweep then reads only local memory; (w, eta) rows are PULLED from
 // the owner's pub_rows by the CTA that needs them (in expectation the rows next to the rank boundaries).
+// Returns false (in every thread) when a peer never published: the caller leaves the kernel.
 template <int NT>
-__device__ __forceinline__ void peer_exchange_lhood(const ChainParams &p, int round, int parity, GridBarrier *bar) {
+__device__ __forceinline__ bool peer_exchange_lhood(const ChainParams &p, int round, int parity, GridBarrier *bar) {
     const int tid = threadIdx.x;
+    const unsigned int want = p.peer_round_base + (unsigned int)(round + 1);
     if (blockIdx.x == 0) {
         const double *mine = p.pub_lhood + (size_t)parity * p.Rg + p.replica_offset;
         for (int q = 0; q < p.n_ranks; ++q) {
@@ -1306,20 +1331,30 @@ __device__ __forceinline__ void peer_exchange_lhood(const ChainParams &p, int ro
         }
         __threadfence_system();
         __syncthreads();
-        if (tid < p.n_ranks) st_release_sys_u32(&p.peer_flags[tid][p.rank], (unsigned int)(round + 1));
+        if (tid < p.n_ranks) st_release_sys_u32(&p.peer_flags[tid][p.rank], want);
     }
+    int bad = 0;
     if (tid == 0) {
         const unsigned int *flags = p.peer_flags[p.rank];
-        const long long t0 = clock64();
-        for (int q = 0; q < p.n_ranks; ++q) {
-            while ((int)(ld_acquire_sys_u32(&flags[q]) - (unsigned int)(round + 1)) < 0) {
+        for (int q = 0; q < p.n_ranks && !bad; ++q) {
+            // progress of rank q = its heartbeat word, read over NVLink only when the limit has run out
+            long long t0 = clock64();
+            unsigned int last = 0u;
+            bool have_last = false;
+            while ((int)(ld_acquire_sys_u32(&flags[q]) - want) < 0) {
                 __nanosleep(64);
-                if (clock64() - t0 > kBarrierTimeoutCycles) { atomicExch(&bar->failed, 1u); break; }
+                if (ld_relaxed_u32(&bar->failed)) { bad = 1; break; }
+                const long long now = clock64();
+                if (now - t0 > p.wait_limit) {
+                    const unsigned int beat = ld_sys_u32(&p.peer_flags[q][kMaxPeers]);
+                    if (!have_last || beat != last) { last = beat; have_last = true; t0 = now; continue; }
+                    atomicExch(&bar->failed, 1u); bad = 1; break;
+                }
             }
         }
         __threadfence_system();
     }
-    __syncthreads();
+    return __syncthreads_or(bad) == 0;
 }
 
 // SPEC_T: the instantiation with speculative windows (small ladders); the plain one carries none of their
@@ -1385,6 +1420,29 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     stream.parity0 = stream.parity1 = 0u;
     tc::State tcst;
     if constexpr (TC) tc::setup<I, H, O>(s_tc, tcst);            // TMEM: 256 columns per CTA, two CTAs per SM
+    // ---- liveness.  A launch on a handle whose earlier wait failed does nothing; the co-residency probe
+    //      (TMEM kernels are launched without the cooperative-launch proof) counts the CTAs that are resident
+    //      TOGETHER with everything a real launch holds (registers, shared memory, TMEM columns) and leaves.
+    {
+        int dead = 0;
+        if (tid == 0) {
+            dead = (int)ld_relaxed_u32(&p.barrier->failed);
+            if (p.probe && !dead) {
+                const unsigned int n = atomicAdd(&p.probe_count[0], 1u) + 1u;
+                atomicMax(&p.probe_count[1], n);
+                const long long t0 = clock64();
+                while (ld_relaxed_u32(&p.probe_count[0]) < gridDim.x && clock64() - t0 < (1ll << 22)) __nanosleep(64);   // ~2 ms
+                atomicMax(&p.probe_count[1], ld_relaxed_u32(&p.probe_count[0]));
+                __nanosleep(2000);                     // late arrivals of a resident grid are counted by everybody
+                atomicSub(&p.probe_count[0], 1u);      // a CTA that starts after this one has left is not co-resident with it
+                dead = 1;
+            }
+        }
+        if (__syncthreads_or(dead)) {
+            if constexpr (TC) tc::teardown<I, H, O>(tcst);
+            return;
+        }
+    }
     // likelihood sums of weight vector wv on both data sets (K5 path)
     auto tc_likelihood = [&](const float *wv, bool with_test, double &a0, double &a1, int &c0, double &b0, double &b1, int &c1) {
         if constexpr (TC) {
@@ -1690,13 +1748,18 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     for (int j = tid; j < P; j += NT) pw[j] = __ldcg(&prev[j]);         // (maybe written by another CTA)
                 }
                 }   // kq < W
-                if (!SPEC) { ++ibase; continue; }
+                if (!SPEC) {
+                    if (tid == 0) atomicAdd(p.heartbeat, 1u);     // progress, as seen by the waits of other CTAs / ranks
+                    ++ibase; continue;
+                }
                 // ---- resolve the window
                 // flag = (window base + 1) << 2 | computed langevin_gradient(w) of the base state << 1 | accepted
                 const bool made_gd = kq < W && !accept && p.memo && gd_valid && !gd_valid0;
-                if (tid == 0)
+                if (tid == 0) {
                     p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 2) | (made_gd ? 2u : 0u) | ((kq < W && accept) ? 1u : 0u);
-                grid_barrier(&p.spec_bar[r], (unsigned int)K, /*spin=*/true);
+                    atomicAdd(p.heartbeat, 1u);
+                }
+                if (!grid_barrier(&p.spec_bar[r], (unsigned int)K, p.wait_limit, p.heartbeat, /*spin=*/true)) goto chain_exit;
                 int kstar = W, kgd = W;
                 for (int q = 0; q < W; ++q) {
                     const unsigned int f = __ldcg(&p.spec_flag[r * K + q]);
@@ -1714,17 +1777,17 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     if (kq == committed && !gd_valid) gd_valid = -1;        // valid, but this CTA does not hold the vector
                 }
                 if (kq == committed) store_state();
-                grid_barrier(&p.spec_bar[r], (unsigned int)K, /*spin=*/true);
+                if (!grid_barrier(&p.spec_bar[r], (unsigned int)K, p.wait_limit, p.heartbeat, /*spin=*/true)) goto chain_exit;
                 ibase += committed + 1;
             }
 
             // ---------------- publish for the hand-shake (R:427-431 / C:438-440) ----------------
             if (SPEC) { if (kq != 0) continue; load_state(); }
             if (swap_at_end) {
-                float *row = p.pub_rows + ((size_t)parity * p.R + r) * (P + 1);
+                float *row = p.pub_rows + ((size_t)parity * p.R + r) * (P + kRowTail);
                 for (int j = tid; j < P; j += NT) row[j] = s_w[j];
                 if (tid == 0) {
-                    row[P] = (float)eta;
+                    put_f64_words(&row[P], eta);
                     p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] =
                         (TASK == kTaskReg) ? lik * temperature : lik;                 // R:430 (Q8) | C:439
                 }
@@ -1737,11 +1800,12 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         if (swap_at_end) {
             if (p.external_swap) break;   // multi-GPU: the host completes the round (ptfnn_swap_*)
             // ---------------- K4: swap round ----------------
-            grid_barrier(p.barrier, nblocks);
-            if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
+            // (a wait that gave up means unpublished rows: leave without touching state, traces or the window)
+            if (!grid_barrier(p.barrier, nblocks, p.wait_limit, p.heartbeat)) goto chain_exit;
+            if (p.n_ranks > 1 && !peer_exchange_lhood<NT>(p, round, parity, p.barrier)) goto chain_exit;
             if (kq == 0) chain_sweep<NT>(p, round, parity, /*apply=*/true, s_sweep, nvb, vblock);
             __syncthreads();
-            if (SPEC) grid_barrier(p.barrier, nblocks);      // the pulled vectors are visible to every CTA of the group
+            if (SPEC && !grid_barrier(p.barrier, nblocks, p.wait_limit, p.heartbeat)) goto chain_exit;   // the pulled vectors are visible to every CTA of the group
             ++round;
         }
     }
@@ -1752,10 +1816,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         if (kq == 0)
             for (int r = vblock; r < p.R; r += nvb)
                 if (tid == 0) p.pub_lhood[(size_t)parity * p.Rg + p.replica_offset + r] = __ldcg(&p.lik[r]);
-        grid_barrier(p.barrier, nblocks);
-        if (p.n_ranks > 1) peer_exchange_lhood<NT>(p, round, parity, p.barrier);
+        if (!grid_barrier(p.barrier, nblocks, p.wait_limit, p.heartbeat)) goto chain_exit;
+        if (p.n_ranks > 1 && !peer_exchange_lhood<NT>(p, round, parity, p.barrier)) goto chain_exit;
         if (blockIdx.x == 0) chain_sweep<NT>(p, round, parity, /*apply=*/false, s_sweep, nvb, 0);
     }
+chain_exit:
     if constexpr (TC) tc::teardown<I, H, O>(tcst);
 }
 
@@ -1784,7 +1849,11 @@ __global__ void __launch_bounds__(NT) init_kernel(const InitParams p) {
     __syncthreads();
     double eta = 0.0, tau = 1.0;                                                  // C:263 junk variable
     if constexpr (TASK == kTaskReg) {
-        // np.var(pred_train - y_train): two-pass population variance (R:270)
+        // np.var(pred_train - y_train) (R:270): ONE forward per row; each thread keeps the shifted sums
+        // sum(d - d0), sum((d - d0)^2) of its rows in fp64 with d0 = the residual of row 0 (no cancellation:
+        // the residuals of an untrained net differ from one another by O(1) like they differ from d0),
+        // var = S2/n - (S1/n)^2.  (Round 1 evaluated every row twice for a two-pass variance: 7.5 ms per launch
+        // at 1024 temperatures.)
         constexpr int IP = IPad<I>::value;
         auto residual = [&](int row) {
             DataView one{p.train.x + (size_t)row * IP, p.train.y + row, 1};
@@ -1794,16 +1863,17 @@ __global__ void __launch_bounds__(NT) init_kernel(const InitParams p) {
             lik_rows_impl<I, H, O, TASK, 1, true, true>(s_w, one, 0, 1, sse, d1, c, &fx, nullptr);
             return (double)fx - (double)p.train.y[row];
         };
-        double sd[1] = {0.0};
-        for (int row = tid; row < p.train.n; row += NT) sd[0] += residual(row);
-        block_sum<1, NT>(sd, s_red);
-        const double mean = sd[0] / p.train.n;
-        double sv[1] = {0.0};
+        const double d0 = residual(0);
+        double sv[2] = {0.0, 0.0};
         for (int row = tid; row < p.train.n; row += NT) {
-            const double dv = residual(row) - mean;
-            sv[0] += dv * dv;
+            const double dv = residual(row) - d0;
+            sv[0] += dv; sv[1] += dv * dv;
         }
-        block_sum<1, NT>(sv, s_red);
+        block_sum<2, NT>(sv, s_red);
+        const double m1 = sv[0] / p.train.n;
+        double var = sv[1] / p.train.n - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        sv[0] = var * p.train.n;
         eta = log(sv[0] / p.train.n);
         tau = exp(eta);                                                           // R:271
     }

@@ -6,14 +6,16 @@
 namespace ptfnn {
 
 // ---- topology-independent kernels ----
-__global__ void op_sweep_kernel(int n, const double *lhood, const float *u, int *src, uint8_t *swapped, int *ns_out) {
+__global__ void op_sweep_kernel(int n, const double *lhood, const float *u, int *src, uint8_t *swapped, int *ns_out,
+                                int kind, const double *temperature) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *l = reinterpret_cast<double *>(smem_raw);
     int *s = reinterpret_cast<int *>(smem_raw + (size_t)n * 8);
     for (int k = threadIdx.x; k < n; k += blockDim.x) { l[k] = lhood[k]; s[k] = k; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int ns = swap_sweep_serial(n, l, s, swapped, [&](int k) { return u[k]; });
+        const int ns = swap_sweep_serial(n, l, s, swapped, [&](int k) { return u[k]; }, kind,
+                                         [&](int slot) { return temperature ? temperature[slot] : 1.0; });
         if (ns_out) *ns_out = ns;
     }
     __syncthreads();
@@ -344,6 +346,98 @@ __global__ void __launch_bounds__(kSumThreads, 2) trace_summary_kernel(const Tra
     if (tid == 0) *a.ticket = 0u;
 }
 
+// ---- percentile bands of the posterior-predictive distribution ----
+// m is the [n, N] prediction matrix (n pooled posterior samples, N data rows, float32).  For every data row the
+// order statistics k0, k0+1, k1, k1+1 of its column are found EXACTLY: a most-significant-digit radix select
+// (four 8-bit digits of the order-preserving integer image of the float, one histogram pass per digit, two
+// targets at once), then one more pass that resolves the successor of each selected value (the next larger
+// element, or the same value when it is tied across the two ranks).  A CTA owns kQCols adjacent columns, so a
+// warp reads whole 32-byte sectors; the matrix is read five times and is L2-resident for the reference's
+// configurations (25 000 samples x 298 rows = 30 MB).  lo / hi follow np.percentile's default (linear) rule.
+constexpr int kQCols = 8;
+constexpr int kQThreads = 256;
+__device__ __forceinline__ unsigned int f32_ordered(float v) {
+    const unsigned int b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_ordered(unsigned int k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+__global__ void __launch_bounds__(kQThreads) quantile_bands_kernel(const float *__restrict__ m, long long n, int N, long long k0, double f0,
+                                                                   long long k1, double f1, double *lo, double *hi) {
+    __shared__ unsigned int hist[2][256][kQCols];
+    __shared__ unsigned int prefix[2][kQCols];
+    __shared__ unsigned long long rank[2][kQCols];
+    __shared__ unsigned long long cnt_le[2][kQCols];
+    __shared__ unsigned int min_gt[2][kQCols];
+    const int tid = threadIdx.x, c = tid % kQCols, sl = tid / kQCols;
+    constexpr int SL = kQThreads / kQCols;
+    const int col = blockIdx.x * kQCols + c;
+    const bool live = col < N;
+    if (tid < 2 * kQCols) { prefix[tid / kQCols][tid % kQCols] = 0u; rank[tid / kQCols][tid % kQCols] = (unsigned long long)(tid / kQCols == 0 ? k0 : k1); }
+    for (int d = 3; d >= 0; --d) {
+        for (int i = tid; i < 2 * 256 * kQCols; i += kQThreads) (&hist[0][0][0])[i] = 0u;
+        __syncthreads();
+        const unsigned int p0 = prefix[0][c], p1 = prefix[1][c];
+        const int sh = 8 * d;
+        const bool same = p0 == p1;                      // both targets still inside the same bucket: one histogram serves both
+        if (live)
+            for (long long r = sl; r < n; r += SL) {
+                const unsigned int key = f32_ordered(m[r * N + col]);
+                const unsigned int hi_bits = d == 3 ? 0u : (key >> (sh + 8));
+                const unsigned int dg = (key >> sh) & 255u;
+                if (d == 3 || hi_bits == (p0 >> (sh + 8))) atomicAdd(&hist[0][dg][c], 1u);
+                if (!same && hi_bits == (p1 >> (sh + 8))) atomicAdd(&hist[1][dg][c], 1u);
+            }
+        __syncthreads();
+        if (tid < 2 * kQCols) {
+            const int t = tid / kQCols, cc = tid % kQCols;
+            const int h = (prefix[0][cc] == prefix[1][cc]) ? 0 : t;
+            unsigned long long want = rank[t][cc], cum = 0;
+            int dsel = 255;
+            for (int b = 0; b < 256; ++b) {
+                const unsigned int v = hist[h][b][cc];
+                if (cum + v > want) { dsel = b; break; }
+                cum += v;
+            }
+            rank[t][cc] = want - cum;
+            __syncwarp((1u << (2 * kQCols)) - 1u);       // both prefixes of a column were read (h) before either is updated
+            prefix[t][cc] |= (unsigned int)dsel << sh;
+        }
+        __syncthreads();
+    }
+    // successor of each selected value
+    if (tid < 2 * kQCols) { cnt_le[tid / kQCols][tid % kQCols] = 0ull; min_gt[tid / kQCols][tid % kQCols] = 0xffffffffu; }
+    __syncthreads();
+    {
+        const unsigned int v0 = prefix[0][c], v1 = prefix[1][c];
+        unsigned long long le0 = 0, le1 = 0;
+        unsigned int g0 = 0xffffffffu, g1 = 0xffffffffu;
+        if (live)
+            for (long long r = sl; r < n; r += SL) {
+                const unsigned int key = f32_ordered(m[r * N + col]);
+                le0 += key <= v0; le1 += key <= v1;
+                if (key > v0) g0 = min(g0, key);
+                if (key > v1) g1 = min(g1, key);
+            }
+        atomicAdd(&cnt_le[0][c], le0); atomicAdd(&cnt_le[1][c], le1);
+        atomicMin(&min_gt[0][c], g0); atomicMin(&min_gt[1][c], g1);
+    }
+    __syncthreads();
+    if (tid < kQCols && blockIdx.x * kQCols + tid < N) {
+        const int cc = tid;
+        auto band = [&](int t, long long k, double f) {
+            const double a = (double)f32_from_ordered(prefix[t][cc]);
+            // rank k+1 holds the same value when at least k+2 elements are <= it, else the next larger element
+            const bool tied = cnt_le[t][cc] >= (unsigned long long)(k + 2) || min_gt[t][cc] == 0xffffffffu;
+            const double b = tied ? a : (double)f32_from_ordered(min_gt[t][cc]);
+            return f > 0.0 ? a + (b - a) * f : a;
+        };
+        lo[blockIdx.x * kQCols + cc] = band(0, k0, f0);
+        hi[blockIdx.x * kQCols + cc] = band(1, k1, f1);
+    }
+}
+
 // multi-GPU: install the rows selected by the sweep (R:435-437)
 __global__ void swap_apply_kernel(int R, int P, int replica_offset, const int *src, const float *rows_local,
                                   const float *rows_in, float *w, double *eta, int *gd_valid) {
@@ -351,9 +445,14 @@ __global__ void swap_apply_kernel(int R, int P, int replica_offset, const int *s
     const int s = src[replica_offset + r];
     if (s == replica_offset + r) return;
     const bool local = s >= replica_offset && s < replica_offset + R;
-    const float *row = local ? rows_local + (size_t)(s - replica_offset) * (P + 1) : rows_in + (size_t)r * (P + 1);
+    constexpr int kTail = 2;                    // eta travels as its fp64 bit pattern (ptfnn_kernels.cuh: kRowTail)
+    const float *row = local ? rows_local + (size_t)(s - replica_offset) * (P + kTail) : rows_in + (size_t)r * (P + kTail);
     for (int j = threadIdx.x; j < P; j += blockDim.x) w[(size_t)r * P + j] = row[j];
-    if (threadIdx.x == 0) { eta[r] = (double)row[P]; gd_valid[r] = 0; }
+    if (threadIdx.x == 0) {
+        const unsigned int *t = reinterpret_cast<const unsigned int *>(row + P);
+        eta[r] = __longlong_as_double((long long)(((unsigned long long)t[1] << 32) | t[0]));
+        gd_valid[r] = 0;
+    }
 }
 
 }  // namespace ptfnn

@@ -1,6 +1,6 @@
 // Kernel dispatch record: one per specialised topology (see ptfnn_topologies.h).
 #pragma once
-#define PTFNN_REGISTRY_VERSION 3      /* layout of PtfnnKernelSet; checked by ptfnn_register_kernels */
+#define PTFNN_REGISTRY_VERSION 4      /* layout of PtfnnKernelSet; checked by ptfnn_register_kernels */
 struct PtfnnKernelSet {
     const char *name;
     int task, I, H, O, NT;
@@ -11,4 +11,5 @@ struct PtfnnKernelSet {
     const void *fwd_tc;   // K5: tcgen05 forward / likelihood of wide-hidden nets (0 = not applicable)
     const void *pack_a;   // data set -> UMMA A tiles for fwd_tc and the chain kernel
     int a_tile_floats, tc_smem_bytes, tc_alias_off;
+    int tmem_cols;        // TMEM columns one CTA of the chain kernel allocates (0 = none)
 };

@@ -33,6 +33,7 @@ const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
         kTc ? (const void *)op_forward_tc_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT> : nullptr,
         kTc ? (const void *)tc::pack_a_kernel<PTFNN_T_I> : nullptr,
         tc::a_tile_floats(PTFNN_T_I), tc::Smem<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O>::total, tc::Smem<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O>::off_a,
+        kTc ? PTFNN_T_H : 0,
     };
     return &ks;
 }

@@ -7,7 +7,7 @@ R/G temperatures (ladder order = rank order) and the only communication is the s
   2. every rank runs the reference's SEQUENTIAL sweep (R:741-748) on the gathered vector with the
      same uniforms (replay) or the same Philox counters (free-running) -> identical ``src``
   3. only rows whose source slot lives on another rank move: batched isend/irecv of (w, eta),
-     (P+1) float32 each -- in expectation the rows next to the G-1 rank boundaries
+     (P+2) float32 words each (eta as its float64 bit pattern) -- in expectation the rows next to the G-1 rank boundaries
   4. install, continue.
 
 On GPUs that can map each other's memory (NVLink / NVSwitch, one box) steps 1-4 run INSIDE the
@@ -74,8 +74,8 @@ class GpuChains:
         R, Rg, P = sampler.R, sampler.Rg, sampler.P
         self.lhood_local = torch.zeros(R, dtype=torch.float64, device=torch_device)
         self.lhood_global = torch.zeros(Rg, dtype=torch.float64, device=torch_device)
-        self.rows_local = torch.zeros(R, P + 1, dtype=torch.float32, device=torch_device)
-        self.rows_in = torch.zeros(R, P + 1, dtype=torch.float32, device=torch_device)
+        self.rows_local = torch.zeros(R, P + 2, dtype=torch.float32, device=torch_device)
+        self.rows_in = torch.zeros(R, P + 2, dtype=torch.float32, device=torch_device)
         sampler.set_stream(torch.cuda.current_stream(torch_device).cuda_stream)
 
     @property
@@ -145,6 +145,16 @@ class PartitionedLadder:
                 req.wait()
         self.chains.swap_apply(src, rows_local, rows_in)
         return src
+
+    def init_chains(self, w0_local):
+        """(Re-)initialise this rank's block.  On peer-connected handles the ranks meet at a barrier afterwards:
+        no rank may publish into the swap window of a rank that is still reading the previous run's
+        (include/ptfnn.h, ptfnn_peer_connect)."""
+        self.chains.s.init_chains(w0_local)
+        self.rounds = 0
+        self.rows_moved = 0
+        self.chains.s.sync()
+        self.dist.barrier(self.group)
 
     def summary(self, first=0, count=None, posterior=True):
         """Result statistics of the WHOLE ladder: every rank reduces its own traces on its

@@ -14,15 +14,19 @@ from . import capi
 from .capi import TASK_CLASSIFICATION, TASK_REGRESSION  # noqa: F401
 
 
-def geometric_ladder(num_chains: int, maxtemp) -> np.ndarray:
-    """Temperatures of ParallelTempering.assign_temperatures (R:615-636): the geometric branch of
-    default_beta_ladder reduces to betas = logspace(0, -log10(maxtemp), num_chains) (R:607)."""
+def geometric_betas(num_chains: int, maxtemp) -> np.ndarray:
+    """Inverse temperatures of the geometric ladder: everything default_beta_ladder computes for the arguments
+    assign_temperatures passes reduces to logspace(0, -log10(maxtemp), num_chains) (R:607)."""
     if num_chains < 1:
         raise ValueError("Invalid number of temperatures specified.")          # R:546-547
     if maxtemp is not None and maxtemp <= 1:
         raise ValueError("``Tmax`` must be greater than 1.")                   # R:544-545
-    betas = np.logspace(0, -np.log10(maxtemp), num_chains)
-    return 1.0 / betas
+    return np.logspace(0, -np.log10(maxtemp), num_chains)
+
+
+def geometric_ladder(num_chains: int, maxtemp) -> np.ndarray:
+    """Temperatures of ParallelTempering.assign_temperatures (R:615-636): T_k = maxtemp^(k / (num_chains - 1))."""
+    return 1.0 / geometric_betas(num_chains, maxtemp)
 
 
 class Sampler:
@@ -30,7 +34,7 @@ class Sampler:
                  l_prob=0.5, learn_rate=0.1, seed=0, common_random_numbers=True, memoize_gradient=True,
                  device=0, debug_traces=False, swap_rule=capi.SWAP_RULE_AUTO, n_replicas_global=None,
                  replica_offset=0, step_w=0.025, step_eta=0.2, sigma_squared=25.0, nu_1=0.0, nu_2=0.0,
-                 pt_fraction=0.6, stream=None, speculation=0):
+                 pt_fraction=0.6, stream=None, speculation=0, swap_kind=capi.SWAP_KIND_REFERENCE, barrier_timeout_ms=0):
         lib = capi.load()
         capi.ensure_topology(task, topology)      # compiles a specialisation on first use of a new topology
         c = capi.default_config()
@@ -41,6 +45,8 @@ class Sampler:
         c.n_replicas_global = int(n_replicas_global or c.n_replicas)
         c.replica_offset = int(replica_offset)
         c.speculation = int(speculation)      # small ladders: 0 automatic, 1 off, K CTAs per temperature
+        c.swap_kind = int(swap_kind)          # 0 = the reference's swap probability (R:674); 1 = the drafts' temperature-aware rule
+        c.barrier_timeout_ms = int(barrier_timeout_ms)   # device-side waits give up after this long without progress (0 = 20 s)
         c.samples, c.swap_interval, c.swap_rule = int(samples), int(swap_interval), int(swap_rule)
         c.use_langevin_gradients = int(bool(use_langevin_gradients))
         c.common_random_numbers = int(bool(common_random_numbers))
@@ -212,17 +218,32 @@ class Sampler:
             out[k] = {"mean": v[0], "std": v[1], "min": v[2], "max": v[3]}
         return out
 
-    def predictive_summary(self, which="test", first=0, count=None):
+    def predictive_summary(self, which="test", first=0, count=None, bands=None):
         """Posterior-predictive mean and std of every data row over the pooled posterior samples (rows
         [first, first+count) of every chain's pos_w), computed from the device traces: what np.mean / np.std
         over the fx_*_all arrays the reference comments out (R:785-788, R:809-815) would give.  Regression.
-        -> dict(mean[rows], std[rows], rmse_of_mean)"""
+        ``bands`` = (q_lo, q_hi) in percent, e.g. (5, 95): also np.percentile(fx_all, q, axis=0) of the same
+        matrix (exact radix select on the device) as ``lo`` / ``hi``.
+        -> dict(mean[rows], std[rows], rmse_of_mean[, lo[rows], hi[rows]])"""
         count = self.S - first if count is None else count
         rows = self.n_train if which == "train" else self.n_test
+        wh = 0 if which == "train" else 1
         mean, std, rm = np.empty(rows), np.empty(rows), C.c_double()
-        self._ck(self._lib.ptfnn_predictive_summary(self._h, 0 if which == "train" else 1, int(first), int(count),
+        self._ck(self._lib.ptfnn_predictive_summary(self._h, wh, int(first), int(count),
                                                     capi.ptr(mean), capi.ptr(std), C.byref(rm)))
-        return {"mean": mean, "std": std, "rmse_of_mean": rm.value}
+        out = {"mean": mean, "std": std, "rmse_of_mean": rm.value}
+        if bands is not None:
+            out["lo"], out["hi"] = self.predictive_bands(which, first, count, *bands)
+        return out
+
+    def predictive_bands(self, which="test", first=0, count=None, q_lo=5.0, q_hi=95.0):
+        """-> (lo[rows], hi[rows]) = np.percentile of the posterior-predictive samples of every data row."""
+        count = self.S - first if count is None else count
+        rows = self.n_train if which == "train" else self.n_test
+        lo, hi = np.empty(rows), np.empty(rows)
+        self._ck(self._lib.ptfnn_predictive_bands(self._h, 0 if which == "train" else 1, int(first), int(count),
+                                                  C.c_double(q_lo), C.c_double(q_hi), capi.ptr(lo), capi.ptr(hi)))
+        return lo, hi
 
     def swap_stats(self, max_rounds=None):
         """-> (num_swap, total_swap_proposals, swapped[rounds, Rg-1])"""
