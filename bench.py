@@ -7,18 +7,26 @@
 Workloads (BASELINE.json configs):
   synth_ts  (default) synthetic 100k-point series, embed 4, FNN 4-64-1, 1024 temperatures per GPU
             (29 998 train / 19 998 test rows), Langevin l_prob 0.5, swap every 10 steps.  The ladder
-            is partitioned over ranks: weak scaling, 1024 temperatures per GPU, boundary swaps over NCCL.
+            is partitioned over ranks: weak scaling, 1024 temperatures per GPU, boundary swaps over NVLink.
   sunspot   Sunspot 4-5-1, 10 temperatures, maxtemp 2, Langevin l_prob 0.5, swap every 50 steps (1 GPU)
   pendigit  PenDigit-shaped 16-256-10, 20k rows, 256 temperatures per GPU
 
 One bench "step" = one swap interval of the whole ladder (swap_interval MCMC steps of every
 replica + the swap round).  ``value`` = replica-steps/s with everything resident in HBM;
 ``e2e`` = the same through the public Sampler API with host buffers (dataset H2D + trace D2H every step).
+
+The default line (workload synth_ts) also carries, under ``sub``, the other north-star configurations measured in
+the same process -- ``burned_in`` (the same ladder after >= 2000 steps, where the acceptance rate is the
+reference's steady state rather than ~1), ``strong_1024`` (the ladder of BASELINE configs[3] as worded: 1024
+temperatures split over the N GPUs), and at N = 1 ``sunspot`` (the >= 100x target) and ``pendigit`` (the tcgen05
+path) -- and, at N > 1, ``multi_gpu_parity``: a replay of the partitioned ladder compared bit for bit with a
+single-GPU run of the whole ladder.  ``--no-sub`` skips them.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -33,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L2_FLUSH_BYTES = 256 << 20
+BURN_IN_STEPS = 2000
 
 
 # ------------------------------------------------------------------------------------------
@@ -67,6 +76,16 @@ def load_workload(name: str, n_gpus: int, replicas_per_gpu=None):
     return w
 
 
+def config_of(w):
+    """What both arms print as ``config``: the workload, nothing about how it was run."""
+    return {"workload": w["desc"],
+            "sampler": "Langevin PT, l_prob %.2f, lr %g, swap_interval %d, maxtemp %s" % (w["l_prob"], w["learn_rate"], w["swap_interval"], w["maxtemp"])}
+
+
+def data_of(w):
+    return "synthetic" if w["name"] != "sunspot" else "Sunspot (reference dataset), random-init weights"
+
+
 def algorithmic_work(w):
     """logical passes of the reference per replica-step, fp32 storage."""
     I, H, O = w["topology"]
@@ -76,8 +95,9 @@ def algorithmic_work(w):
     sgd = fwd + 4 * H * O + 2 * I * H + 5 * H + 5 * O
     sig = H + O
     trace = (w["P"] + 4) * 4
-    rw = dict(flop=(N + M) * fwd, bytes=(N + M) * row_bytes + trace, sfu=(N + M) * sig * 2)
-    lg = dict(flop=2 * N * sgd + (N + M) * fwd, bytes=(3 * N + M) * row_bytes + trace, sfu=(3 * N + M) * sig * 2)
+    rw = dict(flop=(N + M) * fwd, bytes=(N + M) * row_bytes + trace, sfu=(N + M) * sig * 2, tensor_flop=(N + M) * 2 * (I * H + H * O))
+    lg = dict(flop=2 * N * sgd + (N + M) * fwd, bytes=(3 * N + M) * row_bytes + trace, sfu=(3 * N + M) * sig * 2,
+              tensor_flop=(N + M) * 2 * (I * H + H * O))
     return rw, lg
 
 
@@ -155,6 +175,15 @@ def cpu_sample_plan(w, cores):
     return cores, [LG, RW]                       # seconds per replica-step: one Langevin + one random-walk step per core
 
 
+def cpu_baseline_record(w):
+    from oracle import cpu_baseline
+    cores = cpu_baseline.host_cores()
+    n_procs, pattern = cpu_sample_plan(w, cores)
+    wall, units = cpu_sample(w, n_procs, pattern)
+    return {"value": units / wall, "unit": "replica-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d replica processes x %d steps (LG/RW alternating = l_prob 0.5) of the same workload, %.1f s wall" % (n_procs, len(pattern), wall)}
+
+
 def run_reference_arm(args, w):
     """--impl reference: the reference's multiprocessing CPU path (oracle port; /root/reference does not
     exist on the GPU box) on the host cores, same workload / metric / unit.  Every bench step is a
@@ -182,8 +211,7 @@ def run_reference_arm(args, w):
     line = {"impl": "reference", "metric": "replica_mcmc_steps_per_sec", "value": value, "unit": "replica-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic" if w["name"] != "sunspot" else "Sunspot (reference dataset), random-init weights",
-            "config": {"workload": w["desc"], "sampler": "Langevin PT, l_prob %.2f, lr %g, swap_interval %d, maxtemp %s" % (w["l_prob"], w["learn_rate"], w["swap_interval"], w["maxtemp"])},
+            "vs_baseline": None, "dtype": "f64", "data": data_of(w), "config": config_of(w),
             "cpu_baseline": {"value": value, "unit": "replica-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "replica-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -201,213 +229,377 @@ def measure_peaks(device):
     return {"fp32_tflops": out[0], "mufu_gops": out[1], "smem_gbs": out[2], "fp32_3reg_tflops": out[3]}
 
 
-def run_b200_arm(args, w, rank, world, local_rank):
-    import torch
-    from ptnn_b200 import capi
-    from ptnn_b200.sampler import Sampler
-    if capi.device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: libptfnn has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    K, W, si = args.steps, args.warmup, w["swap_interval"]
-    S = si * (K + W) + 2
-    stream = torch.cuda.current_stream(dev)
-    kw = dict(use_langevin_gradients=True, l_prob=w["l_prob"], learn_rate=w["learn_rate"], seed=args.seed,
-              common_random_numbers=True)
-    rs = np.random.RandomState(1000 + rank)
+def measured_peaks_file():
+    mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp_path):
+        d = json.load(open(mp_path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("bf16_tflops_sustained", 0) or 0)
+    return 6650.0, "fallback 6.65 TB/s", 0.0
 
-    def make(memo, samples):
+
+class Bench:
+    """One process per GPU; every measurement of the B200 arm shares the device, the stream and the L2-flush buffer."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        from ptnn_b200 import capi
+        if capi.device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: libptfnn has no CPU path")
+        self.torch, self.args, self.rank, self.world, self.local_rank = torch, args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
         if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=self.dev)
+        self.peaks = None
+
+    # ---- plumbing
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def make(self, w, memo, samples, w0=None, state=None, distributed=True, **extra):
+        """A sampler over this rank's block of ``w``'s ladder (the whole ladder when world == 1 or not distributed)."""
+        from ptnn_b200.sampler import Sampler
+        kw = dict(use_langevin_gradients=True, l_prob=w["l_prob"], learn_rate=w["learn_rate"], seed=self.args.seed,
+                  common_random_numbers=True)
+        kw.update(extra)
+        si = w["swap_interval"]
+        if self.world > 1 and distributed:
             from ptnn_b200.distributed import make_gpu_ladder
-            ladder, smp = make_gpu_ladder(w["task"], w["topology"], w["temperatures"], samples, si, device=local_rank,
+            ladder, smp = make_gpu_ladder(w["task"], w["topology"], w["temperatures"], samples, si, device=self.local_rank,
                                           memoize_gradient=memo, **kw)
         else:
-            smp = Sampler(w["task"], w["topology"], w["temperatures"], samples, si, device=local_rank,
-                          memoize_gradient=memo, stream=stream, **kw)
+            smp = Sampler(w["task"], w["topology"], w["temperatures"], samples, si, device=self.local_rank,
+                          memoize_gradient=memo, stream=self.stream, **kw)
             ladder = None
         smp.set_data(w["train"], w["test"])
-        smp.init_chains(rs.randn(smp.R, smp.P))
+        if w0 is None:
+            w0 = np.random.RandomState(1000 + self.rank).randn(smp.R, smp.P)
+        smp.init_chains(w0)
+        if state is not None:                 # continue a burned-in chain: (w is w0) eta, lik, prior, tau
+            smp.set_state(eta=state["eta"], lik=state["lik"], prior=state["prior"], tau=state["tau"])
+        if ladder is not None:
+            self.barrier()
         return smp, ladder
 
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed_steps(smp, ladder, n_warm, n_timed):
+    def timed_steps(self, smp, ladder, si, n_warm, n_timed):
+        """-> (sum of the timed steps' device time in ms, max over ranks; per-step ms of this rank)."""
+        torch = self.torch
         adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
         for _ in range(n_warm):
             adv()
-        barrier()
-        ev, t_wall0 = [], time.perf_counter()
+        self.barrier()
+        ev = []
         for _ in range(n_timed):
-            flush.fill_(1)                                   # evict L2 between timed steps (untimed)
+            self.flush.fill_(1)                                   # evict L2 between timed steps (untimed)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
+            a.record(self.stream)
             adv()
-            b.record(stream)
+            b.record(self.stream)
             ev.append((a, b))
-        barrier()
-        wall = time.perf_counter() - t_wall0
+        self.barrier()
         ms = [a.elapsed_time(b) for a, b in ev]
-        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)       # max over ranks
-        return float(tot.item()), ms, wall
+        return self.max_over_ranks(sum(ms)), ms
 
-    # ---- (1) device-resident throughput, every logical pass executed (memoize_gradient = 0)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    smp, ladder = make(0, S)
-    total_ms, ms_list, _ = timed_steps(smp, ladder, W, K)
-    clk = clocks.stop() if clocks else None
-    units_per_step = w["R_global"] * si
-    value = units_per_step * K / (total_ms * 1e-3)
-    # exact Langevin / random-walk mix of the timed steps (common random numbers: one lx per step)
-    lx = smp.generate_draws(W * si, K * si)[0][0]
-    n_lg = int(np.sum(lx < w["l_prob"]))
-    n_rw = K * si - n_lg
-    smp.close()
+    def acceptance(self, smp, first_step, n_steps):
+        """Acceptance rate of steps [first_step, first_step + n_steps) of this rank's replicas: accept_list row i+1 is
+        the number accepted BEFORE step i (R:380)."""
+        a = smp.traces(first=first_step + 1, count=1, pos_w=False, debug=False)["accept_list"][:, 0]
+        last = first_step + n_steps
+        if smp.step > last:                                  # row last+1 (the count before step `last`) has been written
+            b = smp.traces(first=last + 1, count=1, pos_w=False, debug=False)["accept_list"][:, 0]
+        else:                                                # the chain stands right after step last-1
+            b = smp.get_state()["num_accepted"].astype(np.float64)
+        tot = self.sum_over_ranks(float(np.sum(b - a)))
+        return tot / (n_steps * smp.R * self.world if self.dist is not None else n_steps * smp.R)
 
-    # ---- (2) the same with the product default (memoised langevin_gradient(w); identical results)
-    smp, ladder = make(1, S)
-    total_ms_memo, _, _ = timed_steps(smp, ladder, W, K)
-    value_memo = units_per_step * K / (total_ms_memo * 1e-3)
-    smp.close()
+    def e2e(self, smp, ladder, w, n_warm, n_timed):
+        """The same steps through the public API with HOST buffers: every step uploads the data set and reads the
+        step's trace rows back.  The read-back is overlapped: step k's rows are fetched on the library's copy
+        stream while step k+1 runs, and arrive as views (float32 weights, nothing widened)."""
+        si = w["swap_interval"]
+        adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
+        for _ in range(n_warm):
+            adv()
+        self.barrier()
+        t0 = time.perf_counter()
+        d2h, pending, checksum = 0, None, 0.0
+        for k in range(n_timed):
+            smp.set_data(w["train"], w["test"])                  # H2D (host float64 arrays, as the reference passes them)
+            adv()
+            first = smp.step - si + 1
+            ticket = smp.traces_begin(first, si, pos_w=True)     # D2H of this step, behind the kernel just launched
+            if pending is not None:
+                t = smp.traces_end(pending)                      # the previous step's rows: copied while this one runs
+                checksum += float(t["lik_prop"][0, -1]) + float(t["pos_w"][0, -1, 0])
+                d2h = sum(v.nbytes for v in t.values())
+            pending = ticket
+        t = smp.traces_end(pending)
+        checksum += float(t["lik_prop"][0, -1]) + float(t["pos_w"][0, -1, 0])
+        d2h = sum(v.nbytes for v in t.values())
+        self.barrier()
+        sec = self.max_over_ranks(time.perf_counter() - t0)
+        I = w["topology"][0]
+        ip = (I + 3) & ~3
+        h2d = sum((n * ip + ((n + 3) & ~3)) * 4 for n in (w["train"].shape[0], w["test"].shape[0]))
+        return {"value": w["R_global"] * si * n_timed / sec, "unit": "replica-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "readback": "overlapped (copy stream, page-locked double buffer, float32 views)",
+                "finite": bool(np.isfinite(checksum))}
 
-    # ---- (3) end to end through the public API with host buffers: every step uploads the dataset
-    #          (pinned-size host arrays) and reads the step's trace rows back
-    smp, ladder = make(0, S)
-    adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
-    for _ in range(W):
-        adv()
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for k in range(K):
-        smp.set_data(w["train"], w["test"])                 # H2D
-        adv()
-        first = smp.step - si + 1
-        t = smp.traces(first=first, count=si, pos_w=True, debug=False)   # D2H (synchronises)
-        d2h = sum(v.nbytes // 2 if v.dtype == np.float64 and kname == "pos_w" else v.nbytes for kname, v in t.items())
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    I = w["topology"][0]
-    ip = (I + 3) & ~3
-    h2d = sum((n * ip + ((n + 3) & ~3)) * 4 for n in (w["train"].shape[0], w["test"].shape[0]))
-    e2e_value = units_per_step * K / e2e_s
-    # ---- (4) result pipeline on the device traces: burn-in slice -> pooled statistics, HBM-bound.
-    #          Event-timed inside the library on the handle's stream; L2 flushed before every call.
-    pipe = None
+    def lx_mix(self, smp, w, first_step, n_steps):
+        lx = smp.generate_draws(first_step, n_steps)[0][0]          # common random numbers: one lx per step
+        n_lg = int(np.sum(lx < w["l_prob"]))
+        return n_lg, n_steps - n_lg
+
+    def rooflines(self, w, n_lg, n_rw, sec, K, clk):
+        """Roofline records of chain_kernel for a timed region of n_lg Langevin + n_rw random-walk steps."""
+        if self.peaks is None:
+            self.peaks = measure_peaks(self.local_rank) or {}
+        peaks, world = self.peaks, self.world
+        rw, lg = algorithmic_work(w)
+        Rg = w["R_global"]
+        flops = Rg * (n_lg * lg["flop"] + n_rw * rw["flop"])
+        byts = Rg * (n_lg * lg["bytes"] + n_rw * rw["bytes"])
+        sfu = Rg * (n_lg * lg["sfu"] + n_rw * rw["sfu"])
+        hbm_peak, hbm_src, bf16_peak = measured_peaks_file()
+        fp32_peak = peaks.get("fp32_tflops")
+        ach_tflops = flops / sec / 1e12 / world                 # per GPU
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(w["name"])
+        kname = "chain_kernel<%d,%d,%d>" % tuple(w["topology"])
+        fp32_roof = {"kernel": kname, "bound": "fp32-issue (not HBM: datasets are SMEM/L2 resident, SURVEY 8d)",
+                     "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (ach_tflops / fp32_peak) if fp32_peak else None,
+                     "peak_source": "measured in this run (csrc/ptfnn_peaks.cu FMA microbenchmark)", "traffic": traffic,
+                     "algorithmic_flop_per_launch": flops / K / world, "launch_ms": 1e3 * sec / K}
+        mufu_peak = peaks.get("mufu_gops")
+        ach_mufu = sfu / sec / 1e9 / world
+        mufu_roof = {"kernel": kname, "bound": "MUFU / XU pipe: 2 transcendental ops per sigmoid (not HBM: datasets are SMEM/L2 resident, SURVEY 8d)",
+                     "achieved": ach_mufu / 1e3, "peak": (mufu_peak / 1e3) if mufu_peak else None, "unit": "Tops/s",
+                     "frac": (ach_mufu / mufu_peak) if mufu_peak else None,
+                     "peak_source": "measured in this run (csrc/ptfnn_peaks.cu MUFU microbenchmark: 16 lanes/clk/SM)", "traffic": traffic,
+                     "algorithmic_sfu_ops_per_launch": sfu / K / world, "launch_ms": 1e3 * sec / K}
+        use_mufu = bool(mufu_roof["frac"] and fp32_roof["frac"] and mufu_roof["frac"] > fp32_roof["frac"])
+        roofline = mufu_roof if use_mufu else fp32_roof
+        alt = {
+            "hbm": {"bound": "hbm", "achieved": byts / sec / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": byts / sec / 1e9 / world / hbm_peak, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": byts / K / world},
+            ("fp32_issue" if use_mufu else "mufu"): (fp32_roof if use_mufu else mufu_roof),
+            "smem_broadcast": {"achieved_gbs": byts / sec / 1e9 / world, "peak_gbs": peaks.get("smem_gbs")},
+        }
+        # The Langevin steps are a serial recurrence over the training rows (SURVEY 3.4): their bound is the
+        # dependent-issue latency of one row, not a throughput peak.  floor = sum of the measured latencies of the
+        # instructions on the chain (tools/latency_probe.cu, DESIGN.md section 5); the upper bound charges the WHOLE
+        # timed region (random-walk steps included) to the serial rows.
+        chain_floor = {(4, 64, 1): 176, (4, 5, 1): 138, (4, 10, 1): 150, (16, 256, 10): 340}.get(tuple(w["topology"]))
+        serial_rows = n_lg * 2 * w["train"].shape[0]
+        if chain_floor and serial_rows and clk and clk.get("sm_mhz"):
+            cyc = sec / serial_rows * clk["sm_mhz"] * 1e6
+            alt["serial_chain"] = {"bound": "dependent-issue latency of the SGD recurrence (one chain per temperature)",
+                                   "serial_rows_per_temperature": serial_rows, "cycles_per_row_upper_bound": cyc,
+                                   "floor_cycles_per_row": chain_floor, "frac": chain_floor / cyc}
+        if tuple(w["topology"]) == (16, 256, 10) and bf16_peak:
+            # K5: both layers of the likelihood pass on the tf32 tensor pipe (3xTF32); dense tf32 peak = half the bf16 one
+            tf = Rg * (n_lg * lg["tensor_flop"] + n_rw * rw["tensor_flop"]) / sec / 1e12 / world
+            alt["tensor_tf32"] = {"bound": "tensor", "achieved": tf, "peak": bf16_peak / 2, "unit": "TFLOP/s", "frac": tf / (bf16_peak / 2),
+                                  "peak_source": "MEASURED_PEAKS.json bf16 sustained / 2",
+                                  "note": "algorithmic flop of the two dense layers (one logical pass); the kernel issues 3 tf32 products per logical one"}
+        return roofline, alt
+
+    # ---- one workload, measured like the headline: value, memoised value, e2e, acceptance, roofline
+    def measure(self, w, K, W, with_cpu, with_pipeline=False, distributed=True, burn=None):
+        """``burn``: dict(w=..., eta=..., lik=..., prior=..., tau=...) of a burned-in ladder (this rank's block) to continue."""
+        si = w["swap_interval"]
+        S = si * (K + W) + 2
+        w0 = None if burn is None else burn["w"]
+        clocks = ClockSampler(self.local_rank) if self.rank == 0 else None
+        smp, ladder = self.make(w, 0, S, w0=w0, state=burn, distributed=distributed)
+        total_ms, ms_list = self.timed_steps(smp, ladder, si, W, K)
+        clk = clocks.stop() if clocks else None
+        world = self.world if distributed else 1
+        units = w["R_global"] * si
+        value = units * K / (total_ms * 1e-3)
+        n_lg, n_rw = self.lx_mix(smp, w, W * si, K * si)
+        acc = self.acceptance(smp, W * si, K * si) if distributed or self.rank == 0 else None
+        smp.close()
+        smp, ladder = self.make(w, 1, S, w0=w0, state=burn, distributed=distributed)
+        total_ms_memo, _ = self.timed_steps(smp, ladder, si, W, K)
+        smp.close()
+        smp, ladder = self.make(w, 0, S, w0=w0, state=burn, distributed=distributed)
+        e2e = self.e2e(smp, ladder, w, W, K)
+        pipe = None
+        if with_pipeline and self.rank == 0:
+            n_rows = smp.step
+            smp.trace_summary(1, n_rows)
+            got = []
+            for _ in range(3):
+                self.flush.fill_(1)
+                self.torch.cuda.synchronize(self.dev)
+                got.append(smp.trace_summary(1, n_rows))
+            ms = float(np.mean([g["kernel_ms"] for g in got]))
+            hbm_peak, hbm_src, _ = measured_peaks_file()
+            ach = got[0]["bytes_read"] / (ms * 1e-3) / 1e9
+            pipe = {"kernel": "trace_summary_kernel<2>", "bound": "hbm", "rows_pooled": int(got[0]["n"]),
+                    "algorithmic_bytes_per_launch": int(got[0]["bytes_read"]), "launch_ms": ms, "achieved": ach, "unit": "GB/s",
+                    "peak": hbm_peak, "frac": ach / hbm_peak, "peak_source": hbm_src}
+        smp.close()
+        if self.rank != 0:
+            return None
+        roofline, alt = self.rooflines(w, n_lg, n_rw, total_ms * 1e-3, K, clk)
+        rec = {"value": value, "unit": "replica-steps/s", "ms_per_step": total_ms / K, "steps": K, "warmup": W,
+               "config": config_of(w), "data": data_of(w), "n_gpus": world,
+               "timed_region": {"replicas_total": w["R_global"], "replica_steps_per_bench_step": units,
+                                "langevin_steps": n_lg, "random_walk_steps": n_rw, "acceptance_rate": acc,
+                                "memoize_gradient": 0, "l2": "flushed between timed steps (256 MiB write)",
+                                "start": "random initial weights" if burn is None else "continued after %d burn-in steps" % BURN_IN_STEPS},
+               "value_memoized": units * K / (total_ms_memo * 1e-3), "ms_per_step_memoized": total_ms_memo / K,
+               "e2e": e2e, "gpu_launches": K, "clocks": clk, "roofline": roofline, "roofline_alt": alt, "step_ms": ms_list}
+        if with_cpu:
+            rec["cpu_baseline"] = cpu_baseline_record(w)
+        if pipe:
+            rec["result_pipeline"] = pipe
+        return rec
+
+    # ---- burn-in: >= BURN_IN_STEPS steps of the same ladder (memoised gradient: same chain, fewer passes), state kept on the host
+    def burn_in(self, w):
+        S = BURN_IN_STEPS + 2
+        smp, ladder = self.make(w, 1, S)
+        t0 = time.perf_counter()
+        (ladder.run(BURN_IN_STEPS) if ladder is not None else smp.run(BURN_IN_STEPS))
+        st = smp.get_state()
+        sec = time.perf_counter() - t0
+        a = smp.traces(first=S - 200, count=1, pos_w=False, debug=False)["accept_list"][:, 0]      # accepted before step S-201
+        late = self.sum_over_ranks(float(np.sum(st["num_accepted"] - a))) / (200.0 * smp.R * (self.world if self.dist is not None else 1))
+        ns, tot, _ = smp.swap_stats(0)
+        smp.close()
+        st["burn_seconds"], st["acceptance_last_200"], st["swap_rate"] = sec, late, (ns / tot if tot else None)
+        return st
+
+    # ---- N > 1: the partitioned ladder against ONE GPU holding the whole ladder, bit for bit
+    def multi_gpu_parity(self, w, n_steps=21):
+        """Replay of ``n_steps`` steps (two swap rounds) with the bench's own 1024 temperatures per rank: the draws are the
+        Philox draws dumped by the library, the swap uniforms are scaled down so that most pairs swap and vectors
+        cross every rank boundary (R:741-748, R:674).  Every rank hashes its block of the result; rank 0 runs the whole
+        ladder on its GPU alone and compares the hashes of the corresponding blocks."""
+        from types import SimpleNamespace
+        dist, world, rank = self.dist, self.world, self.rank
+        si, Rg = w["swap_interval"], w["R_global"]
+        S = n_steps + 1
+        rounds = sum(1 for i in range(n_steps) if i % si == 0 and i != 0) + 1
+        u_swap = (np.random.RandomState(77).rand(rounds, Rg - 1) * 0.05).astype(np.float32)
+        w0 = np.random.RandomState(4242).randn(Rg, w["P"])
+        per = Rg // world
+
+        def digest(smp, lo, n):
+            t = smp.traces(pos_w=True, debug=False)
+            st = smp.get_state()
+            h = []
+            for k in range(0, n, per):
+                m = hashlib.sha256()
+                for a in (t["pos_w"][k:k + per], t["lik_prop"][k:k + per], t["accept_list"][k:k + per], st["w"][k:k + per], st["eta"][k:k + per]):
+                    m.update(np.ascontiguousarray(a).tobytes())
+                h.append(m.hexdigest())
+            return h
+
+        smp, ladder = self.make(w, 0, S, w0=w0[rank * per:(rank + 1) * per])
+        lx, z, z_eta, u = smp.generate_draws(0, n_steps)
+        ladder.run(None, SimpleNamespace(lx=lx, z=z, z_eta=z_eta, u=u), u_swap)
+        mine = digest(smp, rank * per, per)
+        ns, tot, sw = smp.swap_stats()
+        smp.close()
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        out = None
+        if rank == 0:
+            one, _ = self.make(w, 0, S, w0=w0, distributed=False)
+            lx, z, z_eta, u = one.generate_draws(0, n_steps)
+            one.replay(SimpleNamespace(lx=lx, z=z, z_eta=z_eta, u=u, u_swap=u_swap))
+            ref = digest(one, 0, Rg)
+            ns1, tot1, sw1 = one.swap_stats()
+            one.close()
+            got = [h for hs in allh for h in hs]
+            crossings = [int(sw[:, g * per - 1].sum()) for g in range(1, world)]
+            out = {"ok": bool(got == ref and (ns, tot) == (ns1, tot1) and np.array_equal(sw, sw1)),
+                   "temperatures_per_rank": per, "ranks": world, "steps": n_steps, "swap_rounds": int(sw.shape[0]),
+                   "swaps": int(ns), "swap_proposals": int(tot), "swaps_across_each_rank_boundary": crossings,
+                   "compared": "sha256 of pos_w, lik_prop, accept_list, final w and eta of every rank's block vs the same block of a single-GPU run of all %d temperatures" % Rg}
+        self.barrier()
+        return out
+
+
+def run_b200_arm(args, w, rank, world, local_rank):
+    b = Bench(args, rank, world, local_rank)
+    K, W = args.steps, args.warmup
+    head = b.measure(w, K, W, with_cpu=(world == 1 and not args.no_cpu_baseline), with_pipeline=True)
+    sub = {}
+    parity = None
+    if args.sub and args.workload == "synth_ts":
+        # ---- the same ladder in the regime the reference runs in (BASELINE.md: acceptance 12-30 %)
+        st = b.burn_in(w)
+        rec = b.measure(w, K, W, with_cpu=False, burn=st)
+        if rec is not None:
+            rec["burn_in"] = {"steps": BURN_IN_STEPS, "seconds": st["burn_seconds"], "acceptance_rate_last_200_steps": st["acceptance_last_200"],
+                              "swap_rate": st["swap_rate"]}
+            sub["burned_in"] = rec
+        # ---- BASELINE configs[3] as worded: ONE ladder of 1024 temperatures split over the N GPUs (strong scaling)
+        if world > 1 and 1024 % world == 0:
+            ws = load_workload("synth_ts", world, 1024 // world)
+            rec = b.measure(ws, K, W, with_cpu=False)
+            if rec is not None:
+                rec["scaling"] = "strong"
+                sub["strong_1024"] = rec
+            parity = b.multi_gpu_parity(w)
+        elif world == 1:
+            sub["strong_1024"] = {"same_as": "the headline line: at one GPU the 1024-temperature ladder of configs[3] is the weak-scaling workload"}
+        # ---- the reference's own run (the >= 100x target) and the tcgen05 configuration: single-GPU workloads
+        if world == 1:
+            ws = load_workload("sunspot", 1)
+            sub["sunspot"] = b.measure(ws, 80, 20, with_cpu=not args.no_cpu_baseline)
+            wp = load_workload("pendigit", 1)
+            sub["pendigit"] = b.measure(wp, max(3, min(K, 10)), 3, with_cpu=not args.no_cpu_baseline)
     if rank == 0:
-        n_rows = smp.step
-        smp.trace_summary(1, n_rows)
-        got = []
-        for _ in range(3):
-            flush.fill_(1)
-            torch.cuda.synchronize(dev)
-            got.append(smp.trace_summary(1, n_rows))
-        ms = float(np.mean([g["kernel_ms"] for g in got]))
-        pipe = {"kernel": "trace_summary_kernel<2>", "bound": "hbm", "rows_pooled": int(got[0]["n"]),
-                "algorithmic_bytes_per_launch": int(got[0]["bytes_read"]), "launch_ms": ms,
-                "achieved": got[0]["bytes_read"] / (ms * 1e-3) / 1e9, "unit": "GB/s"}
-    smp.close()
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant (only) kernel in the timed region: chain_kernel
-    rw, lg = algorithmic_work(w)
-    Rg = w["R_global"]
-    flops = Rg * (n_lg * lg["flop"] + n_rw * rw["flop"])
-    byts = Rg * (n_lg * lg["bytes"] + n_rw * rw["bytes"])
-    sfu = Rg * (n_lg * lg["sfu"] + n_rw * rw["sfu"])
-    sec = total_ms * 1e-3
-    peaks = measure_peaks(local_rank) or {}
-    mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_peak, hbm_src = 6650.0, "fallback"
-    if os.path.exists(mp_path):
-        hbm_peak, hbm_src = float(json.load(open(mp_path))["hbm_gbs"]), "measured"
-    fp32_peak = peaks.get("fp32_tflops")
-    ach_tflops = flops / sec / 1e12 / world                 # per GPU
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(w["name"])
-    fp32_roof = {"kernel": "chain_kernel<%d,%d,%d>" % w["topology"], "bound": "fp32-issue (not HBM: datasets are SMEM/L2 resident, SURVEY 8d)",
-                 "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (ach_tflops / fp32_peak) if fp32_peak else None,
-                 "peak_source": "measured in this run (csrc/ptfnn_peaks.cu FMA microbenchmark)", "traffic": traffic,
-                 "algorithmic_flop_per_launch": flops / K / world, "launch_ms": total_ms / K}
-    # the bounding on-chip resources are FP32 issue and the MUFU (XU) pipe; the one with the larger
-    # fraction is reported as THE roofline (ncu agrees: XU is the busiest pipe of the bench launch), the other in roofline_alt
-    mufu_peak = peaks.get("mufu_gops")
-    ach_mufu = sfu / sec / 1e9 / world
-    mufu_roof = {"kernel": "chain_kernel<%d,%d,%d>" % w["topology"], "bound": "MUFU / XU pipe: 2 transcendental ops per sigmoid (not HBM: datasets are SMEM/L2 resident, SURVEY 8d)",
-                 "achieved": ach_mufu / 1e3, "peak": (mufu_peak / 1e3) if mufu_peak else None, "unit": "Tops/s",
-                 "frac": (ach_mufu / mufu_peak) if mufu_peak else None,
-                 "peak_source": "measured in this run (csrc/ptfnn_peaks.cu MUFU microbenchmark: 16 lanes/clk/SM)", "traffic": traffic,
-                 "algorithmic_sfu_ops_per_launch": sfu / K / world, "launch_ms": total_ms / K}
-    use_mufu = bool(mufu_roof["frac"] and fp32_roof["frac"] and mufu_roof["frac"] > fp32_roof["frac"])
-    roofline = mufu_roof if use_mufu else fp32_roof
-    roofline_alt = {
-        "hbm": {"bound": "hbm", "achieved": byts / sec / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
-                "frac": byts / sec / 1e9 / world / hbm_peak, "peak_source": hbm_src + " (MEASURED_PEAKS.json)" if hbm_src == "measured" else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": byts / K / world},
-        ("fp32_issue" if use_mufu else "mufu"): (fp32_roof if use_mufu else mufu_roof),
-        "smem_broadcast": {"achieved_gbs": byts / sec / 1e9 / world, "peak_gbs": peaks.get("smem_gbs")},
-    }
-    # The Langevin steps are a serial recurrence over the training rows: their bound is the
-    # dependent-issue latency of one row, not a throughput peak.  floor = sum of the measured latencies of the
-    # instructions on the chain (tools/latency_probe.cu); the upper bound charges the WHOLE
-    # timed region (random-walk steps included) to the serial rows.
-    chain_floor = {(4, 64, 1): 176, (4, 5, 1): 138, (4, 10, 1): 150, (16, 256, 10): 346}.get(tuple(w["topology"]))
-    serial_rows = n_lg * 2 * w["train"].shape[0]
-    if chain_floor and serial_rows and clk and clk.get("sm_mhz"):
-        cyc = sec / serial_rows * clk["sm_mhz"] * 1e6
-        roofline_alt["serial_chain"] = {"bound": "dependent-issue latency of the SGD recurrence (one chain per temperature)",
-                                        "serial_rows_per_temperature": serial_rows, "cycles_per_row_upper_bound": cyc,
-                                        "floor_cycles_per_row": chain_floor, "frac": chain_floor / cyc}
-
-    # ---- CPU baseline on this box's host cores (bounded sample, N = 1 only)
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline
-        cores = cpu_baseline.host_cores()
-        n_procs, pattern = cpu_sample_plan(w, cores)
-        wall, units = cpu_sample(w, n_procs, pattern)
-        cpu = {"value": units / wall, "unit": "replica-steps/s", "cores": cores, "kind": "port",
-               "sample": "%d replica processes x %d steps (LG/RW alternating = l_prob 0.5) of the same workload, %.1f s wall" % (n_procs, len(pattern), wall)}
-
-    line = {"metric": "replica_mcmc_steps_per_sec", "value": value, "unit": "replica-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic" if w["name"] != "sunspot" else "Sunspot (reference dataset), random-init weights",
-            "config": {"workload": w["desc"], "sampler": "Langevin PT, l_prob %.2f, lr %g, swap_interval %d, maxtemp %s" % (w["l_prob"], w["learn_rate"], si, w["maxtemp"]),
-                       "replicas_total": Rg, "replica_steps_per_bench_step": units_per_step,
-                       "langevin_steps_in_timed_region": n_lg, "random_walk_steps_in_timed_region": n_rw,
-                       "memoize_gradient": 0, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": "ladder partitioned over %d GPU(s), swap rounds in-kernel over NVLink peer memory" % world if world > 1 else "1 GPU, in-kernel swap round"},
-            "value_memoized": value_memo, "ms_per_step_memoized": total_ms_memo / K,
-            "e2e": {"value": e2e_value, "unit": "replica-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": K, "clocks": clk, "roofline": roofline, "roofline_alt": roofline_alt,
-            "cpu_baseline": cpu, "peaks_measured": peaks, "step_ms": ms_list}
-    if pipe:
-        pipe.update(peak=hbm_peak, frac=pipe["achieved"] / hbm_peak, peak_source=roofline_alt["hbm"]["peak_source"])
-        line["result_pipeline"] = pipe
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+        line = {"metric": "replica_mcmc_steps_per_sec", "value": head["value"], "unit": "replica-steps/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f32", "data": head["data"], "config": head["config"],
+                "timed_region": head["timed_region"],
+                "parallelism": "ladder partitioned over %d GPU(s), swap rounds in-kernel over NVLink peer memory" % world if world > 1 else "1 GPU, in-kernel swap round",
+                "value_memoized": head["value_memoized"], "ms_per_step_memoized": head["ms_per_step_memoized"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": head["roofline"],
+                "roofline_alt": head["roofline_alt"], "cpu_baseline": head.get("cpu_baseline"), "peaks_measured": b.peaks,
+                "step_ms": head["step_ms"]}
+        if "result_pipeline" in head:
+            line["result_pipeline"] = head["result_pipeline"]
+        if sub:
+            line["sub"] = sub
+        if parity is not None:
+            line["multi_gpu_parity"] = parity["ok"]
+            line["multi_gpu_parity_detail"] = parity
+        print(json.dumps(line))
+    if b.dist is not None:
+        b.dist.destroy_process_group()
 
 
 def main():
@@ -423,6 +615,7 @@ def main():
                          "(BASELINE configs[3] as worded: 1024 over 1/2/4/8); default is weak scaling, 1024 per GPU")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", dest="sub", action="store_false", help="only the headline measurement (no sub-records, no parity replay)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -436,6 +629,8 @@ def main():
         if args.ladder_total % n_dev:
             raise SystemExit("--ladder-total %d does not split evenly over %d GPUs" % (args.ladder_total, n_dev))
         args.replicas_per_gpu, args.scaling = args.ladder_total // n_dev, "strong"
+    if args.replicas_per_gpu or args.ladder_total:
+        args.sub = False
     w = load_workload(args.workload, n_dev, args.replicas_per_gpu)
     if args.impl == "reference":
         if rank == 0:

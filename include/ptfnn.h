@@ -177,6 +177,20 @@ int ptfnn_generate_draws(ptfnn_sampler *s, int32_t i0, int32_t n, float *lx, flo
 int ptfnn_swap_uniforms(const ptfnn_sampler *s, int32_t round, float *u_row /* [n_replicas_global-1] */);
 
 int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, const ptfnn_traces *out);
+/* The same rows without stalling the sampler: ptfnn_traces_begin queues the device -> host copies of rows
+ * [first, first+count) behind everything launched so far, on a copy stream of the handle's own, into one of two
+ * page-locked staging slots, and returns at once; later launches on the handle's stream overlap with the copy.
+ * ptfnn_traces_end waits for that copy only and hands out views INTO the slot (device dtypes: float32 weights,
+ * float64 series, int32 counts -- nothing is widened or copied again).  A view stays valid until the second next
+ * ptfnn_traces_begin.  This is the read-back a streaming consumer (file writer, monitor) of a long run uses. */
+typedef struct ptfnn_trace_views {
+    const float *pos_w;          /* [n_replicas, count, P] or NULL */
+    const double *lik_prop, *rmse_train, *rmse_test, *acc_train, *acc_test;   /* [n_replicas, count] */
+    const int32_t *accept_list;  /* [n_replicas, count] */
+    int32_t first, count;
+} ptfnn_trace_views;
+int ptfnn_traces_begin(ptfnn_sampler *s, int32_t first, int32_t count, int32_t with_pos_w, int32_t *ticket);
+int ptfnn_traces_end(ptfnn_sampler *s, int32_t ticket, ptfnn_trace_views *out);
 /* num_swap / total_swap_proposals (R:501-502, R:769) and the per-pair decisions of every round */
 int ptfnn_get_swap_stats(ptfnn_sampler *s, int64_t *num_swap, int64_t *total_swap_proposals,
                          uint8_t *swapped /* [max_rounds, n_replicas_global-1] or NULL */, int32_t max_rounds);

@@ -197,6 +197,26 @@ def swap_sweep(lhood, u_row):
     return src, swapped
 
 
+def swap_sweep_ratio_temperature(lhood, u_row, temperatures):
+    """The same sweep under the swap rule of the reference's drafts (Misc/ldpt_fnn_multi_fixed.py:505-531):
+    swap_proposal = (lhood1 / [1 if lhood2 == 0 else lhood2]) * (1/T1 * 1/T2), swap when u < swap_proposal; the
+    temperature field travels with its vector (param[num_param + 2]).  No published result uses it."""
+    lhood, temps = list(lhood), list(temperatures)
+    src = list(range(len(lhood)))
+    swapped = []
+    for k in range(len(lhood) - 1):
+        l1, l2, t1, t2 = lhood[k], lhood[k + 1], temps[k], temps[k + 1]
+        with np.errstate(all="ignore"):
+            p = (np.float64(l1) / (1.0 if l2 == 0 else np.float64(l2))) * (1.0 / t1 * 1.0 / t2)
+        s = bool(u_row[k] < p)
+        if s:
+            lhood[k], lhood[k + 1] = l2, l1
+            temps[k], temps[k + 1] = t2, t1
+            src[k], src[k + 1] = src[k + 1], src[k]
+        swapped.append(s)
+    return src, swapped
+
+
 # --------------------------------------------------------------------------------------
 # configuration, draws, traces
 # --------------------------------------------------------------------------------------

@@ -20,13 +20,14 @@ SWAP_RULE_AUTO, SWAP_RULE_AFTER_I, SWAP_RULE_BEFORE_I1 = -1, 0, 1
 SWAP_KIND_REFERENCE, SWAP_KIND_RATIO_TEMPERATURE = 0, 1      # R:674 | Misc/ldpt_fnn_multi_fixed.py:520 (opt-in)
 ABI_VERSION = 2
 PEER_HANDLE_BYTES = 64       # cudaIpcMemHandle_t
+MAX_HIDDEN = 512             # widest hidden layer a specialisation is generated for
 
 # every symbol include/ptfnn.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
     "ptfnn_abi_version", "ptfnn_build_info", "ptfnn_device_count", "ptfnn_default_config", "ptfnn_last_error",
     "ptfnn_create", "ptfnn_destroy", "ptfnn_set_stream", "ptfnn_set_data", "ptfnn_init_chains",
     "ptfnn_set_state", "ptfnn_get_state", "ptfnn_get_step", "ptfnn_run", "ptfnn_replay", "ptfnn_sync",
-    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_get_swap_stats", "ptfnn_trace_summary", "ptfnn_predictive_summary", "ptfnn_predictive_bands",
+    "ptfnn_generate_draws", "ptfnn_swap_uniforms", "ptfnn_get_traces", "ptfnn_traces_begin", "ptfnn_traces_end", "ptfnn_get_swap_stats", "ptfnn_trace_summary", "ptfnn_predictive_summary", "ptfnn_predictive_bands",
     "ptfnn_swap_pending", "ptfnn_swap_export", "ptfnn_swap_plan", "ptfnn_swap_apply",
     "ptfnn_peer_export", "ptfnn_peer_connect", "ptfnn_has_topology", "ptfnn_register_kernels",
     "ptfnn_op_forward_pass", "ptfnn_op_evaluate_proposal", "ptfnn_op_langevin_gradient", "ptfnn_time_langevin_gradient", "ptfnn_op_likelihood", "ptfnn_op_prior",
@@ -58,6 +59,12 @@ class Draws(C.Structure):
 class Traces(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("pos_w", "lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test",
                                           "accept_list", "prior_prop", "diff_prop", "mh_prob", "accepted")]
+
+
+class TraceViews(C.Structure):
+    _fields_ = [("pos_w", C.POINTER(C.c_float))] + \
+        [(n, C.POINTER(C.c_double)) for n in ("lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test")] + \
+        [("accept_list", C.POINTER(C.c_int32)), ("first", C.c_int32), ("count", C.c_int32)]
 
 
 class Summary(C.Structure):
@@ -113,7 +120,7 @@ def ensure_topology(task, topology, verbose=False):
     """The kernels are compile-time specialisations of [I, H, O] (csrc/ptfnn_topologies.h lists the ones
     built into libptfnn.so).  Any other topology is compiled here, once, from the same sources into
     csrc/build/jit/libptfnn_topo_<name>.so (nvcc, sm_100a, ~20 s; cached on disk) and registered with
-    the library.  Needs nvcc; hidden layers wider than 256 units are not supported."""
+    the library.  Needs nvcc; hidden layers wider than MAX_HIDDEN units are not supported."""
     import hashlib
     import subprocess
     import uuid
@@ -124,10 +131,11 @@ def ensure_topology(task, topology, verbose=False):
         return
     if task == TASK_REGRESSION and O != 1:
         raise PtfnnError(E_UNSUPPORTED, "regression needs one output (R:132)")
-    if H > 256 or min(I, H, O) < 1:
-        raise PtfnnError(E_UNSUPPORTED, "no specialisation for topology [%d,%d,%d] (hidden layers up to 256 units)" % (I, H, O))
+    if H > MAX_HIDDEN or O > 32 or min(I, H, O) < 1:
+        raise PtfnnError(E_UNSUPPORTED, "no specialisation for topology [%d,%d,%d] (hidden layers up to %d units, up to 32 outputs: "
+                                        "the weights of a layer live in the registers of one CTA)" % (I, H, O, MAX_HIDDEN))
     name = "jit_%s_%d_%d_%d" % ("reg" if task == TASK_REGRESSION else "cls", I, H, O)
-    nt = 128 if H <= 128 else 256                      # wide nets: one thread per hidden unit (sgd_pass_team)
+    nt = 128 if H <= 256 else 256                      # wide nets: a team of threads, ceil(H / nt) hidden units each (sgd_pass_team)
     minb = 2 if (H > 32 or I > 16) else 4
     csrc = os.path.dirname(LIB_PATH)
     out_dir = os.path.join(csrc, "build", "jit")

@@ -111,6 +111,12 @@ struct ptfnn_sampler {
     std::string err;
     void *pinned = nullptr;           // host staging buffer of get_traces (page-locked, grows on demand)
     size_t pinned_bytes = 0;
+    // overlapped read-back (ptfnn_traces_begin / _end): two page-locked slots filled on a copy stream
+    struct FetchSlot { void *buf = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; size_t off[7] = {}; bool has_w = false; int first = 0, count = 0; bool busy = false; };
+    FetchSlot slot[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr;
+    unsigned int fetch_seq = 0;
 
     bool have_data = false, have_state = false, summary_smem_opted = false;
     int n_train = 0, n_test = 0;
@@ -144,6 +150,15 @@ struct ptfnn_sampler {
     void release_all() {
         if (pinned) cudaFreeHost(pinned);
         pinned = nullptr; pinned_bytes = 0;
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        for (auto &f : slot) {
+            if (f.buf) cudaFreeHost(f.buf);
+            if (f.done) cudaEventDestroy(f.done);
+            f = FetchSlot();
+        }
+        if (ev_compute) cudaEventDestroy(ev_compute);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        ev_compute = nullptr; copy_stream = nullptr;
         train_x.release(); train_y.release(); test_x.release(); test_y.release(); a_train.release(); a_test.release(); temperature.release();
         w.release(); gd_cache.release(); pgd_buf.release(); pos_w.release(); pub_rows.release();
         eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
@@ -850,6 +865,68 @@ extern "C" int ptfnn_get_traces(ptfnn_sampler *s, int32_t first, int32_t count, 
     if ((rc = run_fetch(s, f, first, count))) return rc;
     if (t->accepted)
         CU_TRY(s, cudaMemcpy2D(t->accepted, count, s->dbg_acc.p + first, s->cfg.samples, count, s->cfg.n_replicas, cudaMemcpyDeviceToHost));
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_traces_begin(ptfnn_sampler *s, int32_t first, int32_t count, int32_t with_pos_w, int32_t *ticket) {
+    if (!s || !ticket) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (!s->have_state) return fail(s, PTFNN_E_STATE, "ptfnn_init_chains must come first");
+    if (first < 0 || count < 1 || first + count > s->cfg.samples) return fail(s, PTFNN_E_INVALID, "rows [%d,%d) outside [0,%d)", first, first + count, s->cfg.samples);
+    if (s->device_failed) return fail(s, PTFNN_E_CUDA, "%s", kDeviceFailedMsg);
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    if (!s->copy_stream) {
+        CU_TRY(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(s, cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming));
+    }
+    const int k = (int)(s->fetch_seq & 1u);
+    ptfnn_sampler::FetchSlot &f = s->slot[k];
+    if (!f.done) CU_TRY(s, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    if (f.busy) CU_TRY(s, cudaEventSynchronize(f.done));          // the copy that used this slot two tickets ago
+    const size_t R = s->cfg.n_replicas, S = s->cfg.samples, P = s->P;
+    const size_t rc = R * (size_t)count;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    f.off[0] = take(with_pos_w ? rc * P * 4 : 0);
+    for (int q = 1; q <= 5; ++q) f.off[q] = take(rc * 8);
+    f.off[6] = take(rc * 4);
+    if (o > f.bytes) {
+        if (f.buf) cudaFreeHost(f.buf);
+        f.buf = nullptr; f.bytes = 0;
+        CU_TRY(s, cudaHostAlloc(&f.buf, o, cudaHostAllocDefault));
+        f.bytes = o;
+    }
+    CU_TRY(s, cudaEventRecord(s->ev_compute, s->stream));         // everything launched so far ...
+    CU_TRY(s, cudaStreamWaitEvent(s->copy_stream, s->ev_compute, 0));   // ... precedes the copies; nothing later does
+    char *base = (char *)f.buf;
+    auto copy = [&](size_t off, const void *dev, size_t elem, size_t row_elems) {
+        const size_t w = (size_t)count * row_elems * elem;
+        return cudaMemcpy2DAsync(base + off, w, (const char *)dev + (size_t)first * row_elems * elem, S * row_elems * elem, w, R,
+                                 cudaMemcpyDeviceToHost, s->copy_stream);
+    };
+    if (with_pos_w) CU_TRY(s, copy(f.off[0], s->pos_w.p, 4, P));
+    CU_TRY(s, copy(f.off[1], s->lik_prop.p, 8, 1)); CU_TRY(s, copy(f.off[2], s->rmse_tr.p, 8, 1)); CU_TRY(s, copy(f.off[3], s->rmse_te.p, 8, 1));
+    CU_TRY(s, copy(f.off[4], s->acc_tr.p, 8, 1)); CU_TRY(s, copy(f.off[5], s->acc_te.p, 8, 1)); CU_TRY(s, copy(f.off[6], s->accept_list.p, 4, 1));
+    CU_TRY(s, cudaEventRecord(f.done, s->copy_stream));
+    f.has_w = with_pos_w != 0; f.first = first; f.count = count; f.busy = true;
+    *ticket = (int32_t)s->fetch_seq;
+    s->fetch_seq += 1;
+    return PTFNN_OK;
+}
+
+extern "C" int ptfnn_traces_end(ptfnn_sampler *s, int32_t ticket, ptfnn_trace_views *out) {
+    if (!s || !out) return fail(s, PTFNN_E_INVALID, "null argument");
+    if (ticket < 0 || (unsigned int)ticket >= s->fetch_seq || (unsigned int)ticket + 2u < s->fetch_seq)
+        return fail(s, PTFNN_E_STATE, "ticket %d is not one of the two most recent ptfnn_traces_begin calls", ticket);
+    CU_TRY(s, cudaSetDevice(s->cfg.device));
+    ptfnn_sampler::FetchSlot &f = s->slot[ticket & 1];
+    CU_TRY(s, cudaEventSynchronize(f.done));
+    f.busy = false;
+    const char *base = (const char *)f.buf;
+    out->pos_w = f.has_w ? (const float *)(base + f.off[0]) : nullptr;
+    out->lik_prop = (const double *)(base + f.off[1]); out->rmse_train = (const double *)(base + f.off[2]);
+    out->rmse_test = (const double *)(base + f.off[3]); out->acc_train = (const double *)(base + f.off[4]);
+    out->acc_test = (const double *)(base + f.off[5]); out->accept_list = (const int32_t *)(base + f.off[6]);
+    out->first = f.first; out->count = f.count;
     return PTFNN_OK;
 }
 

@@ -55,6 +55,15 @@ constexpr float kMagic = 12582912.0f;            // 1.5 * 2^23: float(kMagic + v
 constexpr int kMagicSum32 = 0x68000000;          // 32 * bits(kMagic) mod 2^32: what 32 lanes of bare magic add up to
 constexpr int kGuardRows = 30;                   // rows covered by one choice of the fixed-point scale
 
+// Packed pairs kept in 64-bit registers for the whole hidden-unit loop (building the pair from two
+// scalar registers costs a MOV each time, which is what the loop is trying to get rid of).
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // elementwise helpers over the HPL hidden units of a lane; adjacent pairs go through f32x2
 template <int N>
 __device__ __forceinline__ void vfma(float (&r)[N], const float (&a)[N], const float (&b)[N], const float (&c)[N]) {
@@ -457,89 +466,85 @@ __device__ __forceinline__ void sgd_pass(const float *w_in, float *w_out, const 
 }
 
 // ==========================================================================================
-// K2 (wide hidden layers): the serial recurrence run by a TEAM of NT threads.  With H = 256 one
-// warp would need ~216 live registers per lane (8 hidden units x (I + O + 1)) and spills; here
-// thread t owns hidden unit t (row view: W1 column, B1, W2 row in registers) and the output layer is
-// evaluated in a column view: output o belongs to warp o % NWT, which keeps that W2 column in
-// registers (H/32 per lane), reads the hidden activations from shared memory and sums across lanes
-// on the integer REDUX unit (block fixed point on the magic constant, as in SgdWarp).  Two team
-// barriers per row (hid -> out_delta -> hid_delta).  Both views of W2 receive the same update
-// (R:67-69), so they stay bit-identical.
+// K2 (wide hidden layers): the serial recurrence run by a TEAM of NTT threads (H > 64).
 //
-// The first version of this kernel issued 240 instructions per thread and row -- 480 issue cycles
-// per row and CTA, i.e. it was bound by the issue slots, not by the chain, and two co-resident
-// CTAs simply took twice as long.  This version: packed FFMA2 dot products / rank-1 updates over
-// the inputs and outputs of a thread, look-ahead pre-activation in the ex2 domain (one FFMA on
-// the chain), x_next.x + 1 computed once per 128-row tile by the whole team instead of by every
-// thread and row, rows unrolled by two (no register rotation).
+// One warp cannot hold a 256-wide layer (8 hidden units x (I + O + 1) weights per lane spill), so the
+// recurrence of SgdWarp is spread over NTT = 128 threads, UPT = ceil(H / NTT) hidden units per thread, ROW
+// VIEW ONLY: thread t keeps the W1 columns, B1 and the W2 rows of its units in registers.  Per row:
+//
+//     hid = sigmoid(zs)                                   per unit               (EX2, FADD, RCP)
+//     partial[o] = sum over the thread's units hid W2q    packed over o pairs    (FFMA2 on the magic constant)
+//     REDUX.SUM per output                                O per warp, pipelined  (block fixed point, as SgdWarp)
+//     lane 0 -> s_part[row parity][warp][o];  ONE team barrier
+//     lane o of EVERY warp: sum of the NWT warp sums (integer: exact, order free) -> out, out_delta, lr out_delta,
+//              B2 -- redundantly per warp, so the broadcast of lr out_delta[0..O) to the lanes is warp-local
+//              (STS, __syncwarp, LDS.128) and needs no second team barrier
+//     lr hid_delta = hid (1 - hid) sum_o lr out_delta[o] W2[.][o]   with the pre-update W2 (R:59)
+//     zs(next row) = stale pre-activation + lr hid_delta * -log2e (x_next . x + 1)       (one FFMA on the chain)
+//     W2 += hid (x) lr out_delta (needed by the next row's partial sums); W1 / B1 of THIS row are applied in the
+//     shadow of the NEXT row's REDUX latency, followed by the stale pre-activation of the row after it.
+//
+// Round 1's team kept W2 in a second, column-major view (one warp per output) and needed two barriers per row:
+// 138 instructions per thread and row on 256 threads, 1137 cycles per row with two temperatures per SM.  Here:
+// one view, one barrier, ~125 instructions per thread and row on 128 threads.
 // ==========================================================================================
 template <int H>
 struct UseSgdTeam {
     static constexpr bool value = H > 64;
 };
+constexpr int kTeamThreads = 128;
 __host__ __device__ constexpr int team_smem_floats(int H, int O) {
-    return ((H + 31) / 32) * 32 + ((O + 3) & ~3) + kTileRows + 4;  // s_hid, s_od, s_c, two mbarriers
+    // s_part [2][8 warps][OP] (int), s_od [8][OP], s_max [8], s_c [kTileRows]
+    return 3 * 8 * ((O + 3) & ~3) + 8 + kTileRows + 4;
 }
 
-// init + sum_i a[i] * b[i] through two packed partial sums
-template <int N>
-__device__ __forceinline__ float vdot(const float (&a)[N], const float (&b)[N], float init) {
-    float2 acc = make_float2(init, 0.0f);
-#pragma unroll
-    for (int k = 0; k + 1 < N; k += 2) acc = __ffma2_rn(make_float2(a[k], a[k + 1]), make_float2(b[k], b[k + 1]), acc);
-    float r = acc.x + acc.y;
-    if (N & 1) r = fmaf(a[N - 1], b[N - 1], r);
-    return r;
+template <int NTT>
+__device__ __forceinline__ void team_bar() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
 }
 
-#ifdef PTFNN_TEAM_TRACE     // measurement builds only (tools/team_trace.cu): per-phase clock stamps of a few rows
-__device__ long long g_team_trace[8][16][8];
-#define TEAM_STAMP(k) do { if (lane == 0 && trace_row >= 0 && trace_row < 16) g_team_trace[warp][trace_row][k] = clock64(); } while (0)
-#else
-#define TEAM_STAMP(k) do { } while (0)
-#endif
-
-template <int I, int H, int O, int TASK, int NT>
+template <int I, int H, int O, int TASK, int NTT>
 __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, const DataView &d, bool staged, float lr,
                                               SgdStream &st, float *s_team) {
     constexpr int IP = IPad<I>::value;
     constexpr uint32_t RBY = IP * 4u;
-    constexpr int NWT = NT / 32;
-    constexpr int OPW = (O + NWT - 1) / NWT;      // outputs per warp (column view)
-    constexpr int HC = (H + 31) / 32;             // hidden units per lane in the column view
-    constexpr int OP = (O + 3) & ~3;
+    constexpr int NWT = NTT / 32;
+    constexpr int UPT = (H + NTT - 1) / NTT;      // hidden units per thread: h = tid + NTT * k
+    constexpr int OP = (O + 3) & ~3;              // outputs padded to whole LDS.128 / f32x2 pairs
+    constexpr int OJ = OP / 2;
     constexpr int oW2 = I * H, oB1 = I * H + H * O, oB2 = I * H + H * O + H;
-    static_assert(H <= NT && NT % 32 == 0 && HC * 32 <= NT, "one hidden unit per thread");
-    float *s_hid = s_team;                        // [HC * 32]
-    float *s_od = s_hid + HC * 32;                // [OP]
-    float *s_c = s_od + OP;                       // [kTileRows]  x_{r+1}.x_r + 1 of the resident tile
+    static_assert(NTT % 32 == 0 && NWT <= 8 && O <= 32, "team geometry");
+    int *s_part = reinterpret_cast<int *>(s_team);            // [2][NWT][OP]
+    float *s_od = s_team + 2 * 8 * OP;                        // [NWT][OP]  lr * out_delta of the row, per warp
+    unsigned int *s_max = reinterpret_cast<unsigned int *>(s_od + 8 * OP);   // [NWT]
+    float *s_c = reinterpret_cast<float *>(s_max + 8);        // [kTileRows]  x_{r+1}.x_r + 1 of the resident tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int n = d.n;
     asm volatile("" : "+r"(n));                   // keep loop invariants in registers (no LDC in the row loop)
     asm volatile("" : "+f"(lr));
-    const bool act = tid < H;
 
-    // ---- row view (hidden unit tid) and column view (outputs warp, warp + NWT, ...)
-    float w1[I], b1, w2r[O];
-    float w2c[OPW][HC], b2[OPW], b2l[OPW];
+    // ---- weights of this thread's units (layout a1, R:80-90)
+    float w1[I][UPT], b1[UPT];
+    f2_t w2[UPT][OJ], w2q[UPT][OJ];               // W2 rows, outputs in pairs; w2q = fscale * W2 (a power of two: exact)
+    float b2 = 0.0f, b2l = 0.0f;                  // lane o of every warp: B2[o] (identical updates in every warp)
 #pragma unroll
-    for (int i = 0; i < I; ++i) w1[i] = act ? w_in[i * H + tid] : 0.0f;
+    for (int k = 0; k < UPT; ++k) {
+        const int h = tid + NTT * k;
+        const bool act = h < H;
 #pragma unroll
-    for (int o = 0; o < O; ++o) w2r[o] = act ? w_in[oW2 + tid * O + o] : 0.0f;
-    b1 = act ? w_in[oB1 + tid] : 1.0e4f;          // no hidden unit: sigmoid = 0 exactly, every update an exact zero
+        for (int i = 0; i < I; ++i) w1[i][k] = act ? w_in[i * H + h] : 0.0f;
+        // no hidden unit: z = x.0 - 1e4 -> sigmoid = 0 exactly, so every update of the slot is an exact zero
+        b1[k] = act ? w_in[oB1 + h] : 1.0e4f;
 #pragma unroll
-    for (int j = 0; j < OPW; ++j) {
-        const int o = warp + NWT * j;
-#pragma unroll
-        for (int m = 0; m < HC; ++m) {
-            const int h = lane + 32 * m;
-            w2c[j][m] = (o < O && h < H) ? w_in[oW2 + h * O + o] : 0.0f;
+        for (int j = 0; j < OJ; ++j) {
+            const float a = (act && 2 * j < O) ? w_in[oW2 + h * O + 2 * j] : 0.0f;
+            const float b = (act && 2 * j + 1 < O) ? w_in[oW2 + h * O + 2 * j + 1] : 0.0f;
+            w2[k][j] = pack2(a, b);
+            w2q[k][j] = w2[k][j];
         }
-        b2[j] = o < O ? w_in[oB2 + o] : 0.0f;
-        b2l[j] = kL2E * b2[j];
     }
-    if (tid < OP) s_od[tid] = 0.0f;
-    __syncthreads();   // w_in may alias w_out; everybody has read its share
+    if (lane < O) { b2 = w_in[oB2 + lane]; b2l = kL2E * b2; }
+    team_bar<NTT>();   // w_in may alias w_out; everybody has read its share
 
     // ---- data addressing: staged copy or two TMA tiles
     const int ntiles = (n + kTileRows - 1) / kTileRows;
@@ -568,64 +573,81 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         else { mbar_wait(st.bar0, st.parity0); st.parity0 ^= 1u; }
     };
 
-    float zs;                 // ex2-domain pre-activation of this thread's hidden unit for the current row
+    float zs[UPT];            // ex2-domain pre-activations of this thread's units for the current row
     float fscale = 1.0f, cdec = -kL2E;
-    // fixed-point scale of this warp's output sums for the next `rows` rows (see SgdWarp::set_scale);
-    // non-finite weights poison the decode factor so that NaN propagates as in the reference
+    // Fixed-point scale of the output sums for the next `rows` rows (SgdWarp::set_scale, here agreed by the whole
+    // team: one extra barrier per kGuardRows rows).  |partial[o]| of a thread <= sum_k |W2[k][o]| because hid is in
+    // [0,1]; one row moves each |W2| entry by at most lr/4.  2^E > bound -> scale 2^(22-E): a thread's scaled partial
+    // stays below 2^22 (integer-exact on the magic constant) and 32 lanes x NWT warps of it cannot overflow int32.
+    // Non-finite weights poison the decode factor so that NaN propagates as in the reference.
     auto set_scale = [&](int rows) {
         float m = 0.0f;
 #pragma unroll
-        for (int j = 0; j < OPW; ++j) {
-            float a = 0.0f;
+        for (int j = 0; j < OJ; ++j) {
+            float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-            for (int k = 0; k < HC; ++k) a += fabsf(w2c[j][k]);
-            m = fmaxf(m, a);
-            m = (a != a) ? __int_as_float(0x7fc00000) : m;
+            for (int k = 0; k < UPT; ++k) {
+                float x0, x1;
+                unpack2(w2[k][j], x0, x1);
+                a0 += fabsf(x0); a1 += fabsf(x1);
+            }
+            m = fmaxf(m, fmaxf(a0, a1));
+            m = (a0 != a0 || a1 != a1) ? __int_as_float(0x7fc00000) : m;
         }
-        m = fmaxf(m + (float)(rows * HC) * 0.25f * fabsf(lr), 9.765625e-4f);
-        const unsigned int ef = __reduce_max_sync(0xffffffffu, __float_as_uint(m)) >> 23;
+        m = fmaxf(m + (float)(rows * UPT) * 0.25f * fabsf(lr), 9.765625e-4f);
+        const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));     // NaN / Inf bits compare high
+        if (lane == 0) s_max[warp] = wm;
+        team_bar<NTT>();
+        unsigned int mb = 0u;
+#pragma unroll
+        for (int w = 0; w < NWT; ++w) mb = max(mb, s_max[w]);
+        const unsigned int ef = mb >> 23;
         const bool ok = ef < 200u;
         const unsigned int sf = ok ? 275u - ef : 127u;
         fscale = __uint_as_float(sf << 23);
         cdec = ok ? -kL2E * __uint_as_float((254u - sf) << 23) : __int_as_float(0x7fc00000);
+        const f2_t fs2 = pack2(fscale, fscale);
+#pragma unroll
+        for (int k = 0; k < UPT; ++k)
+#pragma unroll
+            for (int j = 0; j < OJ; ++j) w2q[k][j] = mul2(w2[k][j], fs2);
     };
 
-    // Team barriers: BAR.SYNC on sm_100 blocks at the first instruction that touches barrier-protected
-    // state, not at issue, so register-only work placed right after a barrier (weight updates of the
-    // previous row, column-view updates, look-ahead) runs while the other warps arrive.  (mbarrier
-    // arrive / try_wait pairs were measured too: ~75 cycles per phase against ~30 for BAR.SYNC.)
-
-    // carried from one row to the next: what the deferred updates of the previous row need
-    float hid_p = 0.0f, lh_p = 0.0f, lo_p[O];
+    // carried from one row to the next: the W1 / B1 update of the previous row is applied in the next row
+    float lh_p[UPT];
 #pragma unroll
-    for (int o = 0; o < O; ++o) lo_p[o] = 0.0f;
+    for (int k = 0; k < UPT; ++k) lh_p[k] = 0.0f;
+    int par = 0;              // row parity: s_part is double buffered
 
     // One row.  pbuf holds the PREVIOUS row on entry (its W1 update is still pending) and the NEXT row
     // (look-ahead) on exit; cbuf is the current row (only the tile's last row needs it, for x_next.x + 1).
-    // The current row itself enters through zs (its pre-activation) and y.
+    // The current row itself enters through zs (its pre-activations) and y.
     auto row = [&](const bool boundary, float (&pbuf)[IP], const float (&cbuf)[IP], uint32_t y_addr, uint32_t xn_addr,
                    float c_in, bool has_next) {
         const float yv = lds_f32(y_addr);
-#ifdef PTFNN_TEAM_TRACE
-        const int trace_row = (int)((y_addr - yaddr(0)) / 4u) - 64;     // rows 64..79 of the first tile
-#endif
-        TEAM_STAMP(0);
-        // ---- A: hidden activation (R:52-53), published to the team
-        const float hid = rcp_ftz(1.0f + ex2_ftz(zs));
-        if (NT == HC * 32 || tid < HC * 32) s_hid[tid] = hid;
-        __syncthreads();
-        TEAM_STAMP(1);
-        // ---- deferred updates of the PREVIOUS row (off the chain; its hid_delta is already inside zs)
-        {
-            float xi[I];
+        // ---- hidden activations (R:52-53)
+        float hid[UPT];
 #pragma unroll
-            for (int i = 0; i < I; ++i) xi[i] = pbuf[i];
-            vfma_s<I>(w1, xi, lh_p, w1);                         // R:74-76
-            b1 -= lh_p;                                          // R:77-78
-            vfma_s<O>(w2r, lo_p, hid_p, w2r);                    // R:67-69
+        for (int k = 0; k < UPT; ++k) hid[k] = rcp_ftz(1.0f + ex2_ftz(zs[k]));
+        // ---- partial output sums on the magic constant, outputs in pairs; integer REDUX per output
+        int sraw[OP];
+#pragma unroll
+        for (int j = 0; j < OJ; ++j) {
+            f2_t a = pack2(kMagic, kMagic);
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) a = fma2(pack2(hid[k], hid[k]), w2q[k][j], a);
+            float a0, a1;
+            unpack2(a, a0, a1);
+            sraw[2 * j] = (2 * j < O) ? __reduce_add_sync(0xffffffffu, __float_as_int(a0)) : 0;
+            sraw[2 * j + 1] = (2 * j + 1 < O) ? __reduce_add_sync(0xffffffffu, __float_as_int(a1)) : 0;
         }
-        hid_p = hid;
-        // the look-ahead row takes the place of the row that has just been applied
+        // ---- in the shadow of the REDUX latency: W1 / B1 update of the PREVIOUS row (R:74-78) ...
+#pragma unroll
+        for (int i = 0; i < I; ++i) vfma_s<UPT>(w1[i], lh_p, pbuf[i], w1[i]);
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) b1[k] -= lh_p[k];
+        // ... then the look-ahead row takes its place: stale pre-activation of the next row, with the weights
+        // BEFORE this row's update (the previous row's has just been applied)
         float cr = c_in;
         if (boundary) {                               // literal at every call site: folded after inlining
             if (has_next) {
@@ -641,78 +663,80 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         } else {
             lds_row<IP>(xn_addr, pbuf);
         }
-        TEAM_STAMP(2);
-        // ---- B: column view -- all OPW outputs of the warp at once (unused slots have W2 = 0):
-        //      independent dot products, pipelined REDUX and sigmoids
-        float hv[HC];
+        float zn[UPT];
+        {
+            float t[UPT];
+            vmul_s<UPT>(t, b1, -1.0f);
 #pragma unroll
-        for (int m = 0; m < HC; ++m) hv[m] = s_hid[lane + 32 * m];
-        float lo_j[OPW];
-        int sraw[OPW];
-#pragma unroll
-        for (int j = 0; j < OPW; ++j) {
-            float2 a = make_float2(0.0f, 0.0f);               // even / odd hidden units: two chains in one FFMA2 stream
-#pragma unroll
-            for (int m = 0; m + 1 < HC; m += 2)
-                a = __ffma2_rn(make_float2(hv[m], hv[m + 1]), make_float2(w2c[j][m], w2c[j][m + 1]), a);
-            if (HC & 1) a.x = fmaf(hv[HC - 1], w2c[j][HC - 1], a.x);
-            sraw[j] = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(a.x + a.y, fscale, kMagic)));
+            for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], pbuf[i], t);
+            vmul_s<UPT>(zn, t, -kL2E);
         }
+        const float ccl = -kL2E * cr;
+        float g[UPT];
 #pragma unroll
-        for (int j = 0; j < OPW; ++j) {
-            const int o = warp + NWT * j;
-            const float t = fmaf((float)(int)((unsigned int)sraw[j] - (unsigned int)kMagicSum32), cdec, b2l[j]);
+        for (int k = 0; k < UPT; ++k) g[k] = fmaf(-hid[k], hid[k], hid[k]);         // hid (1 - hid)
+        // ---- publish this warp's sums; the ONE team barrier of the row
+        if (lane == 0) {
+            int4 *dst = reinterpret_cast<int4 *>(s_part + (par * 8 + warp) * OP);
+#pragma unroll
+            for (int q = 0; q < OP / 4; ++q) dst[q] = make_int4(sraw[4 * q], sraw[4 * q + 1], sraw[4 * q + 2], sraw[4 * q + 3]);
+        }
+        team_bar<NTT>();
+        // ---- lane o: output o (every warp computes all of them: the broadcast below stays inside the warp)
+        {
+            const int o = lane < OP ? lane : OP - 1;
+            unsigned int us = 0u;
+#pragma unroll
+            for (int w = 0; w < NWT; ++w) us += (unsigned int)s_part[(par * 8 + w) * OP + o];
+            const float t = fmaf((float)(int)(us - (unsigned int)NWT * (unsigned int)kMagicSum32), cdec, b2l);
             const float out = rcp_ftz(1.0f + ex2_ftz(t));                          // R:54-55
             float dd;
-            if constexpr (TASK == kTaskCls) dd = ((int)yv == o) ? 1.0f : 0.0f;     // C:73-75
-            else dd = yv;
-            const float q = lr * fmaf(-out, out, out);
-            const float lo = (o < O) ? (dd - out) * q : 0.0f;                      // lr * out_delta (R:58)
-            if (lane == 0 && o < O) s_od[o] = lo;
-            lo_j[j] = lo;
+            if constexpr (TASK == kTaskCls) dd = ((int)yv == lane) ? 1.0f : 0.0f;  // C:73-75 one-hot
+            else dd = yv;                                                          // O == 1 (R:132)
+            const float lo = (lane < O) ? lr * ((dd - out) * fmaf(-out, out, out)) : 0.0f;   // lr * out_delta (R:58)
+            b2 -= lo;                                                              // R:70-71
+            b2l = kL2E * b2;
+            if (lane < OP) s_od[warp * OP + lane] = lo;
         }
-        __syncthreads();
-        TEAM_STAMP(4);
-        // ---- column-view updates and this thread's look-ahead (off the chain)
-#pragma unroll
-        for (int j = 0; j < OPW; ++j) {
-            vfma_s<HC>(w2c[j], hv, lo_j[j], w2c[j]);                                  // R:67-69 (column view), FFMA2
-            b2[j] -= lo_j[j];                                                         // R:70-71
-            b2l[j] = kL2E * b2[j];
-        }
-        // stale pre-activation of the next row: the weights BEFORE this row's update, i.e. after the
-        // previous row's, which was applied above;  hid (1 - hid) W2 with the pre-update W2 (R:59)
-        float xni[I];
-#pragma unroll
-        for (int i = 0; i < I; ++i) xni[i] = pbuf[i];
-        const float zns = -kL2E * vdot<I>(xni, w1, -b1);
-        const float ccl = -kL2E * cr;
-        const float g = fmaf(-hid, hid, hid);
-        float gw[O];
-        vmul_s<O>(gw, w2r, g);
-        TEAM_STAMP(5);
-        // ---- C: row view -- lr * hid_delta; next row's pre-activation
-        float od[OP];
+        __syncwarp();
+        f2_t lo2[OJ];
 #pragma unroll
         for (int q = 0; q < OP / 4; ++q) {
-            const float4 v = reinterpret_cast<const float4 *>(s_od)[q];
-            od[4 * q] = v.x; od[4 * q + 1] = v.y; od[4 * q + 2] = v.z; od[4 * q + 3] = v.w;
+            const float4 v = reinterpret_cast<const float4 *>(s_od + warp * OP)[q];
+            lo2[2 * q] = pack2(v.x, v.y); lo2[2 * q + 1] = pack2(v.z, v.w);
         }
+        // ---- lr * hid_delta with the PRE-update W2 (R:59); next row's pre-activation (chain: one FFMA)
+        float lh[UPT];
 #pragma unroll
-        for (int o = 0; o < O; ++o) lo_p[o] = od[o];
-        lh_p = vdot<O>(lo_p, gw, 0.0f);                          // lr * hid_delta
-        zs = fmaf(lh_p, ccl, zns);                               // chain: lr*hd*(xn.x + 1) on top of the stale value
-        TEAM_STAMP(7);
+        for (int k = 0; k < UPT; ++k) {
+            f2_t a = mul2(w2[k][0], lo2[0]);
+#pragma unroll
+            for (int j = 1; j < OJ; ++j) a = fma2(w2[k][j], lo2[j], a);
+            float a0, a1;
+            unpack2(a, a0, a1);
+            lh[k] = (a0 + a1) * g[k];
+            zs[k] = fmaf(lh[k], ccl, zn[k]);
+            lh_p[k] = lh[k];
+        }
+        // ---- W2 += hid (x) lr out_delta (R:67-69) and its scaled copy: the next row's partial sums need them
+        const f2_t fs2 = pack2(fscale, fscale);
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+            const f2_t h2 = pack2(hid[k], hid[k]);
+#pragma unroll
+            for (int j = 0; j < OJ; ++j) {
+                w2[k][j] = fma2(h2, lo2[j], w2[k][j]);
+                w2q[k][j] = mul2(w2[k][j], fs2);
+            }
+        }
+        par ^= 1;
     };
-    // applies the updates still pending after the last row
+    // applies the W1 / B1 update still pending after the last row
     auto flush = [&](const float (&xp)[IP]) {
-        float xi[I];
 #pragma unroll
-        for (int i = 0; i < I; ++i) xi[i] = xp[i];
-        vfma_s<I>(w1, xi, lh_p, w1);
-        b1 -= lh_p;
-        vfma_s<O>(w2r, lo_p, hid_p, w2r);
-        lh_p = 0.0f; hid_p = 0.0f;
+        for (int i = 0; i < I; ++i) vfma_s<UPT>(w1[i], lh_p, xp[i], w1[i]);
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) { b1[k] -= lh_p[k]; lh_p[k] = 0.0f; }
     };
 
     // ---- rows.  Register buffers A / B alternate between "previous row" and "current row".
@@ -723,17 +747,18 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
     if (!staged) { issue(0); wait(0); }
     lds_row<IP>(xaddr(0), B);
     {
-        float xi[I];
+        float t[UPT];
+        vmul_s<UPT>(t, b1, -1.0f);
 #pragma unroll
-        for (int i = 0; i < I; ++i) xi[i] = B[i];
-        zs = -kL2E * vdot<I>(xi, w1, -b1);
+        for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], B[i], t);
+        vmul_s<UPT>(zs, t, -kL2E);
     }
     int r = 0;
     for (int t = 0; t < ntiles; ++t) {
         const int base = t * kTileRows;
         const int rows = min(kTileRows, n - base);
         // tile t is resident.  x_{r+1}.x_r + 1 for its rows (the last one needs the next tile: done in its row)
-        for (int q = tid; q < rows - 1; q += NT) {
+        for (int q = tid; q < rows - 1; q += NTT) {
             float u[IP], v[IP];
             lds_row<IP>(xaddr(base + q), u);
             lds_row<IP>(xaddr(base + q + 1), v);
@@ -742,7 +767,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
             for (int i = 0; i < I; ++i) c = fmaf(u[i], v[i], c);
             s_c[q] = c;
         }
-        __syncthreads();          // s_c visible; every thread is past its reads of tile t-1
+        team_bar<NTT>();          // s_c visible; every thread is past its reads of tile t-1
         if (!staged && t + 1 < ntiles) issue(t + 1);
         const int last = base + rows - 1;            // the tile's last row looks ahead into the next tile
         while (last - r >= 2) {                      // pairs of rows whose look-ahead rows are in this tile
@@ -773,19 +798,24 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
     }
     flush(A);                                        // A = the last row processed
 
-    if (act) {
 #pragma unroll
-        for (int i = 0; i < I; ++i) w_out[i * H + tid] = w1[i];
+    for (int k = 0; k < UPT; ++k) {
+        const int h = tid + NTT * k;
+        if (h < H) {
 #pragma unroll
-        for (int o = 0; o < O; ++o) w_out[oW2 + tid * O + o] = w2r[o];
-        w_out[oB1 + tid] = b1;
+            for (int i = 0; i < I; ++i) w_out[i * H + h] = w1[i][k];
+#pragma unroll
+            for (int j = 0; j < OJ; ++j) {
+                float a0, a1;
+                unpack2(w2[k][j], a0, a1);
+                if (2 * j < O) w_out[oW2 + h * O + 2 * j] = a0;
+                if (2 * j + 1 < O) w_out[oW2 + h * O + 2 * j + 1] = a1;
+            }
+            w_out[oB1 + h] = b1[k];
+        }
     }
-#pragma unroll
-    for (int j = 0; j < OPW; ++j) {
-        const int o = warp + NWT * j;
-        if (o < O && lane == 0) w_out[oB2 + o] = b2[j];
-    }
-    __syncthreads();
+    if (warp == 0 && lane < O) w_out[oB2 + lane] = b2;
+    team_bar<NTT>();
 }
 
 // ==========================================================================================
@@ -928,15 +958,6 @@ template <int I, int H, int O>
 __device__ __forceinline__ void lik_prepare(float *lw, const float *w, int t, int nt) {
     for (int j = t; j < I * H + H * O + H; j += nt) lik_scatter<I, H, O>(lw, j, w[j]);
 }
-
-// Packed pairs kept in 64-bit registers for the whole hidden-unit loop (building the pair from two
-// scalar registers costs a MOV each time, which is what the loop is trying to get rid of).
-typedef unsigned long long f2_t;
-__device__ __forceinline__ f2_t pack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // Sigmoids of NP row pairs from their ex2-domain pre-activations (sigmoid(z), zs = -log2(e) z):
 // one MUFU.EX2 each, ONE MUFU.RCP per four (per two when NP == 1).
@@ -1094,10 +1115,10 @@ __device__ __forceinline__ void lik_fast(const float *__restrict__ lw, const flo
 namespace ptfnn {
 
 // K5 applies to the wide-hidden specialisations whose geometry matches the tcgen05 tile (M = 128 rows,
-// N = H = 256 accumulator columns, two epilogue warps per TMEM lane quadrant)
+// N = H = 256 accumulator columns, one epilogue warp per TMEM lane quadrant)
 template <int I, int H, int O, int NT>
 struct UseTc {
-    static constexpr bool value = (H == 256 && NT == 256 && (O % 2) == 0 && ((H * O) % 4) == 0);
+    static constexpr bool value = (H == 256 && NT == 128 && (O % 2) == 0 && ((H * O) % 4) == 0);
 };
 
 // ==========================================================================================

@@ -224,15 +224,14 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
     using G = Geometry<I>;
     using BG = BGeometry<I, H>;
     using S = Smem<I, H, O>;
-    static_assert(NT == 256 && H == 256, "two warps per TMEM lane quadrant, 128 accumulator columns each");
+    static_assert(NT == 128 && H % 32 == 0 && H <= 256, "one warp per TMEM lane quadrant: thread = row, all H accumulator columns");
     static_assert(O % 2 == 0 && (H * O) % 4 == 0, "output-layer rows are read in aligned pairs");
     constexpr int oW2 = I * H, oB2 = I * H + H * O + H;
     constexpr uint32_t IDESC = instr_desc_tf32(kRows, H);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint64_t *bar_a = &bars[0], *bar_mma = &bars[1];
-    float *s_x = reinterpret_cast<float *>(smem + S::off_x);
     const uint32_t a_base = smem_u32(smem + S::off_a), b_base = smem_u32(smem + S::off_b);
     const int ntiles = (n + kRows - 1) / kRows;
 
@@ -270,14 +269,14 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
             mbar_arrive_expect_tx(bar_a, G::A_TILE_BYTES);
             tma_load_1d(smem + S::off_a, tiles + (size_t)(t + 1) * G::A_TILE_FLOATS, G::A_TILE_BYTES, bar_a);
         }
-        // ---- epilogue: this thread = row (32 quad + lane) of the tile, hidden units [128 half, +128)
+        // ---- epilogue: this thread = row (32 quad + lane) of the tile, all H hidden units
         f2_t acc2[O / 2];
 #pragma unroll
         for (int j = 0; j < O / 2; ++j) acc2[j] = pack2(0.0f, 0.0f);
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < H / 32; ++cb) {
             float z[32];
-            const int h0 = half * 128 + cb * 32;
+            const int h0 = cb * 32;
             tmem_ld32(st.tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)h0, z);
 #pragma unroll
             for (int g = 0; g < 32; g += 4) {
@@ -308,18 +307,14 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
 #pragma unroll
         for (int j = 0; j < O / 2; ++j) unpack2(acc2[j], part[2 * j], part[2 * j + 1]);
         const int row_in = quad * 32 + lane;
-        if (half == 1) {
-#pragma unroll
-            for (int o = 0; o < O; ++o) s_x[row_in * S::XO + o] = part[o];
-        }
         tc_fence_before();
-        __syncthreads();                              // partial sums visible; every TMEM read of this tile is done
+        __syncthreads();                              // every TMEM read of this tile is done: the next tile's MMAs may overwrite it
         const int r = t * kRows + row_in;
-        if (half == 0 && r < n) {
+        if (r < n) {
             float out[O];
             const float yv = y[r];
 #pragma unroll
-            for (int o = 0; o < O; ++o) out[o] = sigmoid_fast(part[o] + s_x[row_in * S::XO + o] - w[oB2 + o]);   // R:54-55
+            for (int o = 0; o < O; ++o) out[o] = sigmoid_fast(part[o] - w[oB2 + o]);   // R:54-55
             if constexpr (TASK == kTaskReg) {
                 const float e = yv - out[0];
                 s0 += (double)(e * e);
@@ -348,7 +343,6 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                 }
             }
         }
-        __syncthreads();                              // s_x may be rewritten by the next tile
         tc_fence_after();
     }
 }

@@ -200,6 +200,25 @@ class Sampler:
             out["accepted"] = out["accepted"].astype(bool)
         return out
 
+    def traces_begin(self, first, count, pos_w=True) -> int:
+        """Queue the read-back of rows [first, first+count) behind everything launched so far and return at once
+        (copy stream + two page-locked slots inside the library); later run() calls overlap with the copy."""
+        t = C.c_int32()
+        self._ck(self._lib.ptfnn_traces_begin(self._h, int(first), int(count), int(bool(pos_w)), C.byref(t)))
+        return t.value
+
+    def traces_end(self, ticket) -> dict:
+        """-> NumPy VIEWS into the library's staging slot (float32 pos_w, float64 series, int32 accept_list), valid
+        until the second next traces_begin(); no widening, no further copy."""
+        v = capi.TraceViews()
+        self._ck(self._lib.ptfnn_traces_end(self._h, int(ticket), C.byref(v)))
+        shape = (self.R, v.count)
+        out = {k: np.ctypeslib.as_array(getattr(v, k), shape=shape)
+               for k in ("lik_prop", "rmse_train", "rmse_test", "acc_train", "acc_test", "accept_list")}
+        if v.pos_w:
+            out["pos_w"] = np.ctypeslib.as_array(v.pos_w, shape=(self.R, v.count, self.P))
+        return out
+
     def trace_summary(self, first=0, count=None, posterior=True):
         """The reference's result statistics (R:1036-1044: mean / np.std / min of the pooled RMSE columns
         after the burn-in slice, R:777) reduced on the device -- the traces are not copied to the host.

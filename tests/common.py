@@ -47,3 +47,19 @@ def case(name):
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def lik_scale(cfg, ref, n_train, temps):
+    """[R, S] magnitude of the terms of the proposed log-likelihood (row i+1 = step i); 1 for classification."""
+    if cfg.task != on.REGRESSION:
+        return np.ones_like(ref.lik_prop)
+    tau = np.maximum(ref.state_tau, 1e-300)                  # row i+1: tau^2 proposed at step i (R:356)
+    sse = (ref.rmse_train ** 2) * n_train                    # on accepted rows; carried rows understate it (harmless: a max below)
+    t1 = 0.5 * n_train * np.abs(np.log(2.0 * np.pi * tau))
+    t2 = 0.5 * sse / tau
+    S = ref.lik_prop.shape[1]
+    adapt = np.repeat(np.asarray(temps, dtype=np.float64)[:, None], S, axis=1)
+    sw = cfg.pt_fraction * cfg.samples                       # R:301-324: adapttemp = 1 from step 0.6 S on, if that is an integer
+    if float(sw).is_integer():
+        adapt[:, int(sw) + 1:] = 1.0                         # row i+1 = step i
+    return np.maximum(np.maximum(t1, t2) / adapt, np.abs(ref.lik_prop))

@@ -77,7 +77,7 @@ def test_argument_validation_happens_before_cuda(lib):
         Sampler(capi.TASK_REGRESSION, (4, 5, 2), [1.0, 2.0], 10, 5)           # regression needs O == 1 (R:132)
     assert e.value.code == capi.E_UNSUPPORTED
     with pytest.raises(capi.PtfnnError) as e:
-        Sampler(capi.TASK_REGRESSION, (4, 300, 1), [1.0, 2.0], 10, 5)         # hidden layers up to 256 units
+        Sampler(capi.TASK_REGRESSION, (4, 600, 1), [1.0, 2.0], 10, 5)         # hidden layers up to capi.MAX_HIDDEN units
     assert e.value.code == capi.E_UNSUPPORTED
 
     with pytest.raises(capi.PtfnnError) as e:

@@ -225,3 +225,120 @@ def test_class_labels_outside_the_outputs_are_refused_where_they_are_used():
     frac[:, 4] += 0.5                                            # int(y) truncates (C:74, C:217)
     assert np.allclose(capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, frac, w, 1.0, 1.0)[0],
                        capi.op_likelihood(capi.TASK_CLASSIFICATION, topo, good, w, 1.0, 1.0)[0])
+
+
+def test_swap_sweep_under_the_drafts_temperature_rule():
+    """the temperature-aware swap rule of the reference's drafts (Misc/ldpt_fnn_multi_fixed.py:520) as
+    an opt-in ``swap_kind`` of the same sequential sweep; the temperature field travels with its vector."""
+    rs = np.random.RandomState(9)
+    for n in (2, 5, 64, 500):
+        temps = 1.0 / np.logspace(0, -np.log10(4.0), n)
+        lh = -np.abs(rs.randn(n)) * 50 - 1.0                       # log-likelihood fields are negative
+        lh[rs.randint(0, n)] = 0.0                                 # the rule's lhood2 == 0 guard
+        u = rs.randint(0, 1 << 24, size=n - 1).astype(np.float64) / (1 << 24)
+        a, b = on.swap_sweep_ratio_temperature(lh, u, temps)
+        c, d = capi.op_swap_sweep(lh, u, swap_kind=capi.SWAP_KIND_RATIO_TEMPERATURE, temperatures=temps)
+        assert a == c.tolist() and b == d.tolist(), n
+        assert any(b) and not all(b)
+    with pytest.raises(capi.PtfnnError):
+        capi.op_swap_sweep([1.0, 2.0], [0.5], swap_kind=capi.SWAP_KIND_RATIO_TEMPERATURE)      # needs the temperatures
+
+
+def test_chain_runs_under_the_drafts_swap_rule_and_counts_every_proposal():
+    from ptnn_b200.sampler import Sampler, geometric_ladder
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    R, S, si = 6, 61, 10
+    out = {}
+    for kind in (capi.SWAP_KIND_REFERENCE, capi.SWAP_KIND_RATIO_TEMPERATURE):
+        with Sampler(on.REGRESSION, (4, 5, 1), geometric_ladder(R, 2), S, si, seed=5, swap_kind=kind) as s:
+            s.set_data(tr, te)
+            s.init_chains(np.random.RandomState(1).randn(R, 31))
+            assert s.run() == S - 1
+            ns, tot, sw = s.swap_stats()
+            out[kind] = (ns, tot, sw, s.traces()["lik_prop"])
+        assert tot == sw.shape[0] * (R - 1) and ns == int(sw.sum())
+    # same chains up to the first round, different swap decisions afterwards
+    assert np.array_equal(out[0][3][:, :si + 1], out[1][3][:, :si + 1])
+    assert not np.array_equal(out[0][2], out[1][2])
+    with pytest.raises(capi.PtfnnError) as e:                      # opt-in on a single GPU only
+        Sampler(on.REGRESSION, (4, 5, 1), geometric_ladder(R, 2)[:3], S, si, n_replicas_global=R, swap_kind=1)
+    assert e.value.code == capi.E_UNSUPPORTED
+
+
+def test_eta_crosses_a_swap_round_as_float64():
+    """R:430-437: the hand-shake moves the float64 eta.  A handle that stops BEFORE the round (its block is half of a
+    larger ladder, so the host would complete the round) shows the pre-swap state; the same chains on one handle run
+    through the round on the device: every eta afterwards must be one of the pre-swap values BIT FOR BIT, at the slot
+    the sweep assigns."""
+    from ptnn_b200.sampler import Sampler, geometric_ladder
+    tr, te = cm.dataset(on.REGRESSION, "Lazer")
+    R, si = 8, 6
+    S = si + 3
+    temps = geometric_ladder(2 * R, 3)
+    w0 = np.random.RandomState(2).randn(R, 31)
+    kw = dict(seed=11, learn_rate=0.1, common_random_numbers=False)
+    with Sampler(on.REGRESSION, (4, 5, 1), temps[:R], S, si, n_replicas_global=2 * R, **kw) as a:
+        a.set_data(tr, te)
+        a.init_chains(w0)
+        n = a.run()                                                # stops right after the swap step
+        assert a.swap_pending()[0] and n == si + 1
+        before = a.get_state()
+    with Sampler(on.REGRESSION, (4, 5, 1), temps[:R], S, si, **kw) as b:
+        b.set_data(tr, te)
+        b.init_chains(w0)
+        assert b.run(n) == n
+        after = b.get_state()
+        ns, tot, sw = b.swap_stats()
+    assert ns > 0 and tot == R - 1
+    src = list(range(R))
+    for k in range(R - 1):                                         # the sweep's permutation from its own decisions
+        if sw[0, k]:
+            src[k], src[k + 1] = src[k + 1], src[k]
+    assert src != list(range(R))
+    assert np.array_equal(after["eta"], before["eta"][src])        # float64, bit for bit (no float32 round trip)
+    assert np.array_equal(after["w"], before["w"][src])
+    assert len(set(before["eta"].tolist())) == R                   # (distinct values: the check can tell them apart)
+
+
+def test_a_wait_that_gives_up_fails_closed():
+    """A device-side wait that times out (here: a peer flag that never arrives -- rank 1 is a process that exports its
+    swap window and then never runs) must end the launch WITHOUT touching chain state or traces, report PTFNN_E_CUDA
+    from every later call, and be cleared by ptfnn_init_chains."""
+    import os
+    import subprocess
+    import sys
+    from ptnn_b200.sampler import Sampler, geometric_ladder
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    R, S, si = 4, 30, 5
+    temps = geometric_ladder(2 * R, 2)
+    w0 = np.random.RandomState(0).randn(R, 31)
+    idle = subprocess.Popen([sys.executable, os.path.join(root, "tests", "peer_idle_worker.py")], stdin=subprocess.PIPE,
+                            stdout=subprocess.PIPE, text=True, cwd=root)
+    try:
+        line = idle.stdout.readline()
+        assert line.startswith("HANDLES "), line
+        theirs = bytes.fromhex(line.split()[1])
+        with Sampler(on.REGRESSION, (4, 5, 1), temps[:R], S, si, n_replicas_global=2 * R, seed=3, barrier_timeout_ms=300) as s:
+            s.set_data(tr, te)
+            s.init_chains(w0)
+            s.peer_connect([s.peer_export(), theirs], 0)
+            s.run(si + 1)                            # reaches the first round and waits for rank 1, which never publishes
+            with pytest.raises(capi.PtfnnError) as e:
+                s.sync()
+            assert e.value.code == capi.E_CUDA and "timed out" in str(e.value)
+            for call in (lambda: s.get_state(), lambda: s.swap_stats(), lambda: s.traces(), lambda: s.run(1)):
+                with pytest.raises(capi.PtfnnError) as e:
+                    call()
+                assert e.value.code == capi.E_CUDA
+            s.init_chains(w0)                        # starts over: the failure is cleared, and the first steps run again
+            assert s.run(si) == si                   # (stops short of the round)
+            s.sync()
+            t = s.traces(first=0, count=si + 1)
+            assert np.all(np.isfinite(t["lik_prop"]))
+    finally:
+        try:
+            idle.stdin.write("bye\n"); idle.stdin.flush()
+        except OSError:
+            pass
+        idle.wait(timeout=60)

@@ -18,12 +18,14 @@ from tests import common as cm
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4          # per step (teacher-forced): the north-star criterion
-# Free replay shares only the initial state, so fp32 rounding compounds from step to step -- most where every
-# step is a Langevin step (two SGD epochs feed the next state) and tau^2 is small (the Gaussian log-likelihood
-# is a difference of large terms): reg_henon_lg1 reaches 1.2e-4 after 44 Langevin steps, the other ten
-# cases stay below 1e-4.  Decisions must still be identical (or a documented near-tie).
-RTOL_FREE = 3e-4
-LONG_LANGEVIN_CASES = ("reg_henon_lg1",)
+# Free replay shares only the initial state, so fp32 rounding compounds from step to step.  The bar stays the
+# north-star's 1e-4; what is compared against it is chosen by the CONDITIONING of each quantity, not by what was
+# observed: weights and RMSE relative to themselves; the Gaussian log-likelihood (R:204-205)
+#     lik = [-N/2 log(2 pi tau^2) - SSE / (2 tau^2)] / T
+# relative to the magnitude of its two terms -- where tau^2 ~ MSE they cancel (|lik| << N/2 |log 2 pi tau^2|), and an
+# SSE that is right to 1e-5 then moves lik by 1e-4 of ITSELF (reg_henon_lg1: 44 consecutive Langevin steps, weights
+# within 5.5e-6, |lik| ~ 25 against terms of ~400).  `lik_scale` is that magnitude, from the oracle's own tau^2.
+RTOL_FREE = 1e-4
 
 
 def _sampler(cfg, temps, **kw):
@@ -117,8 +119,10 @@ def test_free_replay_decisions_and_traces(name):
             lo, hi = sorted([t["mh_prob"][r, i_acc + 1], ref.mh_prob[r, i_acc + 1]])
             assert lo - 1e-7 <= u <= hi + 1e-7 and (hi - lo) <= 1e-3 * max(hi, 1e-30) + 1e-7, (name, i_acc, r, u, lo, hi)
     rows = slice(0, i_star + 1)     # rows 0..i_star were written by steps < i_star
-    tol = RTOL_FREE if name in LONG_LANGEVIN_CASES else RTOL
-    assert cm.relerr(t["lik_prop"][:, rows][:, 1:], ref.lik_prop[:, rows][:, 1:]) < tol
+    tol = RTOL_FREE
+    scale = np.maximum(1.0, cm.lik_scale(cfg, ref, tr.shape[0], fx["temperatures"]))
+    err = np.abs(t["lik_prop"] - ref.lik_prop) / scale
+    assert float(np.max(err[:, rows][:, 1:])) < tol
     assert cm.relerr(t["pos_w"][:, rows], fx["ref_pos_w"][:, rows]) < tol          # the reference's own file
     assert np.array_equal(t["accept_list"][:, rows], fx["ref_accept_list"][:, rows])
     if cfg.task == on.REGRESSION:

@@ -170,3 +170,42 @@ def test_run_chains_predictive_moments_agree_with_the_per_sample_predictions(tmp
         assert fx.shape[0] == 4 * 30 and np.any(fx != 0)
         assert np.allclose(pt.predictive[k]["mean"], fx.mean(axis=0), rtol=1e-6, atol=1e-9)
         assert np.allclose(pt.predictive[k]["std"], fx.std(axis=0), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("ds,topo,R,S,first,count,q", [("Sunspot", (4, 5, 1), 4, 60, 20, 40, (5.0, 95.0)),
+                                                     ("Lazer", (4, 10, 1), 3, 25, 3, 17, (2.5, 97.5)),
+                                                     ("Mackey", (4, 64, 1), 2, 12, 6, 6, (0.0, 100.0)),
+                                                     ("Henon", (4, 5, 1), 1, 9, 8, 1, (50.0, 50.0))])
+def test_predictive_bands_match_numpy_percentile(ds, topo, R, S, first, count, q):
+    """the 5 % - 95 % band of the posterior-predictive distribution per data row.  The device selects
+    exact order statistics of the [samples, rows] prediction matrix (radix select), so the band equals
+    np.percentile (linear interpolation) over the very predictions the batched forward pass returns -- including
+    ties (a rejected step repeats the previous row of pos_w), a single sample and the 0 / 100 % ends."""
+    from ptnn_b200 import capi
+    tr, te = cm.dataset(on.REGRESSION, ds)
+    P = topo[0] * topo[1] + topo[1] * topo[2] + topo[1] + topo[2]
+    w0 = np.random.RandomState(4).randn(R, P) * 0.5
+    with Sampler(on.REGRESSION, topo, geometric_ladder(R, 3) if R > 1 else np.ones(1), S, 5, learn_rate=0.05, l_prob=0.5, seed=3) as s:
+        s.set_data(tr, te)
+        s.init_chains(w0)
+        s.run()
+        got = {k: s.predictive_summary(k, first, count, bands=q) for k in ("train", "test")}
+        pw = s.traces()["pos_w"][:, first:first + count].reshape(-1, P)
+    for k, data in (("train", tr), ("test", te)):
+        fx = capi.op_posterior_predictive(on.REGRESSION, topo, data, pw)[0]          # the same float32 predictions, on the host
+        lo, hi = np.percentile(fx, q, axis=0)
+        assert np.allclose(got[k]["lo"], lo, rtol=1e-12, atol=1e-12), (k, np.max(np.abs(got[k]["lo"] - lo)))
+        assert np.allclose(got[k]["hi"], hi, rtol=1e-12, atol=1e-12), (k, np.max(np.abs(got[k]["hi"] - hi)))
+        assert np.all(got[k]["lo"] <= got[k]["mean"] + 1e-9) or q[0] > 50
+        assert np.all(got[k]["lo"] <= got[k]["hi"])
+
+
+def test_run_chains_predictive_bands(tmp_path):
+    pt = _pt(reg, on.REGRESSION, "Sunspot", (4, 5, 1), tmp_path, 4, 60, 10, 2, write_files=False, results_from_files=False,
+             posterior_predictive=True, predictive_moments=True, predictive_bands=(5, 95))
+    res = pt.run_chains()
+    for k, fx_all, data in (("train", res[1], pt.traindata), ("test", res[2], pt.testdata)):
+        fx = fx_all.reshape(-1, data.shape[0])
+        lo, hi = np.percentile(fx, (5, 95), axis=0)
+        assert np.allclose(pt.predictive[k]["lo"], lo, rtol=1e-6, atol=1e-9)
+        assert np.allclose(pt.predictive[k]["hi"], hi, rtol=1e-6, atol=1e-9)

@@ -230,3 +230,76 @@ def test_classification_cli_like_run_sh(tmp_path, monkeypatch):
     assert 50.0 < vals[6] <= 100.0 and 50.0 < vals[9] <= 100.0                        # mean train / test accuracy of the pooled posterior
     files = [f for _, _, fs in os.walk(tmp_path / "out" / "iris_0") for f in fs]
     assert len(files) == 10 * 8 + 5                                                   # 8 files per chain + 4 aggregates + result.txt
+
+
+def test_free_running_statistics_classification_match_reference_spread():
+    """The classification sampler (C:313-448) in free-running mode -- Iris 4-12-3, 10 replicas, maxtemp 10, Langevin
+    lr 0.01, swap interval 100 (C:1036-1045; 1000 samples per replica here) -- against the float64 oracle on the
+    device's own draws and on independent seeds: acceptance rate, swap rate and the posterior's mean train / test
+    accuracy must lie inside the oracle's run-to-run spread."""
+    from oracle import ptfnn_c as oc
+    from ptnn_b200.sampler import Sampler
+    tr, te = cm.dataset(on.CLASSIFICATION, "Iris")
+    R, S, si = 10, 1000, 100
+    cfg = on.PTConfig(task=on.CLASSIFICATION, topology=(4, 12, 3), samples=S, swap_interval=si,
+                      use_langevin_gradients=True, l_prob=0.5, learn_rate=0.01)
+    temps = on.geometric_ladder(R, 10)
+
+    def stats(acc_train, acc_test, accept_last, ns, tot):
+        b = S // 2
+        return np.array([acc_train[:, b:].mean(), acc_test[:, b:].mean(), np.mean(accept_last / S) * 100, 100.0 * ns / max(tot, 1)])
+
+    dev, same, other = [], [], []
+    for seed in (1, 2, 3):
+        w0 = np.random.RandomState(seed).randn(R, cfg.P)
+        with Sampler(on.CLASSIFICATION, (4, 12, 3), temps, S, si, learn_rate=0.01, l_prob=0.5, seed=seed) as s:
+            s.set_data(tr, te)
+            s.init_chains(w0)
+            lx, z, ze, u = s.generate_draws(0, S - 1)
+            us = np.stack([s.swap_uniforms(r) for r in range(cfg.total_rounds())])
+            assert s.run() == S - 1
+            t = s.traces(pos_w=False)
+            ns, tot, _ = s.swap_stats()
+        dev.append(stats(t["acc_train"], t["acc_test"], t["accept_list"][:, -1], ns, tot))
+        ref = oc.run_pt(cfg, tr, te, temps, w0, on.Draws(lx=lx, z=z, z_eta=ze, u=u, u_swap=us), with_state=False)
+        same.append(stats(ref.acc_train, ref.acc_test, ref.accept_list[:, -1], ref.num_swap, ref.total_swap_proposals))
+        assert tot == ref.total_swap_proposals
+        ind = oc.run_pt(cfg, tr, te, temps, w0, on.random_draws(cfg, R, 100 + seed), with_state=False)
+        other.append(stats(ind.acc_train, ind.acc_test, ind.accept_list[:, -1], ind.num_swap, ind.total_swap_proposals))
+    dev, same, other = np.array(dev), np.array(same), np.array(other)
+    # (a) the device's draws replayed by the oracle: the same chain up to rare near-tie flips
+    assert np.all(np.abs(dev[:, :2] - same[:, :2]) < 8.0), (dev, same)                 # accuracy, percentage points
+    assert np.all(np.abs(dev[:, 2] - same[:, 2]) < 3.0) and np.all(np.abs(dev[:, 3] - same[:, 3]) < 12.0), (dev, same)
+    # (b) inside the oracle's run-to-run spread over all six oracle runs
+    allref = np.vstack([same, other])
+    lo, hi = allref.min(axis=0), allref.max(axis=0)
+    span = np.maximum(hi - lo, np.array([5.0, 5.0, 2.0, 8.0]))
+    assert np.all(dev.mean(axis=0) > lo - span) and np.all(dev.mean(axis=0) < hi + span), (dev, allref)
+    assert dev[:, 0].mean() > 60.0                                                     # the sampler learns Iris (BASELINE.md: 96.8 % at 50k samples)
+
+
+def test_sunspot_run_matches_the_published_rows(tmp_path):
+    """The reference's only published numbers for the north-star configuration are single unseeded runs
+    (Res_LG01 / Res_LG001 / Res_RW master_result_file.txt:2 -- Sunspot, 100 000 samples,
+    10 replicas, maxtemp 5, swap interval 100, Langevin l_prob 0.5, lr 0.1): acceptance 12.6-18.3 %, swap rate
+    44.5-48.5 %, test RMSE 0.019-0.024 (std 0.003-0.005 over the pooled posterior).  Three seeded device runs of that
+    configuration through the reference surface must bracket those rows: the margins below are the published spread
+    widened by the spread of the three runs themselves."""
+    tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+    rows = []
+    for seed in (1, 2, 3):
+        path = str(tmp_path / ("s%d" % seed))
+        pt = reg.ParallelTempering(True, 0.1, tr, te, [4, 5, 1], 10, 5, 100000, 100, 0.5, path)
+        pt.write_files, pt.results_from_files, pt.seed = False, False, seed
+        for d in RESULT_DIRS:
+            pt.make_directory(path + d)
+        np.random.seed(seed)
+        pt.initialize_chains(0.5)
+        sm = pt.run_summary()
+        rows.append([sm["rmse_train"]["mean"], sm["rmse_test"]["mean"], sm["accept_per"], sm["swap_perc"]])
+    rows = np.array(rows)
+    mean, spread = rows.mean(axis=0), rows.max(axis=0) - rows.min(axis=0)
+    published_lo = np.array([0.0199, 0.0192, 12.58, 44.46])         # Res_LG01:2 (RMSE, accept), Res_RW:2 (swap)
+    published_hi = np.array([0.0242, 0.0239, 18.31, 48.45])
+    margin = np.array([0.006, 0.006, 5.0, 10.0]) + spread
+    assert np.all(mean > published_lo - margin) and np.all(mean < published_hi + margin), (rows, mean)

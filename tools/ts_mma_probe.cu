@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 #include "ptfnn_kernels.cuh"
 
 using namespace ptfnn;
@@ -123,15 +124,16 @@ __global__ void __launch_bounds__(128) probe(const float *hid, const float *w2, 
     if (tid < 32) tmem_dealloc(tm, 256);
 }
 
-// pacing: NI back-to-back SS-free TS MMAs of width N accumulating into one D
-template <int N>
-__global__ void __launch_bounds__(128) pace(long long *cyc, int reps) {
+// pacing: `reps` back-to-back TS MMAs of width N, round-robin over ND independent accumulators; the grid may put
+// two CTAs on every SM (do their MMAs overlap, or is the cost per instruction pipe occupancy?)
+template <int N, int ND>
+__global__ void __launch_bounds__(128, 2) pace(long long *cyc, int reps) {
     __shared__ __align__(128) unsigned char s_b[2 * 256 * 16];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t slot;
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (tid < 32) tmem_alloc(&slot, 512);
+    if (tid < 32) tmem_alloc(&slot, 256);
     for (int i = tid; i < 2 * 256 * 4; i += 128) reinterpret_cast<float *>(s_b)[i] = 0.0f;
     fence_async_smem();
     tc_fence_before();
@@ -141,13 +143,13 @@ __global__ void __launch_bounds__(128) pace(long long *cyc, int reps) {
     if (tid == 0) {
         const uint64_t bd = smem_desc(smem_u32(s_b), N * 16, 128);
         const long long t0 = clock64();
-        for (int r = 0; r < reps; ++r) mma_tf32_ts(tm + 256, tm + (r & 7) * 8, bd, instr_desc_tf32(128, N), r > 0);
+        for (int r = 0; r < reps; ++r) mma_tf32_ts(tm + 64 + (r % ND) * (N < 32 ? 32 : N), tm + (r & 7) * 8, bd, instr_desc_tf32(128, N), r >= ND);
         mma_commit(&bar);
         mbar_wait(&bar, 0);
-        cyc[0] = clock64() - t0;
+        cyc[blockIdx.x] = clock64() - t0;
     }
     __syncthreads();
-    if (tid < 32) tmem_dealloc(tm, 512);
+    if (tid < 32) tmem_dealloc(tm, 256);
 }
 
 int main() {
@@ -179,9 +181,13 @@ int main() {
                mode == 0 ? "3xTF32" : "plain tf32", worst, wr, wn, std::sqrt((double)K2) * 0.6, hc, (K2 / 8) * (mode == 0 ? 3 : 1));
     }
     const int reps = 256;
-#define PACE(N) pace<N><<<1, 128>>>(dc, reps); cudaDeviceSynchronize(); cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost); \
-    printf("TS MMA M=128 N=%3d K=8: %.1f cycles per instruction (%d back to back)\n", N, (double)hc / reps, reps);
-    PACE(16) PACE(32) PACE(64) PACE(128) PACE(256)
+    long long *dcs; cudaMalloc(&dcs, 8 * 512);
+    std::vector<long long> hcs(512);
+#define PACE(N, ND, GRID) pace<N, ND><<<GRID, 128>>>(dcs, reps); cudaDeviceSynchronize(); cudaMemcpy(hcs.data(), dcs, 8 * GRID, cudaMemcpyDeviceToHost); \
+    { double mx = 0; for (int i = 0; i < GRID; ++i) mx = std::max(mx, (double)hcs[i]); \
+      printf("TS MMA M=128 N=%3d K=8, %d accumulators, %3d CTAs: %.1f cycles per instruction and CTA (%d back to back)\n", N, ND, GRID, mx / reps, reps); }
+    PACE(16, 1, 1) PACE(16, 2, 1) PACE(16, 4, 1) PACE(32, 1, 1) PACE(32, 2, 1) PACE(64, 1, 1) PACE(64, 2, 1) PACE(128, 1, 1) PACE(192, 1, 1)
+    PACE(16, 1, 296) PACE(16, 2, 296) PACE(32, 1, 296) PACE(64, 1, 296) PACE(128, 1, 296)
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
