@@ -135,7 +135,9 @@ def ensure_topology(task, topology, verbose=False):
         raise PtfnnError(E_UNSUPPORTED, "no specialisation for topology [%d,%d,%d] (hidden layers up to %d units, up to 32 outputs: "
                                         "the weights of a layer live in the registers of one CTA)" % (I, H, O, MAX_HIDDEN))
     name = "jit_%s_%d_%d_%d" % ("reg" if task == TASK_REGRESSION else "cls", I, H, O)
-    nt = 128 if H <= 256 else 256                      # wide nets: a team of threads, ceil(H / nt) hidden units each (sgd_pass_team)
+    # threads per CTA: 128 (one serial warp + three likelihood warps, or the 128-thread SGD team of a wide hidden layer);
+    # 160 for the tcgen05 geometry (H = 256, up to 16 outputs: four epilogue warps + the MMA warp); 256 above that
+    nt = 160 if (H == 256 and O <= 16) else 128 if H <= 256 else 256
     minb = 2 if (H > 32 or I > 16) else 4
     csrc = os.path.dirname(LIB_PATH)
     out_dir = os.path.join(csrc, "build", "jit")

@@ -117,6 +117,15 @@ struct ptfnn_sampler {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_compute = nullptr;
     unsigned int fetch_seq = 0;
+    // acceptance feedback for the automatic depth of the speculative windows: after every launch the sum of the
+    // replicas' acceptance counters is copied (asynchronously) into a small page-locked ring; the next launch looks at
+    // the newest copy that has ARRIVED -- no synchronisation, the estimate is one or two launches old
+    struct AccSample { long long *host = nullptr; cudaEvent_t ev = nullptr; int step = 0; bool used = false; };
+    AccSample acc_ring[4];
+    DevBuf<long long> acc_sum;
+    unsigned int acc_seq = 0;
+    long long acc_prev_sum = 0; int acc_prev_step = 0; bool acc_have_prev = false;
+    double acc_est = -1.0;            // < 0: nothing known yet
 
     bool have_data = false, have_state = false, summary_smem_opted = false;
     int n_train = 0, n_test = 0;
@@ -129,7 +138,7 @@ struct ptfnn_sampler {
     DevBuf<float> train_x, train_y, test_x, test_y;
     DevBuf<float> a_train, a_test;                    // K5: UMMA A tiles of the data sets (wide-hidden topologies)
     DevBuf<double> temperature;
-    DevBuf<float> w, gd_cache, pgd_buf, pos_w, pub_rows;
+    DevBuf<float> w, gd_cache, pgd_buf, prop_buf, pos_w, pub_rows;
     DevBuf<double> eta, tau, lik, prior, last4, init_rmse, pub_lhood;
     DevBuf<double> lik_prop, rmse_tr, rmse_te, acc_tr, acc_te, dbg_prior, dbg_diff, dbg_mh;
     DevBuf<int> n_acc, init_count, gd_valid, accept_list;
@@ -156,11 +165,17 @@ struct ptfnn_sampler {
             if (f.done) cudaEventDestroy(f.done);
             f = FetchSlot();
         }
+        for (auto &a : acc_ring) {
+            if (a.host) cudaFreeHost(a.host);
+            if (a.ev) cudaEventDestroy(a.ev);
+            a = AccSample();
+        }
+        acc_sum.release();
         if (ev_compute) cudaEventDestroy(ev_compute);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         ev_compute = nullptr; copy_stream = nullptr;
         train_x.release(); train_y.release(); test_x.release(); test_y.release(); a_train.release(); a_test.release(); temperature.release();
-        w.release(); gd_cache.release(); pgd_buf.release(); pos_w.release(); pub_rows.release();
+        w.release(); gd_cache.release(); pgd_buf.release(); prop_buf.release(); pos_w.release(); pub_rows.release();
         eta.release(); tau.release(); lik.release(); prior.release(); last4.release(); init_rmse.release();
         pub_lhood.release(); lik_prop.release(); rmse_tr.release(); rmse_te.release(); acc_tr.release();
         acc_te.release(); dbg_prior.release(); dbg_diff.release(); dbg_mh.release(); n_acc.release();
@@ -332,7 +347,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
         rc = fail(nullptr, PTFNN_E_NOMEM, "cudaMalloc(" #buf ", %zu elems): %s", (size_t)(count), cudaGetErrorString(e)); \
         s->release_all(); delete s; cudaGetLastError(); return rc;                            \
     }
-    ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(gd_cache, R * P); ALLOC(pgd_buf, cfg->n_hidden > 64 ? R * P : 1);
+    ALLOC(temperature, R); ALLOC(w, R * P); ALLOC(gd_cache, R * P); ALLOC(pgd_buf, cfg->n_hidden > 64 ? R * P : 1); ALLOC(prop_buf, ks->fwd_tc ? R * P : 1);
     ALLOC(pos_w, R * S * P + kSumTracePadFloats); ALLOC(pub_rows, 2 * R * (P + kRowTail)); ALLOC(pub_lhood, 2 * (size_t)Rg);
     ALLOC(eta, R); ALLOC(tau, R); ALLOC(lik, R); ALLOC(prior, R); ALLOC(last4, R * 4); ALLOC(init_rmse, R * 2);
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
@@ -493,6 +508,8 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     // run are not taken for "already published".
     if (s->have_state) s->peer_round_base += (unsigned int)h_total_rounds(s) + 2u;
     s->device_failed = false;
+    s->acc_est = -1.0; s->acc_have_prev = false; s->acc_prev_sum = 0; s->acc_prev_step = 0;
+    for (auto &a : s->acc_ring) a.used = false;
     s->step = 0; s->rounds_done = 0; s->swap_pending = false; s->pending_final = false;
     s->host_num_swap = 0; s->host_total_prop = 0; s->host_swap_log.clear(); s->host_swap_log_round.clear();
     s->have_state = true;
@@ -590,7 +607,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     p.a_train = s->a_train.p; p.a_test = s->a_test.p;
     p.w = s->w.p; p.eta = s->eta.p; p.tau = s->tau.p; p.lik = s->lik.p; p.prior = s->prior.p;
     p.n_acc = s->n_acc.p; p.init_count = s->init_count.p; p.last4 = s->last4.p;
-    p.gd_cache = s->gd_cache.p; p.pgd_buf = s->pgd_buf.p; p.gd_valid = s->gd_valid.p;
+    p.gd_cache = s->gd_cache.p; p.pgd_buf = s->pgd_buf.p; p.prop_buf = s->prop_buf.p; p.gd_valid = s->gd_valid.p;
     p.pos_w = s->pos_w.p; p.lik_prop = s->lik_prop.p; p.rmse_tr = s->rmse_tr.p; p.rmse_te = s->rmse_te.p;
     p.acc_tr = s->acc_tr.p; p.acc_te = s->acc_te.p; p.accept_list = s->accept_list.p;
     p.dbg_prior = s->dbg_prior.p; p.dbg_diff = s->dbg_diff.p; p.dbg_mh = s->dbg_mh.p; p.dbg_acc = s->dbg_acc.p;
@@ -689,15 +706,38 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     // evaluate K consecutive steps speculatively (chain_kernel, "speculative windows").  cfg.speculation:
     // 0 = automatic, 1 = off, K > 1 = that depth (clamped to what is co-resident).
     int spec = 1;
-    if (s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms) {
+    const bool spec_possible = s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms;
+    const bool spec_auto = spec_possible && c.speculation == 0;
+    if (spec_auto) {                                     // newest acceptance sample that has arrived (never waits)
+        for (int k = 0; k < 4; ++k) {
+            ptfnn_sampler::AccSample &a = s->acc_ring[(s->acc_seq + 3 - k) & 3];
+            if (!a.used || cudaEventQuery(a.ev) != cudaSuccess) continue;
+            if (s->acc_have_prev && a.step > s->acc_prev_step) {
+                const double rate = (double)(*a.host - s->acc_prev_sum) / ((double)R * (a.step - s->acc_prev_step));
+                s->acc_est = s->acc_est < 0.0 ? rate : 0.5 * s->acc_est + 0.5 * rate;
+            }
+            if (!s->acc_have_prev || a.step > s->acc_prev_step) { s->acc_prev_sum = *a.host; s->acc_prev_step = a.step; s->acc_have_prev = true; }
+            break;
+        }
+    }
+    if (spec_possible) {
+        // A window of depth K costs about one step (of the slowest kind in it) and advances (1 - (1-a)^K) / a steps
+        // for acceptance rate a: K pays as soon as proposals are mostly rejected, which is the reference's steady
+        // state (12-30 %; a few per cent on 30 000-row data sets) but not the first steps of a run from
+        // random weights, where Langevin proposals are accepted almost always and extra CTAs only add contention
+        // (measured in round 1: 42-48 ms against 36-40 ms per 10 steps of 128-512 temperatures at acceptance ~1).
+        //   automatic:  ladder <= half the SMs (the reference's own 10 temperatures): one CTA per SM, as before;
+        //               otherwise the depth follows the acceptance rate observed on THIS run so far.
+        const int cap = std::min(kMaxSpec, per_sm * s->num_sms / R);
         int want = c.speculation;
-        // automatic: one CTA per SM while the ladder is that small -- for Langevin runs only (a random-walk step is
-        // shorter than the two group barriers of a window: measured 7 us per step against 4 us sequentially)
-        // (Deeper automatic windows -- every co-resident CTA slot -- were measured on the 4-64-1 ladder at 512 / 256 /
-        // 128 temperatures: 48.6 / 48.5 / 42.3 ms per 10 steps against 40.6 / 37.4 / 36.4 ms without: early in a run
-        // Langevin proposals are accepted almost always, so a window advances one step at several CTAs' contention.)
-        if (want == 0) want = c.use_langevin_gradients ? std::max(1, s->num_sms / R) : 1;
-        spec = std::max(1, std::min(std::min(want, kMaxSpec), per_sm * s->num_sms / R));
+        if (want == 0) {
+            const double a = s->acc_est;
+            if (R * 2 <= s->num_sms)      // tiny ladders: one CTA per SM for Langevin runs; none for random-walk runs (a step is shorter than a window's two group barriers)
+                want = c.use_langevin_gradients ? std::max(1, s->num_sms / R) : 1;
+            else
+                want = a < 0.0 ? 1 : a <= 0.30 ? cap : a <= 0.60 ? std::min(cap, 4) : 1;
+        }
+        spec = std::max(1, std::min(want, cap));
     }
     p.spec_k = spec; p.spec_bar = s->spec_bar.p; p.spec_flag = s->spec_flag.p;
     const void *chain_fn = s->ks->chain;
@@ -716,6 +756,21 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     else CU_TRY(s, cudaLaunchCooperativeKernel(chain_fn, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());
     s->step = end;
+    if (spec_auto) {
+        ptfnn_sampler::AccSample &a = s->acc_ring[s->acc_seq & 3];
+        if (!a.host) {
+            CU_TRY(s, cudaHostAlloc((void **)&a.host, sizeof(long long), cudaHostAllocDefault));
+            CU_TRY(s, cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
+        }
+        if (!a.used || cudaEventQuery(a.ev) == cudaSuccess) {         // (a slot whose copy is still in flight is left alone)
+            CU_TRY(s, s->acc_sum.ensure(1));
+            sum_int_kernel<<<1, 256, 0, s->stream>>>(s->n_acc.p, R, s->acc_sum.p);
+            CU_TRY(s, cudaMemcpyAsync(a.host, s->acc_sum.p, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+            CU_TRY(s, cudaEventRecord(a.ev, s->stream));
+            a.step = end; a.used = true;
+            s->acc_seq += 1;
+        }
+    }
     if (external) {
         if (rounds_in_span > 0) { s->swap_pending = true; s->pending_final = false; }
         else if (final_round) { s->swap_pending = true; s->pending_final = true; }

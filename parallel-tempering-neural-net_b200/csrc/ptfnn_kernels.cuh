@@ -525,7 +525,10 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
 
     // ---- weights of this thread's units (layout a1, R:80-90)
     float w1[I][UPT], b1[UPT];
-    f2_t w2[UPT][OJ], w2q[UPT][OJ];               // W2 rows, outputs in pairs; w2q = fscale * W2 (a power of two: exact)
+    // W2 rows, outputs in pairs, kept ONLY in block-fixed-point scale: w2s = fscale * W2.  fscale is a power of two, so
+    // every product, sum and update below is the unscaled one times fscale exactly (scaling by a power of two commutes
+    // with fp32 rounding), and W2 = w2s / fscale at the end is bit for bit what an unscaled copy would hold.
+    f2_t w2s[UPT][OJ];
     float b2 = 0.0f, b2l = 0.0f;                  // lane o of every warp: B2[o] (identical updates in every warp)
 #pragma unroll
     for (int k = 0; k < UPT; ++k) {
@@ -539,8 +542,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         for (int j = 0; j < OJ; ++j) {
             const float a = (act && 2 * j < O) ? w_in[oW2 + h * O + 2 * j] : 0.0f;
             const float b = (act && 2 * j + 1 < O) ? w_in[oW2 + h * O + 2 * j + 1] : 0.0f;
-            w2[k][j] = pack2(a, b);
-            w2q[k][j] = w2[k][j];
+            w2s[k][j] = pack2(a, b);
         }
     }
     if (lane < O) { b2 = w_in[oB2 + lane]; b2l = kL2E * b2; }
@@ -574,7 +576,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
     };
 
     float zs[UPT];            // ex2-domain pre-activations of this thread's units for the current row
-    float fscale = 1.0f, cdec = -kL2E;
+    float fscale = 1.0f, inv_fscale = 1.0f, cdec = -kL2E;
     // Fixed-point scale of the output sums for the next `rows` rows (SgdWarp::set_scale, here agreed by the whole
     // team: one extra barrier per kGuardRows rows).  |partial[o]| of a thread <= sum_k |W2[k][o]| because hid is in
     // [0,1]; one row moves each |W2| entry by at most lr/4.  2^E > bound -> scale 2^(22-E): a thread's scaled partial
@@ -588,9 +590,10 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 float x0, x1;
-                unpack2(w2[k][j], x0, x1);
+                unpack2(w2s[k][j], x0, x1);
                 a0 += fabsf(x0); a1 += fabsf(x1);
             }
+            a0 *= inv_fscale; a1 *= inv_fscale;                     // back to the scale of W2 (exact)
             m = fmaxf(m, fmaxf(a0, a1));
             m = (a0 != a0 || a1 != a1) ? __int_as_float(0x7fc00000) : m;
         }
@@ -604,13 +607,16 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         const unsigned int ef = mb >> 23;
         const bool ok = ef < 200u;
         const unsigned int sf = ok ? 275u - ef : 127u;
-        fscale = __uint_as_float(sf << 23);
-        cdec = ok ? -kL2E * __uint_as_float((254u - sf) << 23) : __int_as_float(0x7fc00000);
-        const f2_t fs2 = pack2(fscale, fscale);
+        const float fnew = __uint_as_float(sf << 23);
+        const float ratio = fnew * inv_fscale;                     // a power of two
+        fscale = fnew;
+        inv_fscale = __uint_as_float((254u - sf) << 23);
+        cdec = ok ? -kL2E * inv_fscale : __int_as_float(0x7fc00000);
+        const f2_t r2 = pack2(ratio, ratio);
 #pragma unroll
         for (int k = 0; k < UPT; ++k)
 #pragma unroll
-            for (int j = 0; j < OJ; ++j) w2q[k][j] = mul2(w2[k][j], fs2);
+            for (int j = 0; j < OJ; ++j) w2s[k][j] = mul2(w2s[k][j], r2);
     };
 
     // carried from one row to the next: the W1 / B1 update of the previous row is applied in the next row
@@ -635,7 +641,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         for (int j = 0; j < OJ; ++j) {
             f2_t a = pack2(kMagic, kMagic);
 #pragma unroll
-            for (int k = 0; k < UPT; ++k) a = fma2(pack2(hid[k], hid[k]), w2q[k][j], a);
+            for (int k = 0; k < UPT; ++k) a = fma2(pack2(hid[k], hid[k]), w2s[k][j], a);
             float a0, a1;
             unpack2(a, a0, a1);
             sraw[2 * j] = (2 * j < O) ? __reduce_add_sync(0xffffffffu, __float_as_int(a0)) : 0;
@@ -674,7 +680,7 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         const float ccl = -kL2E * cr;
         float g[UPT];
 #pragma unroll
-        for (int k = 0; k < UPT; ++k) g[k] = fmaf(-hid[k], hid[k], hid[k]);         // hid (1 - hid)
+        for (int k = 0; k < UPT; ++k) g[k] = fmaf(-hid[k], hid[k], hid[k]) * inv_fscale;   // hid (1 - hid), and the un-scaling of the W2 dot product below
         // ---- publish this warp's sums; the ONE team barrier of the row
         if (lane == 0) {
             int4 *dst = reinterpret_cast<int4 *>(s_part + (par * 8 + warp) * OP);
@@ -709,25 +715,24 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         float lh[UPT];
 #pragma unroll
         for (int k = 0; k < UPT; ++k) {
-            f2_t a = mul2(w2[k][0], lo2[0]);
+            f2_t a = mul2(w2s[k][0], lo2[0]);
 #pragma unroll
-            for (int j = 1; j < OJ; ++j) a = fma2(w2[k][j], lo2[j], a);
+            for (int j = 1; j < OJ; ++j) a = fma2(w2s[k][j], lo2[j], a);
             float a0, a1;
             unpack2(a, a0, a1);
             lh[k] = (a0 + a1) * g[k];
             zs[k] = fmaf(lh[k], ccl, zn[k]);
             lh_p[k] = lh[k];
         }
-        // ---- W2 += hid (x) lr out_delta (R:67-69) and its scaled copy: the next row's partial sums need them
+        // ---- W2 += hid (x) lr out_delta (R:67-69), in the scaled domain: the next row's partial sums need it
         const f2_t fs2 = pack2(fscale, fscale);
+#pragma unroll
+        for (int j = 0; j < OJ; ++j) lo2[j] = mul2(lo2[j], fs2);
 #pragma unroll
         for (int k = 0; k < UPT; ++k) {
             const f2_t h2 = pack2(hid[k], hid[k]);
 #pragma unroll
-            for (int j = 0; j < OJ; ++j) {
-                w2[k][j] = fma2(h2, lo2[j], w2[k][j]);
-                w2q[k][j] = mul2(w2[k][j], fs2);
-            }
+            for (int j = 0; j < OJ; ++j) w2s[k][j] = fma2(h2, lo2[j], w2s[k][j]);
         }
         par ^= 1;
     };
@@ -807,9 +812,9 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
 #pragma unroll
             for (int j = 0; j < OJ; ++j) {
                 float a0, a1;
-                unpack2(w2[k][j], a0, a1);
-                if (2 * j < O) w_out[oW2 + h * O + 2 * j] = a0;
-                if (2 * j + 1 < O) w_out[oW2 + h * O + 2 * j + 1] = a1;
+                unpack2(w2s[k][j], a0, a1);
+                if (2 * j < O) w_out[oW2 + h * O + 2 * j] = a0 * inv_fscale;
+                if (2 * j + 1 < O) w_out[oW2 + h * O + 2 * j + 1] = a1 * inv_fscale;
             }
             w_out[oB1 + h] = b1[k];
         }
@@ -1115,10 +1120,10 @@ __device__ __forceinline__ void lik_fast(const float *__restrict__ lw, const flo
 namespace ptfnn {
 
 // K5 applies to the wide-hidden specialisations whose geometry matches the tcgen05 tile (M = 128 rows,
-// N = H = 256 accumulator columns, one epilogue warp per TMEM lane quadrant)
+// H = 256 hidden units in two N = 128 halves, one epilogue warp per TMEM lane quadrant + the MMA warp)
 template <int I, int H, int O, int NT>
 struct UseTc {
-    static constexpr bool value = (H == 256 && NT == 128 && (O % 2) == 0 && ((H * O) % 4) == 0);
+    static constexpr bool value = (H == 256 && NT == tc::kThreads && O <= tc::kN2);
 };
 
 // ==========================================================================================
@@ -1148,6 +1153,7 @@ struct ChainParams {
     double *last4;                 // [R][4]  rmse_train, rmse_test, acc_train, acc_test carried rows (R:420-423)
     float *gd_cache;               // [R][P]  langevin_gradient(w) memo (wide nets: the working copy too)
     float *pgd_buf;                // [R][P]  langevin_gradient(w_prop) of wide nets (0 otherwise)
+    float *prop_buf;               // [R][P]  the proposal of the tcgen05 topologies (their shared memory holds the MMA operands)
     int *gd_valid;                 // [R]
     // ---- traces
     float *pos_w;                  // [R][S][P]
@@ -1224,7 +1230,7 @@ __host__ __device__ inline ChainSmem chain_smem_layout(int P, int IP, int nt, in
     // replaced by the tcgen05 operands, and the SGD pass's TMA tiles + team scratch alias the A tile
     // (the two passes never overlap in time)
     const bool tc = tc_bytes > 0;
-    L.off_w = take(tc ? 0 : L.P4 * 4); L.off_prop = take(L.P4 * 4);
+    L.off_w = take(tc ? 0 : L.P4 * 4); L.off_prop = take(tc ? 0 : L.P4 * 4);
     // langevin_gradient(w) and langevin_gradient(w_prop): shared memory, or (wide nets) the replica's global rows
     L.off_gd = take(gd_in_smem ? L.P4 * 4 : 0); L.off_pgd = take(gd_in_smem ? L.P4 * 4 : 0);
     L.off_lw = take(tc ? (size_t)tc_bytes : (size_t)lik_floats * 4);   // likelihood layout of the proposal (LikLayout) | tc::Smem
@@ -1515,7 +1521,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
         for (int r = vblock; r < p.R; r += nvb) {
             // ---------------- load this replica's state ----------------
             if constexpr (TEAM) { s_gd = p.gd_cache + (size_t)r * P; s_pgd = p.pgd_buf + (size_t)r * P; }
-            if constexpr (TC) s_w = p.w + (size_t)r * P;             // the state vector stays in its global row
+            if constexpr (TC) { s_w = p.w + (size_t)r * P; s_prop = p.prop_buf + (size_t)r * P; }   // state and proposal stay in global rows
             double eta, tau, lik, prior_cur, last_rtr, last_rte, last_atr, last_ate;
             int n_acc, init_count, gd_valid;
             auto load_state = [&]() {            // __ldcg: with speculative windows another CTA wrote it
@@ -1581,13 +1587,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     double dummy = 0.0;
                     int c0 = 0;
                     if constexpr (TC) {
-                        // through s_prop (dead at this point): the epilogue reads the output layer with
-                        // 16-byte loads and the global rows of w are only 8-byte aligned for odd P
-                        for (int j = tid; j < P; j += NT) s_prop[j] = s_w[j];
-                        __syncthreads();
                         double d2 = 0.0, d3 = 0.0;
                         int c1 = 0;
-                        tc_likelihood(s_prop, false, s[0], dummy, c0, d2, d3, c1);
+                        tc_likelihood(s_w, false, s[0], dummy, c0, d2, d3, c1);
                     } else {
                         lik_prepare<I, H, O>(s_lw, s_w, tid, NT);
                         __syncthreads();
@@ -1614,7 +1616,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                 const bool lg = p.use_lg && ((double)lx < p.l_prob);              // R:329
                 // ---- Langevin branch, first SGD epoch: w_gd = langevin_gradient(w)   (R:330)
                 if (lg && !gd_valid) {
-                    if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_gd, train, p.staged != 0, p.lr, stream, s_team);
+                    if constexpr (TEAM) { if (tid < kTeamThreads) sgd_pass_team<I, H, O, TASK, kTeamThreads>(s_w, s_gd, train, p.staged != 0, p.lr, stream, s_team); }
                     else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_w, s_gd, train, p.staged != 0, p.lr, stream);
                     __syncthreads();
                     gd_valid = p.memo;
@@ -1668,7 +1670,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
                     }
                 } else {
                     if (lg) {
-                        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream, s_team);
+                        if constexpr (TEAM) { if (tid < kTeamThreads) sgd_pass_team<I, H, O, TASK, kTeamThreads>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream, s_team); }
                         else if (is_sgd_warp) sgd_pass<I, H, O, TASK>(s_prop, s_pgd, train, p.staged != 0, p.lr, stream);
                         __syncthreads();
                     }
@@ -1949,7 +1951,7 @@ __global__ void __launch_bounds__(NT) op_forward_kernel(const float *w, DataView
 }
 
 template <int I, int H, int O, int TASK, int NT>
-__global__ void __launch_bounds__(UseSgdTeam<H>::value ? NT : 32) op_sgd_kernel(const float *w_in, float *w_out, DataView d, float lr, int depth) {
+__global__ void __launch_bounds__(UseSgdTeam<H>::value ? kTeamThreads : 32) op_sgd_kernel(const float *w_in, float *w_out, DataView d, float lr, int depth) {
     constexpr int P = NetSizes<I, H, O>::P;
     constexpr int IP = IPad<I>::value;
     constexpr bool TEAM = UseSgdTeam<H>::value;
@@ -1968,7 +1970,7 @@ __global__ void __launch_bounds__(UseSgdTeam<H>::value ? NT : 32) op_sgd_kernel(
     st.bar0 = &s_bar[0]; st.bar1 = &s_bar[1];
     st.parity0 = st.parity1 = 0u;
     for (int e = 0; e < depth; ++e) {                       // R:108 `depth` epochs (sgd_depth is always 1, R:170)
-        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, NT>(s_w, s_w, d, false, lr, st, s_team);
+        if constexpr (TEAM) sgd_pass_team<I, H, O, TASK, kTeamThreads>(s_w, s_w, d, false, lr, st, s_team);
         else sgd_pass<I, H, O, TASK>(s_w, s_w, d, false, lr, st);   // always exercise the TMA-streamed path
         __syncthreads();
     }
@@ -1983,7 +1985,6 @@ __global__ void __launch_bounds__(NT) op_forward_tc_kernel(const float *w, const
     if constexpr (UseTc<I, H, O, NT>::value) {
         extern __shared__ __align__(128) unsigned char smem_raw[];
         __shared__ double s_red[3 * (NT / 32)];
-        __shared__ __align__(16) float s_tail[H * O + H + O + 4];  // [W2, B1, B2]: the epilogue reads W2 with 16-byte loads
         constexpr int P = NetSizes<I, H, O>::P;
         w += (size_t)blockIdx.x * P;
         if (fx) fx += (size_t)blockIdx.x * n;
@@ -1996,10 +1997,7 @@ __global__ void __launch_bounds__(NT) op_forward_tc_kernel(const float *w, const
         __syncthreads();
         double s[3] = {0.0, 0.0, 0.0};
         int c = 0;
-        // (the rows of a batch of weight vectors are only 8-byte aligned for odd P: go through shared memory)
-        for (int j = threadIdx.x; j < H * O + H + O; j += NT) s_tail[j] = w[I * H + j];
-        __syncthreads();
-        tc::lik_pass<I, H, O, TASK, NT, true>(smem_raw, st, tiles, y, n, s_tail - I * H, s[0], s[1], c, fx, prob);
+        tc::lik_pass<I, H, O, TASK, NT, true>(smem_raw, st, tiles, y, n, w, s[0], s[1], c, fx, prob);
         s[2] = (double)c;
         block_sum<3, NT>(s, s_red);
         if (threadIdx.x == 0) { sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2]; }

@@ -41,6 +41,21 @@ __global__ void op_prior_kernel(int task, int I, int H, int O, const float *w, d
     }
 }
 
+// sum of an int array (the replicas' acceptance counters: feedback for the speculative-window depth)
+__global__ void sum_int_kernel(const int *v, int n, long long *out) {
+    __shared__ long long red[8];
+    long long a = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) a += v[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+        *out = t;
+    }
+}
+
 // Dump the Philox draws of free-running mode (verification only).
 __global__ void draws_kernel(uint64_t seed, int crn, int replica_offset, int R, int P, int i0, int n, float *lx,
                              float *z, float *z_eta, float *u) {

@@ -1,28 +1,40 @@
 // K5: tcgen05 likelihood pass for wide hidden layers (BASELINE configs[4], FNN 16-256-10).
 //
 // Network.evaluate_proposal (C:134-153) + likelihood_func (C:209-222) with a FIXED weight vector is the
-// one place on the hot path where a layer really is a dense GEMM:  Z[N x H] = X[N x I] . W1[I x H] - B1.
-// It runs on the 5th-generation tensor cores:
+// one place on the hot path where the layers really are dense GEMMs:
+//     Z[N x H] = X[N x I] . W1[I x H] - B1,   hid = sigmoid(Z),   Z2[N x O] = hid[N x H] . W2[H x O] - B2.
+// BOTH run on the 5th-generation tensor cores; the CUDA cores keep the sigmoids and the softmax epilogue:
 //
-//   * A operand = a 128-row tile of the data set, stored ONCE per data set in HBM in the UMMA
+//   * layer 1, A operand = a 128-row tile of the data set, stored ONCE per data set in HBM in the UMMA
 //     canonical K-major / no-swizzle layout (8-row x 16-byte core matrices), so that one 1-D TMA
 //     bulk copy (UBLKCP) lands it in shared memory ready for the tensor core.  The tile is augmented
-//     with a constant-one column: the bias is part of the GEMM.
-//   * B operand = -log2(e) W1^T (and +log2(e) B1 in the bias row), rebuilt per proposal in shared
-//     memory: the accumulator is born in the ex2 domain of the sigmoid.
-//   * fp32 accuracy from the tf32 pipe: both operands are split into tf32 "hi" and "lo" parts and
+//     with a constant-one column: the bias is part of the GEMM.  B operand = -log2(e) W1^T (and +log2(e) B1
+//     in the bias row), rebuilt per proposal in shared memory: the accumulator is born in the ex2 domain
+//     of the sigmoid.  tcgen05.mma.cta_group::1.kind::tf32 (SS), M = 128, N = 128 (one half of the hidden
+//     layer at a time), K = 8 per instruction.
+//   * layer 2, A operand = the hidden activations IN TENSOR MEMORY: the epilogue threads read 32 columns of
+//     pre-activations (tcgen05.ld), apply the grouped-reciprocal sigmoid and write the activations back IN PLACE
+//     (tcgen05.st) -- the accumulator columns of layer 1 become the A operand of layer 2 (TS-mode MMA,
+//     A[row = lane][k = column]).  B operand = -log2(e) W2^T padded to 16 outputs, in shared memory.  Round 1
+//     evaluated this layer on the CUDA cores: 2560 FMAs and 640 broadcast LDS.128 per row kept the FMA pipe
+//     and the shared-memory port busier than the XU pipe the sigmoids need (tensor pipe 12 %, shared-memory
+//     wavefronts 59 %).
+//   * fp32 accuracy from the tf32 pipe: every operand is split into tf32 "hi" and "lo" parts and
 //     D = A_hi B_hi + A_lo B_hi + A_hi B_lo (3xTF32, error ~2^-21).  Plain tf32 (2^-11) would put
-//     ~1e-2 of noise on a 20 000-row log-likelihood, i.e. on the Metropolis-Hastings decision.
-//   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = H = 256, K = 8 per instruction, issued by one
-//     elected thread; accumulator 128 lanes x 256 columns of TMEM (two temperatures per SM = all 512
-//     columns); completion through tcgen05.commit -> mbarrier.
-//   * epilogue on the CUDA cores straight from TMEM (tcgen05.ld 32x32b.x32): grouped-reciprocal
-//     sigmoids, the H x O output layer with packed FFMA2, softmax-of-sigmoid log-likelihood (C:108-110,
-//     C:215-219).  Each lane quadrant of TMEM is read by two warps (128 hidden units each); the two
-//     halves of a row meet through shared memory.
+//     ~1e-2 of noise on a 20 000-row log-likelihood, i.e. on the Metropolis-Hastings decision.  For layer 2
+//     the hi / lo parts of W2 sit side by side in one N = 32 operand (one MMA gives A_hi B_hi | A_hi B_lo),
+//     the lo part of the activations is a second, N = 16 MMA: 2 instead of 3 instructions per K step --
+//     a CTA issues one small MMA per ~56 cycles whatever its N (tools/ts_mma_probe.cu), so their NUMBER is
+//     what layer 2 costs.
+//   * TMEM, 256 columns per CTA (two temperatures per SM): Z = 128 (layer-1 accumulator of one half of the hidden
+//     layer, overwritten by hid_hi), L = 2 x 32 (hid_lo of the sub-block in flight, double buffered), D2 = 32
+//     (layer-2 accumulator: 16 columns hi.hi + lo.hi, 16 columns hi.lo).  MMAs of one CTA execute in issue order,
+//     so layer 1 of the next half is issued right behind the layer-2 MMAs that still read Z.
+//   * warp-specialised: four epilogue warps (one per TMEM lane quadrant, thread = row) and one MMA warp whose elected
+//     lane issues every MMA; hand-offs through mbarriers only (tcgen05.commit -> mbarrier towards the epilogue, one
+//     arrival per epilogue warp towards the MMA warp) -- no CTA-wide barrier inside the pass.
 //
-// The epilogue, not the tensor pipe, bounds the pass (256 sigmoids per row on the 16-lane MUFU unit),
-// as SURVEY 7 predicted; the tensor cores take the 2 I H flop of layer 1 off the FMA pipe.
+// The XU pipe (256 sigmoids per row at 16 lanes / clk / SM) bounds the pass, as SURVEY 7 predicted.
 #pragma once
 #include "ptfnn_device.cuh"
 
@@ -150,25 +162,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------------------------------
 // shared-memory plan of the pass (bytes; all parts 128-byte aligned)
 // ------------------------------------------------------------------------------------------
+constexpr int kN2 = 16;                          // outputs padded to the smallest N of an M = 128 MMA
+constexpr int kSub = 32;                         // hidden units per epilogue sub-block (one tcgen05.ld / st)
+constexpr int kHalf = 128;                       // hidden units per layer-1 MMA (N)
+constexpr int kTmemCols = 256;                   // Z 128 | L 2 x 32 | D2 32 | spare 32
+constexpr int kColZ = 0, kColL = 128, kColD = 192;
+
 template <int I, int H, int O>
 struct Smem {
-    static constexpr int off_b = 0;
-    static constexpr int off_a = off_b + BGeometry<I, H>::B_BYTES;
-    static constexpr int off_x = off_a + Geometry<I>::A_TILE_BYTES;          // [kRows][XO] partial output sums of the upper half
-    static constexpr int XO = (O + 3) & ~3;
-    static constexpr int off_bar = off_x + kRows * XO * 4;                   // a_full, mma_done, tmem slot
-    static constexpr int total = off_bar + 32;
+    static constexpr int off_b = 0;                                          // layer 1: hi | lo, CH chunks x H rows x 16 B
+    static constexpr int off_b2 = off_b + BGeometry<I, H>::B_BYTES;           // layer 2: H/4 chunks x (16 hi rows + 16 lo rows) x 16 B
+    static constexpr int B2_CHUNK_BYTES = 2 * kN2 * 16;
+    static constexpr int B2_BYTES = (H / 4) * B2_CHUNK_BYTES;
+    static constexpr int off_a = off_b2 + B2_BYTES;
+    static constexpr int off_bar = off_a + Geometry<I>::A_TILE_BYTES;        // a_full, z_full, l_free[2], d_full, tmem slot
+    static constexpr int total = off_bar + 128;
 };
-__host__ __device__ constexpr int tc_smem_bytes(int I, int H, int O) {
-    return 2 * (2 * (((I + 3) / 4 + 2) / 2)) * H * 16 + a_tile_floats(I) * 4 + kRows * ((O + 3) & ~3) * 4 + 32;
-}
 
-// B operand of a weight vector w (layout a1): thread n < H writes row n (hidden unit n) of every chunk.
+// Both B operands of a weight vector w (layout a1).  Layer 1: row n (hidden unit n) of every chunk.  Layer 2: chunk
+// c holds hidden units 4c .. 4c+3 (K) for the 16 (padded) outputs: rows 0-15 the tf32 hi part, rows 16-31 the lo part.
 template <int I, int H, int O>
 __device__ __forceinline__ void build_b(unsigned char *smem, const float *w, int tid, int nt) {
     using G = Geometry<I>;
     using BG = BGeometry<I, H>;
-    constexpr int oB1 = I * H + H * O;
+    using S = Smem<I, H, O>;
+    constexpr int oW2 = I * H, oB1 = I * H + H * O;
     for (int n = tid; n < H; n += nt) {
 #pragma unroll
         for (int c = 0; c < G::CH; ++c) {
@@ -183,40 +201,107 @@ __device__ __forceinline__ void build_b(unsigned char *smem, const float *w, int
                 lo[e] = tf32_hi(v - hi[e]);
             }
             const int off = c * BG::B_CHUNK_BYTES + n * 16;
-            *reinterpret_cast<float4 *>(smem + Smem<I, H, O>::off_b + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(smem + Smem<I, H, O>::off_b + BG::B_HALF_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4 *>(smem + S::off_b + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4 *>(smem + S::off_b + BG::B_HALF_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
+    }
+    for (int idx = tid; idx < (H / 4) * kN2; idx += nt) {
+        const int c = idx / kN2, o = idx % kN2;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v = o < O ? -kL2E * w[oW2 + (c * 4 + e) * O + o] : 0.0f;     // -log2(e) W2[h][o]: z2 in the ex2 domain too
+            hi[e] = tf32_hi(v);
+            lo[e] = tf32_hi(v - hi[e]);
+        }
+        unsigned char *row = smem + S::off_b2 + c * S::B2_CHUNK_BYTES + o * 16;
+        *reinterpret_cast<float4 *>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(row + kN2 * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
+// TS-mode MMA: A from tensor memory (rows = lanes, K = consecutive columns), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// 32 registers per thread -> 32 lanes x 32 consecutive columns of TMEM (lane = TMEM lane)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kEpiThreads = 128;                 // warps 0-3: one per TMEM lane quadrant (thread = row of the tile)
+constexpr int kThreads = 160;                    // + warp 4: issues every MMA (a CTA issues one small MMA per ~56 cycles;
+                                                 //   done by an epilogue warp, that time was added to the sigmoids' instead of hidden under them)
+// mbarriers of the pass
+enum { kBarA = 0, kBarZ = 1, kBarL0 = 2, kBarL1 = 3, kBarD = 4, kBarH0 = 5, kBarH1 = 6, kNumBars = 7 };
+
 struct State {
-    uint32_t tmem;          // TMEM base address of the 128 x H accumulator
-    uint32_t ph_a, ph_mma;  // mbarrier phases (every thread tracks them)
+    uint32_t tmem;                      // TMEM base address of the CTA's 256 columns
+    // mbarrier phases, each tracked by the role that waits on it
+    uint32_t ph_a, ph_h0, ph_h1;        // issuer: A tile landed; hid of sub-block buffer b stored by all four warps
+    uint32_t ph_z, ph_d, ph_l0, ph_l1;  // epilogue: Z full; D2 full; L[b] consumed
+    bool pend_l0, pend_l1;              // epilogue: a commit on L[b] that has not been waited for yet
 };
 
 // One-time set-up by the whole CTA: mbarriers, TMEM allocation (warp 0).
 template <int I, int H, int O>
 __device__ __forceinline__ void setup(unsigned char *smem, State &st) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Smem<I, H, O>::off_bar);
-    uint32_t *slot = reinterpret_cast<uint32_t *>(bars + 2);
-    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    if (threadIdx.x < 32) tmem_alloc(slot, H);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bars + kNumBars);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kNumBars; ++k) mbar_init(&bars[k], (k == kBarH0 || k == kBarH1) ? kEpiThreads / 32 : 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     st.tmem = *slot;
-    st.ph_a = st.ph_mma = 0u;
+    st.ph_a = st.ph_h0 = st.ph_h1 = 0u;
+    st.ph_z = st.ph_d = st.ph_l0 = st.ph_l1 = 0u;
+    st.pend_l0 = st.pend_l1 = false;
 }
 template <int I, int H, int O>
 __device__ __forceinline__ void teardown(State &st) {
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(st.tmem, H);
+    if (threadIdx.x < 32) tmem_dealloc(st.tmem, kTmemCols);
 }
 
 // The pass over one data set.  tiles = A tiles of the data set (pack_a_kernel), y = labels, n rows.
-// B must have been built (build_b) and made visible (fence_async_smem + __syncthreads) by the caller.
-// w2 / b2 point at the output layer of the SAME weight vector (layout a1, anywhere readable).
+// Both B operands must have been built (build_b) and made visible (fence_async_smem + __syncthreads) by the caller.
+// w points at the SAME weight vector (layout a1, anywhere readable): only B2 is read from it here.
+// Called by the whole CTA (kThreads); the caller synchronises the CTA afterwards (block_sum does).
+//
+//   issuer (warp 4, one lane)                         epilogue (warps 0-3, thread = row)
+//   wait A tile; layer 1 (half 0) -> Z; commit Z      wait Z
+//   per 32-unit sub-block g, buffer b = g & 1:        ld z; sigmoid; hi -> Z in place, lo -> L[b] (after L[b] is free);
+//     wait H[b]                                         fence; arrive H[b]  (one lane per warp)
+//     layer 2 from Z / L[b] -> D2
+//     commit L[b]  |  + layer 1 of the next half, commit Z  |  commit D (last sub-block of the tile)
+//                                                      wait D; ld D2; output sigmoids, softmax, sums
+// MMAs execute in issue order, so layer 1 of the next half / tile is issued right behind the layer-2 MMAs that still read
+// Z; the epilogue's own reads of Z and D2 precede its arrival on H, which precedes every MMA that overwrites them.
 template <int I, int H, int O, int TASK, int NT, bool WRITE>
 __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const float *__restrict__ tiles,
                                          const float *__restrict__ y, int n, const float *__restrict__ w,
@@ -224,108 +309,154 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
     using G = Geometry<I>;
     using BG = BGeometry<I, H>;
     using S = Smem<I, H, O>;
-    static_assert(NT == 128 && H % 32 == 0 && H <= 256, "one warp per TMEM lane quadrant: thread = row, all H accumulator columns");
-    static_assert(O % 2 == 0 && (H * O) % 4 == 0, "output-layer rows are read in aligned pairs");
-    constexpr int oW2 = I * H, oB2 = I * H + H * O + H;
-    constexpr uint32_t IDESC = instr_desc_tf32(kRows, H);
+    static_assert(NT == kThreads && H % kHalf == 0 && H <= 256 && O <= kN2, "four epilogue warps (thread = row) + the MMA warp");
+    constexpr int oB2 = I * H + H * O + H;
+    constexpr uint32_t IDESC1 = instr_desc_tf32(kRows, kHalf);
+    constexpr uint32_t IDESC2A = instr_desc_tf32(kRows, 2 * kN2), IDESC2B = instr_desc_tf32(kRows, kN2);
+    constexpr int NHALF = H / kHalf, NSUB = kHalf / kSub;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quad = warp & 3;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
-    uint64_t *bar_a = &bars[0], *bar_mma = &bars[1];
-    const uint32_t a_base = smem_u32(smem + S::off_a), b_base = smem_u32(smem + S::off_b);
+    const uint32_t a_base = smem_u32(smem + S::off_a), b_base = smem_u32(smem + S::off_b), b2_base = smem_u32(smem + S::off_b2);
+    const uint32_t tZ = st.tmem + kColZ, tL = st.tmem + kColL, tD = st.tmem + kColD;
     const int ntiles = (n + kRows - 1) / kRows;
+    if (ntiles <= 0) return;
 
-    if (tid == 0 && ntiles > 0) {
-        mbar_arrive_expect_tx(bar_a, G::A_TILE_BYTES);
-        tma_load_1d(smem + S::off_a, tiles, G::A_TILE_BYTES, bar_a);
-    }
-    for (int t = 0; t < ntiles; ++t) {
-        if (tid == 0) {
-            mbar_wait(bar_a, st.ph_a);
-            tc_fence_after();
-            // D = A_hi B_hi + A_lo B_hi + A_hi B_lo, K = 8 per instruction (two 16-byte chunks)
-            bool acc = false;
+    if (warp == kEpiThreads / 32) {
+        // ================= the MMA warp =================
+        if (lane == 0) {
+            // layer 1 of one half of the hidden layer: Z = A_hi B_hi + A_lo B_hi + A_hi B_lo (N = 128 rows of B from `half`)
+            auto issue_layer1 = [&](int half) {
+                const uint32_t bh = b_base + (uint32_t)half * kHalf * 16;
+                bool acc = false;
 #pragma unroll
-            for (int ks = 0; ks < G::CH / 2; ++ks) {
-                mma_tf32(st.tmem, smem_desc(a_base + ks * 2 * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
-                         smem_desc(b_base + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC, acc);
-                acc = true;
-            }
+                for (int ks = 0; ks < G::CH / 2; ++ks) {
+                    mma_tf32(tZ, smem_desc(a_base + ks * 2 * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
+                             smem_desc(bh + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC1, acc);
+                    acc = true;
+                }
 #pragma unroll
-            for (int ks = 0; ks < G::CL / 2; ++ks)
-                mma_tf32(st.tmem, smem_desc(a_base + (G::CH + ks * 2) * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
-                         smem_desc(b_base + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC, true);
+                for (int ks = 0; ks < G::CL / 2; ++ks)
+                    mma_tf32(tZ, smem_desc(a_base + (G::CH + ks * 2) * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
+                             smem_desc(bh + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC1, true);
 #pragma unroll
-            for (int ks = 0; ks < G::CH / 2; ++ks)
-                mma_tf32(st.tmem, smem_desc(a_base + ks * 2 * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
-                         smem_desc(b_base + BG::B_HALF_BYTES + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC, true);
-            mma_commit(bar_mma);
-        }
-        st.ph_a ^= 1u;
-        mbar_wait(bar_mma, st.ph_mma);
-        st.ph_mma ^= 1u;
-        tc_fence_after();
-        if (tid == 0 && t + 1 < ntiles) {           // the MMAs have consumed the A tile: fetch the next one under the epilogue
-            mbar_arrive_expect_tx(bar_a, G::A_TILE_BYTES);
-            tma_load_1d(smem + S::off_a, tiles + (size_t)(t + 1) * G::A_TILE_FLOATS, G::A_TILE_BYTES, bar_a);
-        }
-        // ---- epilogue: this thread = row (32 quad + lane) of the tile, all H hidden units
-        f2_t acc2[O / 2];
+                for (int ks = 0; ks < G::CH / 2; ++ks)
+                    mma_tf32(tZ, smem_desc(a_base + ks * 2 * G::A_CHUNK_BYTES, G::A_CHUNK_BYTES, 128),
+                             smem_desc(bh + BG::B_HALF_BYTES + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC1, true);
+            };
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&bars[kBarA], st.ph_a);
+                st.ph_a ^= 1u;
+                tc_fence_after();
+                issue_layer1(0);
+                mma_commit(&bars[kBarZ]);
 #pragma unroll
-        for (int j = 0; j < O / 2; ++j) acc2[j] = pack2(0.0f, 0.0f);
-#pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
-            float z[32];
-            const int h0 = cb * 32;
-            tmem_ld32(st.tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)h0, z);
+                for (int half = 0; half < NHALF; ++half) {
 #pragma unroll
-            for (int g = 0; g < 32; g += 4) {
-                f2_t zz[2] = {pack2(z[g], z[g + 1]), pack2(z[g + 2], z[g + 3])}, hh[2];
-                sigmoid_pairs<2>(zz, hh);
-                float hid[4];
-                unpack2(hh[0], hid[0], hid[1]);
-                unpack2(hh[1], hid[2], hid[3]);
+                    for (int sb = 0; sb < NSUB; ++sb) {
+                        const int b = sb & 1;
+                        if (b) { mbar_wait(&bars[kBarH1], st.ph_h1); st.ph_h1 ^= 1u; }
+                        else { mbar_wait(&bars[kBarH0], st.ph_h0); st.ph_h0 ^= 1u; }
+                        tc_fence_after();
+                        // layer 2, K = 32 hidden units of this sub-block: hid_hi . [W2_hi | W2_lo] (N = 32), hid_lo . W2_hi (N = 16)
 #pragma unroll
-                for (int q = 0; q < 4; q += 2) {
-                    // output-layer rows of hidden units h, h+1: 2 O contiguous floats (layout a1), 16-byte aligned
-                    const float4 *wr = reinterpret_cast<const float4 *>(w + oW2 + (h0 + g + q) * O);
-                    float wv[2 * O];
-#pragma unroll
-                    for (int v4 = 0; v4 < (2 * O) / 4; ++v4) {
-                        const float4 u = wr[v4];
-                        wv[4 * v4] = u.x; wv[4 * v4 + 1] = u.y; wv[4 * v4 + 2] = u.z; wv[4 * v4 + 3] = u.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < O / 2; ++j) {
-                        acc2[j] = fma2(pack2(wv[2 * j], wv[2 * j + 1]), pack2(hid[q], hid[q]), acc2[j]);
-                        acc2[j] = fma2(pack2(wv[O + 2 * j], wv[O + 2 * j + 1]), pack2(hid[q + 1], hid[q + 1]), acc2[j]);
+                        for (int ks = 0; ks < kSub / 8; ++ks) {
+                            const uint32_t bk = b2_base + (uint32_t)(((half * kHalf + sb * kSub) / 4 + ks * 2) * S::B2_CHUNK_BYTES);
+                            const uint64_t bd = smem_desc(bk, S::B2_CHUNK_BYTES, 128);
+                            mma_tf32_ts(tD, tZ + (uint32_t)(sb * kSub + ks * 8), bd, IDESC2A, !(half == 0 && sb == 0 && ks == 0));
+                            mma_tf32_ts(tD, tL + (uint32_t)(b * kSub + ks * 8), bd, IDESC2B, true);
+                        }
+                        if (sb < NSUB - 1) {
+                            mma_commit(&bars[b ? kBarL1 : kBarL0]);
+                        } else if (half + 1 < NHALF) {
+                            issue_layer1(half + 1);            // executes behind the MMAs above (issue order): Z is free by then
+                            mma_commit(&bars[kBarZ]);
+                        } else {
+                            mma_commit(&bars[kBarD]);
+                        }
                     }
                 }
             }
         }
-        float part[O];
+        return;
+    }
+
+    // ================= the epilogue warps =================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;          // this warp's TMEM lane quadrant
+    float b2l[O];
 #pragma unroll
-        for (int j = 0; j < O / 2; ++j) unpack2(acc2[j], part[2 * j], part[2 * j + 1]);
-        const int row_in = quad * 32 + lane;
-        tc_fence_before();
-        __syncthreads();                              // every TMEM read of this tile is done: the next tile's MMAs may overwrite it
+    for (int o = 0; o < O; ++o) b2l[o] = kL2E * w[oB2 + o];
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[kBarA], G::A_TILE_BYTES);
+        tma_load_1d(smem + S::off_a, tiles, G::A_TILE_BYTES, &bars[kBarA]);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+#pragma unroll
+        for (int half = 0; half < NHALF; ++half) {
+            mbar_wait(&bars[kBarZ], st.ph_z);          // layer-1 pre-activations of this half are in Z (and every earlier MMA is done)
+            st.ph_z ^= 1u;
+            tc_fence_after();
+            if (half == NHALF - 1 && tid == 0 && t + 1 < ntiles) {     // layer 1 has consumed the A tile: fetch the next one under the epilogue
+                mbar_arrive_expect_tx(&bars[kBarA], G::A_TILE_BYTES);
+                tma_load_1d(smem + S::off_a, tiles + (size_t)(t + 1) * G::A_TILE_FLOATS, G::A_TILE_BYTES, &bars[kBarA]);
+            }
+#pragma unroll 1
+            for (int sb = 0; sb < NSUB; ++sb) {
+                const int b = sb & 1;
+                float z[32];
+                tmem_ld32(tZ + lane_base + (uint32_t)(sb * kSub), z);
+                float lo[32];
+#pragma unroll
+                for (int g = 0; g < 32; g += 4) {
+                    f2_t zz[2] = {pack2(z[g], z[g + 1]), pack2(z[g + 2], z[g + 3])}, hh[2];
+                    sigmoid_pairs<2>(zz, hh);
+                    float h4[4];
+                    unpack2(hh[0], h4[0], h4[1]);
+                    unpack2(hh[1], h4[2], h4[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        z[g + q] = tf32_hi(h4[q]);             // hi part, in place of the pre-activation
+                        lo[g + q] = h4[q] - z[g + q];          // lo part (the tensor core reads its leading 11 bits: 2^-21 relative to hid)
+                    }
+                }
+                if (b ? st.pend_l1 : st.pend_l0) {             // the layer-2 MMAs that read L[b] two sub-blocks ago
+                    mbar_wait(&bars[b ? kBarL1 : kBarL0], b ? st.ph_l1 : st.ph_l0);
+                    if (b) { st.ph_l1 ^= 1u; st.pend_l1 = false; } else { st.ph_l0 ^= 1u; st.pend_l0 = false; }
+                    tc_fence_after();
+                }
+                tmem_st32(tZ + lane_base + (uint32_t)(sb * kSub), z);
+                tmem_st32(tL + lane_base + (uint32_t)(b * kSub), lo);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[b ? kBarH1 : kBarH0]);      // this warp's 32 rows of the sub-block are in tensor memory
+                if (sb < NSUB - 1) { if (b) st.pend_l1 = true; else st.pend_l0 = true; }
+            }
+        }
+        // ---- output layer of the tile: D2 = hi.hi + lo.hi | hi.lo
+        mbar_wait(&bars[kBarD], st.ph_d);
+        st.ph_d ^= 1u;
+        tc_fence_after();
+        float d2[32];
+        tmem_ld32(tD + lane_base, d2);
+        tc_fence_before();                                     // (ordered before this warp's next arrival on H: D2 is rewritten after it)
+        const int row_in = warp * 32 + lane;
         const int r = t * kRows + row_in;
         if (r < n) {
             float out[O];
             const float yv = y[r];
 #pragma unroll
-            for (int o = 0; o < O; ++o) out[o] = sigmoid_fast(part[o] - w[oB2 + o]);   // R:54-55
+            for (int o = 0; o < O; ++o) out[o] = rcp_ftz(1.0f + ex2_ftz(d2[o] + d2[kN2 + o] + b2l[o]));     // R:54-55
             if constexpr (TASK == kTaskReg) {
                 const float e = yv - out[0];
                 s0 += (double)(e * e);
                 if constexpr (WRITE) fx_out[r] = out[0];
             } else {
                 int am = 0;
-                float se = 0.0f;
+                float se = 0.0f, om = out[0];
 #pragma unroll
                 for (int o = 0; o < O; ++o) se += expf(out[o]);                  // C:108-110
 #pragma unroll
-                for (int o = 1; o < O; ++o) am = (out[o] > out[am]) ? o : am;    // np.argmax: first max
+                for (int o = 1; o < O; ++o) { const bool g = out[o] > om; am = g ? o : am; om = g ? out[o] : om; }   // np.argmax: first max
                 const int lab = (int)yv;
                 float ol = out[0];
 #pragma unroll
@@ -343,7 +474,6 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                 }
             }
         }
-        tc_fence_after();
     }
 }
 

@@ -14,4 +14,4 @@
     X(cls_9_12_2, 1, 9, 12, 2, 128, 2)    /* Cancer, C:950-957 */                                     \
     X(cls_34_50_2, 1, 34, 50, 2, 128, 2)  /* Ionosphere, C:942-949 */                                 \
     X(cls_16_30_10, 1, 16, 30, 10, 128, 2) /* PenDigit, C:972-986 */                                  \
-    X(cls_16_256_10, 1, 16, 256, 10, 128, 2) /* PenDigit-shaped synthetic, BASELINE configs[4] */
+    X(cls_16_256_10, 1, 16, 256, 10, 160, 2) /* PenDigit-shaped synthetic, BASELINE configs[4] */

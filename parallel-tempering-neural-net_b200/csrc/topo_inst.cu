@@ -29,11 +29,11 @@ const PtfnnKernelSet *PTFNN_CAT(ptfnn_kernelset_, PTFNN_T_NAME)() {
         (const void *)init_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_forward_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
         (const void *)op_sgd_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT>,
-        ptfnn::UseSgdTeam<PTFNN_T_H>::value ? PTFNN_T_NT : 32,
+        ptfnn::UseSgdTeam<PTFNN_T_H>::value ? ptfnn::kTeamThreads : 32,
         kTc ? (const void *)op_forward_tc_kernel<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O, PTFNN_T_TASK, PTFNN_T_NT> : nullptr,
         kTc ? (const void *)tc::pack_a_kernel<PTFNN_T_I> : nullptr,
         tc::a_tile_floats(PTFNN_T_I), tc::Smem<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O>::total, tc::Smem<PTFNN_T_I, PTFNN_T_H, PTFNN_T_O>::off_a,
-        kTc ? PTFNN_T_H : 0,
+        kTc ? tc::kTmemCols : 0,
     };
     return &ks;
 }

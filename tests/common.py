@@ -52,7 +52,7 @@ def relerr(a, b):
 def lik_scale(cfg, ref, n_train, temps):
     """[R, S] magnitude of the terms of the proposed log-likelihood (row i+1 = step i); 1 for classification."""
     if cfg.task != on.REGRESSION:
-        return np.ones_like(ref.lik_prop)
+        return np.abs(ref.lik_prop)                          # a plain sum of log-probabilities: relative to itself
     tau = np.maximum(ref.state_tau, 1e-300)                  # row i+1: tau^2 proposed at step i (R:356)
     sse = (ref.rmse_train ** 2) * n_train                    # on accepted rows; carried rows understate it (harmless: a max below)
     t1 = 0.5 * n_train * np.abs(np.log(2.0 * np.pi * tau))

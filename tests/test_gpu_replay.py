@@ -220,3 +220,37 @@ def test_speculative_windows_are_bit_identical(memo):
         assert sw[0] == sw1[0] and sw[1] == sw1[1] and np.array_equal(sw[2], sw1[2]), depth
         for k in ("w", "eta", "lik", "prior", "tau", "num_accepted"):
             assert np.array_equal(st[k], st1[k]), (depth, k)
+
+
+def test_automatic_window_depth_follows_acceptance_and_changes_nothing():
+    """Ladders that leave CTA slots free (here 96 temperatures of the 4-64-1 net: ~10 slots each) get speculative
+    windows whose depth follows the acceptance rate observed so far on the run -- launches early in
+    the run, where everything is accepted, stay sequential; later ones go deep.  Whatever depth each launch picks, the
+    chain is the sequential one bit for bit."""
+    from ptnn_b200 import datasets
+    tr, te = datasets.synthetic_timeseries()
+    tr, te = tr[:3000], te[:1000]
+    R, S, si = 96, 121, 10
+    from ptnn_b200.sampler import geometric_ladder
+    temps = geometric_ladder(R, 2)
+    w0 = np.random.RandomState(5).randn(R, 385) * 0.5
+    out = {}
+    for depth in (1, 0, 6):                 # sequential | automatic | fixed
+        with Sampler(on.REGRESSION, (4, 64, 1), temps, S, si, use_langevin_gradients=True, l_prob=0.5, learn_rate=0.01,
+                     seed=9, common_random_numbers=True, memoize_gradient=1, debug_traces=True, speculation=depth) as s:
+            s.set_data(tr, te)
+            s.init_chains(w0)
+            while s.step < S - 1:
+                s.run(si)
+                s.sync()                    # (gives the asynchronous acceptance sample time to arrive: the depth may change)
+            out[depth] = (s.traces(), s.swap_stats(), s.get_state())
+    t1, sw1, st1 = out[1]
+    acc_rate = t1["accepted"][:, 60:].mean()
+    assert acc_rate < 0.6                   # the regime in which the automatic policy opens windows
+    for depth in (0, 6):
+        t, sw, st = out[depth]
+        for k in t1:
+            assert np.array_equal(t[k], t1[k]), (depth, k)
+        assert sw[0] == sw1[0] and np.array_equal(sw[2], sw1[2]), depth
+        for k in ("w", "eta", "lik", "prior", "tau", "num_accepted"):
+            assert np.array_equal(st[k], st1[k]), (depth, k)
