@@ -625,11 +625,13 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
     for (int k = 0; k < UPT; ++k) lh_p[k] = 0.0f;
     int par = 0;              // row parity: s_part is double buffered
 
-    // One row.  pbuf holds the PREVIOUS row on entry (its W1 update is still pending) and the NEXT row
-    // (look-ahead) on exit; cbuf is the current row (only the tile's last row needs it, for x_next.x + 1).
-    // The current row itself enters through zs (its pre-activations) and y.
-    auto row = [&](const bool boundary, float (&pbuf)[IP], const float (&cbuf)[IP], uint32_t y_addr, uint32_t xn_addr,
-                   float c_in, bool has_next) {
+    // One row.  The current row enters through zs (its pre-activations) and y.  Input rows are NOT kept in registers
+    // from one row to the next: the previous row (its W1 update is still pending) and the look-ahead row are read from
+    // shared memory where they are used (broadcast LDS.128: the port is idle otherwise) -- 32 registers that the
+    // 168-register budget of the five-warp tcgen05 geometry does not have.  xprev = shared-memory address of the previous
+    // row; the pending update is flushed before a streamed tile buffer is recycled.
+    uint32_t xprev = 0u;
+    auto row = [&](const bool boundary, uint32_t xcur_addr, uint32_t y_addr, uint32_t xn_addr, float c_in, bool has_next) {
         const float yv = lds_f32(y_addr);
         // ---- hidden activations (R:52-53)
         float hid[UPT];
@@ -648,33 +650,40 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
             sraw[2 * j + 1] = (2 * j + 1 < O) ? __reduce_add_sync(0xffffffffu, __float_as_int(a1)) : 0;
         }
         // ---- in the shadow of the REDUX latency: W1 / B1 update of the PREVIOUS row (R:74-78) ...
+        {
+            float xp[IP];
+            lds_row<IP>(xprev, xp);
 #pragma unroll
-        for (int i = 0; i < I; ++i) vfma_s<UPT>(w1[i], lh_p, pbuf[i], w1[i]);
+            for (int i = 0; i < I; ++i) vfma_s<UPT>(w1[i], lh_p, xp[i], w1[i]);
+        }
 #pragma unroll
         for (int k = 0; k < UPT; ++k) b1[k] -= lh_p[k];
         // ... then the look-ahead row takes its place: stale pre-activation of the next row, with the weights
         // BEFORE this row's update (the previous row's has just been applied)
         float cr = c_in;
+        float xn[IP];
         if (boundary) {                               // literal at every call site: folded after inlining
             if (has_next) {
-                lds_row<IP>(xn_addr, pbuf);
+                float xc[IP];
+                lds_row<IP>(xn_addr, xn);
+                lds_row<IP>(xcur_addr, xc);
                 cr = 1.0f;
 #pragma unroll
-                for (int i = 0; i < I; ++i) cr = fmaf(cbuf[i], pbuf[i], cr);
+                for (int i = 0; i < I; ++i) cr = fmaf(xc[i], xn[i], cr);
             } else {
 #pragma unroll
-                for (int i = 0; i < IP; ++i) pbuf[i] = 0.0f;
+                for (int i = 0; i < IP; ++i) xn[i] = 0.0f;
                 cr = 1.0f;
             }
         } else {
-            lds_row<IP>(xn_addr, pbuf);
+            lds_row<IP>(xn_addr, xn);
         }
         float zn[UPT];
         {
             float t[UPT];
             vmul_s<UPT>(t, b1, -1.0f);
 #pragma unroll
-            for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], pbuf[i], t);
+            for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], xn[i], t);
             vmul_s<UPT>(zn, t, -kL2E);
         }
         const float ccl = -kL2E * cr;
@@ -735,27 +744,28 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
             for (int j = 0; j < OJ; ++j) w2s[k][j] = fma2(h2, lo2[j], w2s[k][j]);
         }
         par ^= 1;
+        xprev = xcur_addr;
     };
-    // applies the W1 / B1 update still pending after the last row
-    auto flush = [&](const float (&xp)[IP]) {
+    // applies the W1 / B1 update still pending after the last row processed (xprev)
+    auto flush = [&]() {
+        float xp[IP];
+        lds_row<IP>(xprev, xp);
 #pragma unroll
         for (int i = 0; i < I; ++i) vfma_s<UPT>(w1[i], lh_p, xp[i], w1[i]);
 #pragma unroll
         for (int k = 0; k < UPT; ++k) { b1[k] -= lh_p[k]; lh_p[k] = 0.0f; }
     };
 
-    // ---- rows.  Register buffers A / B alternate between "previous row" and "current row".
+    // ---- rows
     constexpr bool PlainRow = false, TileEnd = true;
-    float A[IP], B[IP];
-#pragma unroll
-    for (int i = 0; i < IP; ++i) A[i] = 0.0f;      // "previous row" of row 0: nothing pending
     if (!staged) { issue(0); wait(0); }
-    lds_row<IP>(xaddr(0), B);
+    xprev = xaddr(0);                              // "previous row" of row 0: nothing pending (lh_p = 0), any finite row
     {
-        float t[UPT];
+        float x0[IP], t[UPT];
+        lds_row<IP>(xaddr(0), x0);
         vmul_s<UPT>(t, b1, -1.0f);
 #pragma unroll
-        for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], B[i], t);
+        for (int i = 0; i < I; ++i) vfma_s<UPT>(t, w1[i], x0[i], t);
         vmul_s<UPT>(zs, t, -kL2E);
     }
     int r = 0;
@@ -782,8 +792,8 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
             const float *pc = s_c + (r - base);
             r += 2 * pairs;
             for (; pairs > 0; --pairs) {
-                row(PlainRow, A, B, py, px, pc[0], true);             // prev A, current B; A <- next
-                row(PlainRow, B, A, py + 4u, px + RBY, pc[1], true);  // prev B, current A; B <- next
+                row(PlainRow, px - RBY, py, px, pc[0], true);             // current row r, look-ahead r + 1
+                row(PlainRow, px, py + 4u, px + RBY, pc[1], true);        // current row r + 1, look-ahead r + 2
                 px += 2u * RBY; py += 8u; pc += 2;
             }
         }
@@ -791,17 +801,11 @@ __device__ __forceinline__ void sgd_pass_team(const float *w_in, float *w_out, c
         const bool has_next = last + 1 < n;
         if (has_next && !staged) wait(t + 1);        // issued 127 rows ago
         const uint32_t xnext = xaddr(has_next ? last + 1 : last);
-        if (last - r == 1) {
-            row(PlainRow, A, B, yaddr(r), xaddr(r + 1), s_c[r - base], true);
-            row(TileEnd, B, A, yaddr(last), xnext, 1.0f, has_next);
-        } else {                                     // odd-sized (last) tile: the roles end up swapped
-            row(TileEnd, A, B, yaddr(last), xnext, 1.0f, has_next);
-#pragma unroll
-            for (int i = 0; i < IP; ++i) { const float tmp = A[i]; A[i] = B[i]; B[i] = tmp; }
-        }
+        if (last - r == 1) row(PlainRow, xaddr(r), yaddr(r), xaddr(r + 1), s_c[r - base], true);
+        row(TileEnd, xaddr(last), yaddr(last), xnext, 1.0f, has_next);
         r = last + 1;
+        flush();                                     // before the next tile's refill recycles this tile's buffer
     }
-    flush(A);                                        // A = the last row processed
 
 #pragma unroll
     for (int k = 0; k < UPT; ++k) {
@@ -1386,8 +1390,8 @@ __device__ __forceinline__ bool peer_exchange_lhood(const ChainParams &p, int ro
 
 // SPEC_T: the instantiation with speculative windows (small ladders); the plain one carries none of their
 // state (at 72 registers per thread for 1024 co-resident temperatures every live value counts).
-template <int I, int H, int O, int TASK, int NT, int MINB, bool SPEC_T = false>
-__global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
+template <int I, int H, int O, int TASK, int NT, bool SPEC_T>
+__device__ __forceinline__ void chain_body(const ChainParams &p) {
     constexpr int P = NetSizes<I, H, O>::P;
     constexpr int IP = NetSizes<I, H, O>::IP;
     constexpr int NW = NT / 32;
@@ -1845,6 +1849,14 @@ __global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
     }
 chain_exit:
     if constexpr (TC) tc::teardown<I, H, O>(tcst);
+}
+
+// The kernel proper.  Registers are bounded through the number of co-resident CTAs per SM (MINB).  (The five-warp
+// tcgen05 geometry gets 168 registers at two CTAs per SM: the register file is carved up per PAIR of warps, so 160
+// threads cost what 192 do -- a build with 200 registers left one CTA per SM resident, as the probe launch reported.)
+template <int I, int H, int O, int TASK, int NT, int MINB, bool SPEC_T = false>
+__global__ void __launch_bounds__(NT, MINB) chain_kernel(const ChainParams p) {
+    chain_body<I, H, O, TASK, NT, SPEC_T>(p);
 }
 
 // ==========================================================================================

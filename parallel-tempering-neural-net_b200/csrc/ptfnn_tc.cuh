@@ -158,6 +158,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load without the wait: the registers may be read after tmem_wait_ld() only
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// (the registers are in/out operands of the wait so that no use of them can be scheduled above it)
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // shared-memory plan of the pass (bytes; all parts 128-byte aligned)
@@ -230,24 +250,30 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 // 32 registers per thread -> 32 lanes x 32 consecutive columns of TMEM (lane = TMEM lane)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
         "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
         ::"r"(taddr),
-          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+          "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+          "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+          "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+          "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+#ifdef PTFNN_TC_TRACE      // measurement builds only (tools/tc_trace.cu): clock stamps of the first tiles, per role
+__device__ long long g_tc_trace[2][8][64];
+#define TC_STAMP(role, k) do { if (lane == 0 && (role == 1 || warp == 0) && t < 8) g_tc_trace[role][t][k] = clock64(); } while (0)
+#else
+#define TC_STAMP(role, k) do { } while (0)
+#endif
 constexpr int kEpiThreads = 128;                 // warps 0-3: one per TMEM lane quadrant (thread = row of the tile)
 constexpr int kThreads = 160;                    // + warp 4: issues every MMA (a CTA issues one small MMA per ~56 cycles;
                                                  //   done by an epilogue warp, that time was added to the sigmoids' instead of hidden under them)
@@ -344,11 +370,14 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                              smem_desc(bh + BG::B_HALF_BYTES + ks * 2 * BG::B_CHUNK_BYTES, BG::B_CHUNK_BYTES, 128), IDESC1, true);
             };
             for (int t = 0; t < ntiles; ++t) {
+                TC_STAMP(1, 0);
                 mbar_wait(&bars[kBarA], st.ph_a);
                 st.ph_a ^= 1u;
                 tc_fence_after();
+                TC_STAMP(1, 1);
                 issue_layer1(0);
                 mma_commit(&bars[kBarZ]);
+                TC_STAMP(1, 2);
 #pragma unroll
                 for (int half = 0; half < NHALF; ++half) {
 #pragma unroll
@@ -357,6 +386,7 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                         if (b) { mbar_wait(&bars[kBarH1], st.ph_h1); st.ph_h1 ^= 1u; }
                         else { mbar_wait(&bars[kBarH0], st.ph_h0); st.ph_h0 ^= 1u; }
                         tc_fence_after();
+                        TC_STAMP(1, 3 + 2 * (half * NSUB + sb));
                         // layer 2, K = 32 hidden units of this sub-block: hid_hi . [W2_hi | W2_lo] (N = 32), hid_lo . W2_hi (N = 16)
 #pragma unroll
                         for (int ks = 0; ks < kSub / 8; ++ks) {
@@ -373,6 +403,7 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                         } else {
                             mma_commit(&bars[kBarD]);
                         }
+                        TC_STAMP(1, 4 + 2 * (half * NSUB + sb));
                     }
                 }
             }
@@ -390,60 +421,77 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
         tma_load_1d(smem + S::off_a, tiles, G::A_TILE_BYTES, &bars[kBarA]);
     }
     for (int t = 0; t < ntiles; ++t) {
+        // this row's label: requested now, used after the whole tile (a global load in the tile epilogue cost ~600 cycles)
+        const int row_in = warp * 32 + lane;
+        const int r = t * kRows + row_in;
+        const float yv = y[r < n ? r : n - 1];
 #pragma unroll
         for (int half = 0; half < NHALF; ++half) {
+            TC_STAMP(0, 40 + 2 * half);
             mbar_wait(&bars[kBarZ], st.ph_z);          // layer-1 pre-activations of this half are in Z (and every earlier MMA is done)
             st.ph_z ^= 1u;
             tc_fence_after();
+            TC_STAMP(0, 41 + 2 * half);
             if (half == NHALF - 1 && tid == 0 && t + 1 < ntiles) {     // layer 1 has consumed the A tile: fetch the next one under the epilogue
                 mbar_arrive_expect_tx(&bars[kBarA], G::A_TILE_BYTES);
                 tma_load_1d(smem + S::off_a, tiles + (size_t)(t + 1) * G::A_TILE_FLOATS, G::A_TILE_BYTES, &bars[kBarA]);
             }
-#pragma unroll 1
+            // the pre-activations of sub-block sb + 1 are fetched from tensor memory while sub-block sb is computed
+            // (two register buffers, the loop unrolled so that they alternate without copies)
+            uint32_t zr[2][32];
+            tmem_ld32_issue(tZ + lane_base, zr[0]);
+#pragma unroll
             for (int sb = 0; sb < NSUB; ++sb) {
                 const int b = sb & 1;
-                float z[32];
-                tmem_ld32(tZ + lane_base + (uint32_t)(sb * kSub), z);
-                float lo[32];
+                tmem_wait_ld(zr[b]);
+                if (sb + 1 < NSUB) tmem_ld32_issue(tZ + lane_base + (uint32_t)((sb + 1) * kSub), zr[b ^ 1]);
+                TC_STAMP(0, 4 * (half * NSUB + sb));
+                uint32_t lo[32];               // (the hi parts go back into zr[b]: the same registers they were loaded into)
 #pragma unroll
                 for (int g = 0; g < 32; g += 4) {
-                    f2_t zz[2] = {pack2(z[g], z[g + 1]), pack2(z[g + 2], z[g + 3])}, hh[2];
+                    f2_t zz[2] = {pack2(__uint_as_float(zr[b][g]), __uint_as_float(zr[b][g + 1])),
+                                  pack2(__uint_as_float(zr[b][g + 2]), __uint_as_float(zr[b][g + 3]))}, hh[2];
                     sigmoid_pairs<2>(zz, hh);
                     float h4[4];
                     unpack2(hh[0], h4[0], h4[1]);
                     unpack2(hh[1], h4[2], h4[3]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        z[g + q] = tf32_hi(h4[q]);             // hi part, in place of the pre-activation
-                        lo[g + q] = h4[q] - z[g + q];          // lo part (the tensor core reads its leading 11 bits: 2^-21 relative to hid)
+                        // hi = the leading 11 bits (truncated: one LOP3; cvt.rna.tf32 is a four-instruction sequence on sm_100),
+                        // lo = the exact rest, of which the tensor core reads the leading 11 bits: 2^-21 relative to hid in all
+                        const uint32_t hb = __float_as_uint(h4[q]) & 0xffffe000u;
+                        zr[b][g + q] = hb;
+                        lo[g + q] = __float_as_uint(h4[q] - __uint_as_float(hb));
                     }
                 }
+                TC_STAMP(0, 4 * (half * NSUB + sb) + 1);
                 if (b ? st.pend_l1 : st.pend_l0) {             // the layer-2 MMAs that read L[b] two sub-blocks ago
                     mbar_wait(&bars[b ? kBarL1 : kBarL0], b ? st.ph_l1 : st.ph_l0);
                     if (b) { st.ph_l1 ^= 1u; st.pend_l1 = false; } else { st.ph_l0 ^= 1u; st.pend_l0 = false; }
                     tc_fence_after();
                 }
-                tmem_st32(tZ + lane_base + (uint32_t)(sb * kSub), z);
+                TC_STAMP(0, 4 * (half * NSUB + sb) + 2);
+                tmem_st32(tZ + lane_base + (uint32_t)(sb * kSub), zr[b]);
                 tmem_st32(tL + lane_base + (uint32_t)(b * kSub), lo);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[b ? kBarH1 : kBarH0]);      // this warp's 32 rows of the sub-block are in tensor memory
+                TC_STAMP(0, 4 * (half * NSUB + sb) + 3);
                 if (sb < NSUB - 1) { if (b) st.pend_l1 = true; else st.pend_l0 = true; }
             }
         }
         // ---- output layer of the tile: D2 = hi.hi + lo.hi | hi.lo
+        TC_STAMP(0, 44);
         mbar_wait(&bars[kBarD], st.ph_d);
         st.ph_d ^= 1u;
         tc_fence_after();
+        TC_STAMP(0, 45);
         float d2[32];
         tmem_ld32(tD + lane_base, d2);
         tc_fence_before();                                     // (ordered before this warp's next arrival on H: D2 is rewritten after it)
-        const int row_in = warp * 32 + lane;
-        const int r = t * kRows + row_in;
         if (r < n) {
             float out[O];
-            const float yv = y[r];
 #pragma unroll
             for (int o = 0; o < O; ++o) out[o] = rcp_ftz(1.0f + ex2_ftz(d2[o] + d2[kN2 + o] + b2l[o]));     // R:54-55
             if constexpr (TASK == kTaskReg) {
@@ -454,14 +502,14 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                 int am = 0;
                 float se = 0.0f, om = out[0];
 #pragma unroll
-                for (int o = 0; o < O; ++o) se += expf(out[o]);                  // C:108-110
+                for (int o = 0; o < O; ++o) se += __expf(out[o]);                // C:108-110 (arguments in (0,1): ex2.approx is good to ~2 ulp)
 #pragma unroll
                 for (int o = 1; o < O; ++o) { const bool g = out[o] > om; am = g ? o : am; om = g ? out[o] : om; }   // np.argmax: first max
                 const int lab = (int)yv;
                 float ol = out[0];
 #pragma unroll
                 for (int o = 1; o < O; ++o) ol = (o == lab) ? out[o] : ol;
-                s0 += (double)(ol - logf(se));
+                s0 += (double)(ol - __logf(se));
                 const float e = (float)am - yv;
                 s1 += (double)(e * e);
                 correct += ((float)am == yv) ? 1 : 0;
@@ -469,7 +517,7 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
                     fx_out[r] = (float)am;
                     if (prob_out) {
 #pragma unroll
-                        for (int o = 0; o < O; ++o) prob_out[(size_t)r * O + o] = expf(out[o]) / se;
+                        for (int o = 0; o < O; ++o) prob_out[(size_t)r * O + o] = __expf(out[o]) / se;
                     }
                 }
             }

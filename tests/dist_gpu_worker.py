@@ -34,7 +34,9 @@ def main():
     draws.u_swap[:] = draws.u_swap * 0.3                  # frequent swaps: rows really cross rank boundaries
     lo, n = partition(Rg, world, rank)
     kw = dict(use_langevin_gradients=True, l_prob=0.5, learn_rate=0.1, seed=77, common_random_numbers=False)
-    ladder, smp = make_gpu_ladder(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, peer=peer, **kw)
+    spec = int(os.environ.get("PT_TEST_SPEC", "1"))           # speculative windows on every rank (the single-GPU comparison runs without)
+    ladder, smp = make_gpu_ladder(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, peer=peer,
+                                  speculation=spec, **kw)
     smp.set_data(tr, te)
 
     def one_pass(w0, tag):
@@ -57,7 +59,7 @@ def main():
         dist.all_reduce(moved)
         ok = True
         if rank == 0:
-            with Sampler(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, **kw) as one:
+            with Sampler(on.REGRESSION, (4, 5, 1), temps, S, si, device=local_rank, debug_traces=True, speculation=1, **kw) as one:
                 one.set_data(tr, te)
                 one.init_chains(w0)
                 if mode == "replay":

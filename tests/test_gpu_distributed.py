@@ -18,13 +18,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_worker(mode, exchange, reinit):
+def _run_worker(mode, exchange, reinit, spec=1):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     world = 2 if n < 4 else 4
-    env = dict(os.environ, PT_TEST_MODE=mode, PT_TEST_EXCHANGE=exchange, PT_TEST_REINIT="1" if reinit else "0")
+    env = dict(os.environ, PT_TEST_MODE=mode, PT_TEST_EXCHANGE=exchange, PT_TEST_REINIT="1" if reinit else "0", PT_TEST_SPEC=str(spec))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
@@ -46,3 +46,10 @@ def test_second_run_on_connected_handles(exchange):
     never reset) must not satisfy the waits of the second -- the flag domain moves on with every init."""
     out = _run_worker("free", exchange, reinit=True)
     assert "DIST_GPU_PASS second" in out and "DIST_GPU_PASS second mode=free exchange=%s ok=True" % exchange in out
+
+
+@pytest.mark.parametrize("mode", ["replay", "free"])
+def test_speculative_windows_on_a_partitioned_ladder(mode):
+    """Speculative windows (several CTAs per temperature) together with the peer-memory swap round: every rank runs
+    windows of depth 3, the single-GPU comparison runs sequentially -- bit-identical traces, swaps and final state."""
+    _run_worker(mode, "peer", reinit=False, spec=3)
