@@ -416,7 +416,10 @@ class Bench:
         # timed region (random-walk steps included) to the serial rows.
         chain_floor = {(4, 64, 1): 176, (4, 5, 1): 138, (4, 10, 1): 150, (16, 256, 10): 340}.get(tuple(w["topology"]))
         serial_rows = n_lg * 2 * w["train"].shape[0]
-        if chain_floor and serial_rows and clk and clk.get("sm_mhz"):
+        # (only where one CTA per temperature runs the steps one after the other: with speculative windows -- small
+        # ladders, or a ladder that leaves CTA slots free -- several steps of a chain are evaluated at once)
+        sequential = w["name"] == "pendigit" or w["R_per_gpu"] >= 1024
+        if sequential and chain_floor and serial_rows and clk and clk.get("sm_mhz"):
             cyc = sec / serial_rows * clk["sm_mhz"] * 1e6
             alt["serial_chain"] = {"bound": "dependent-issue latency of the SGD recurrence (one chain per temperature)",
                                    "serial_rows_per_temperature": serial_rows, "cycles_per_row_upper_bound": cyc,
@@ -571,6 +574,13 @@ def run_b200_arm(args, w, rank, world, local_rank):
             if rec is not None:
                 rec["scaling"] = "strong"
                 sub["strong_1024"] = rec
+            st = b.burn_in(ws)                       # ... and in the reference's steady state (speculative windows follow the acceptance rate)
+            rec = b.measure(ws, K, W, with_cpu=False, burn=st)
+            if rec is not None:
+                rec["scaling"] = "strong"
+                rec["burn_in"] = {"steps": BURN_IN_STEPS, "seconds": st["burn_seconds"], "acceptance_rate_last_200_steps": st["acceptance_last_200"],
+                                  "swap_rate": st["swap_rate"]}
+                sub["strong_1024_burned_in"] = rec
             parity = b.multi_gpu_parity(w)
         elif world == 1:
             sub["strong_1024"] = {"same_as": "the headline line: at one GPU the 1024-temperature ladder of configs[3] is the weak-scaling workload"}
