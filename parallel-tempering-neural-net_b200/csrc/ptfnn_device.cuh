@@ -238,6 +238,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// The same wait for a warp that may wait long next to warps that are busy (the MMA warp of the tcgen05 pass): the
+// thread is SUSPENDED by the hardware until the phase completes or the hint (ns) runs out, instead of re-issuing
+// try_wait every few cycles from the issue slots of the warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_suspended(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!ok);
+}
 // 1-D TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

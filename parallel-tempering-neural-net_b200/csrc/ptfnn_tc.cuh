@@ -371,7 +371,7 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
             };
             for (int t = 0; t < ntiles; ++t) {
                 TC_STAMP(1, 0);
-                mbar_wait(&bars[kBarA], st.ph_a);
+                mbar_wait_suspended(&bars[kBarA], st.ph_a);
                 st.ph_a ^= 1u;
                 tc_fence_after();
                 TC_STAMP(1, 1);
@@ -383,8 +383,8 @@ __device__ __forceinline__ void lik_pass(unsigned char *smem, State &st, const f
 #pragma unroll
                     for (int sb = 0; sb < NSUB; ++sb) {
                         const int b = sb & 1;
-                        if (b) { mbar_wait(&bars[kBarH1], st.ph_h1); st.ph_h1 ^= 1u; }
-                        else { mbar_wait(&bars[kBarH0], st.ph_h0); st.ph_h0 ^= 1u; }
+                        if (b) { mbar_wait_suspended(&bars[kBarH1], st.ph_h1); st.ph_h1 ^= 1u; }
+                        else { mbar_wait_suspended(&bars[kBarH0], st.ph_h0); st.ph_h0 ^= 1u; }
                         tc_fence_after();
                         TC_STAMP(1, 3 + 2 * (half * NSUB + sb));
                         // layer 2, K = 32 hidden units of this sub-block: hid_hi . [W2_hi | W2_lo] (N = 32), hid_lo . W2_hi (N = 16)
