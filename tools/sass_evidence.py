@@ -32,12 +32,12 @@ def main():
     print("|---|---|" + "---|" * len(MNEMONICS))
     excerpts = {}
     for k, lines in kernels.items():
-        short = re.sub(r"\(.*", "", names[k]).replace("ptfnn::", "")
+        short = names[k].rsplit("(", 1)[0].replace("ptfnn::", "").replace("(int)", "").replace("(bool)", "")
         counts = [sum(1 for l in lines if re.search(r"\b" + re.escape(m), l)) for m in MNEMONICS]
         if sum(counts[:6]) == 0 and "chain_kernel" not in short:
             continue
         print("| `%s` | %d | %s |" % (short[:110], len(lines), " | ".join(str(c) for c in counts)))
-        if "op_forward_tc_kernel" in short or ("chain_kernel<16, 256, 10" in short):
+        if "op_forward_tc_kernel" in short or ("chain_kernel<16, 256, 10" in short and short not in excerpts):
             excerpts[short] = lines
     for short, lines in excerpts.items():
         print("\n## `%s`: first occurrences\n\n```" % short[:120])
