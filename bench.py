@@ -283,6 +283,8 @@ class Bench:
         from ptnn_b200.sampler import Sampler
         kw = dict(use_langevin_gradients=True, l_prob=w["l_prob"], learn_rate=w["learn_rate"], seed=self.args.seed,
                   common_random_numbers=True)
+        if self.args.speculation:
+            kw["speculation"] = self.args.speculation
         kw.update(extra)
         si = w["swap_interval"]
         if self.world > 1 and distributed:
@@ -307,9 +309,11 @@ class Bench:
         """-> (sum of the timed steps' device time in ms, max over ranks; per-step ms of this rank)."""
         torch = self.torch
         adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
+        self.align(smp, ladder, si)
         for _ in range(n_warm):
             adv()
         self.barrier()
+        self.first_timed = smp.step
         ev = []
         for _ in range(n_timed):
             self.flush.fill_(1)                                   # evict L2 between timed steps (untimed)
@@ -321,6 +325,16 @@ class Bench:
         self.barrier()
         ms = [a.elapsed_time(b) for a, b in ev]
         return self.max_over_ranks(sum(ms)), ms
+
+    @staticmethod
+    def align(smp, ladder, si):
+        """Advance (untimed) so that every bench step ends ON a swap round: the regression chain swaps after steps
+        i % si == 0 (R:427), so its bench steps are [k si + 1, (k+1) si]; the classification chain swaps after
+        (i + 1) % si == 0 (C:438) and needs nothing.  A bench step that straddles a round would be two segments."""
+        want = 1 if smp.cfg.task == 0 else 0
+        off = (want - smp.step) % si
+        if off:
+            (ladder.run(off) if ladder is not None else smp.run(off))
 
     def acceptance(self, smp, first_step, n_steps):
         """Acceptance rate of steps [first_step, first_step + n_steps) of this rank's replicas: accept_list row i+1 is
@@ -340,6 +354,7 @@ class Bench:
         stream while step k+1 runs, and arrive as views (float32 weights, nothing widened)."""
         si = w["swap_interval"]
         adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
+        self.align(smp, ladder, si)
         for _ in range(n_warm):
             adv()
         self.barrier()
@@ -436,7 +451,7 @@ class Bench:
     def measure(self, w, K, W, with_cpu, with_pipeline=False, distributed=True, burn=None):
         """``burn``: dict(w=..., eta=..., lik=..., prior=..., tau=...) of a burned-in ladder (this rank's block) to continue."""
         si = w["swap_interval"]
-        S = si * (K + W) + 2
+        S = si * (K + W + 1) + 2
         w0 = None if burn is None else burn["w"]
         clocks = ClockSampler(self.local_rank) if self.rank == 0 else None
         smp, ladder = self.make(w, 0, S, w0=w0, state=burn, distributed=distributed)
@@ -445,8 +460,8 @@ class Bench:
         world = self.world if distributed else 1
         units = w["R_global"] * si
         value = units * K / (total_ms * 1e-3)
-        n_lg, n_rw = self.lx_mix(smp, w, W * si, K * si)
-        acc = self.acceptance(smp, W * si, K * si) if distributed or self.rank == 0 else None
+        n_lg, n_rw = self.lx_mix(smp, w, self.first_timed, K * si)
+        acc = self.acceptance(smp, self.first_timed, K * si) if distributed or self.rank == 0 else None
         smp.close()
         smp, ladder = self.make(w, 1, S, w0=w0, state=burn, distributed=distributed)
         total_ms_memo, _ = self.timed_steps(smp, ladder, si, W, K)
@@ -477,6 +492,7 @@ class Bench:
                "timed_region": {"replicas_total": w["R_global"], "replica_steps_per_bench_step": units,
                                 "langevin_steps": n_lg, "random_walk_steps": n_rw, "acceptance_rate": acc,
                                 "memoize_gradient": 0, "l2": "flushed between timed steps (256 MiB write)",
+                                "first_timed_chain_step": self.first_timed, "bench_step": "swap_interval chain steps ending on a swap round",
                                 "start": "random initial weights" if burn is None else "continued after %d burn-in steps" % BURN_IN_STEPS},
                "value_memoized": units * K / (total_ms_memo * 1e-3), "ms_per_step_memoized": total_ms_memo / K,
                "e2e": e2e, "gpu_launches": K, "clocks": clk, "roofline": roofline, "roofline_alt": alt, "step_ms": ms_list}
@@ -624,6 +640,7 @@ def main():
                     help="strong scaling: a fixed ladder of this many temperatures split over the GPUs "
                          "(BASELINE configs[3] as worded: 1024 over 1/2/4/8); default is weak scaling, 1024 per GPU")
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--speculation", type=int, default=0, help="CTAs per temperature: 0 = the library's automatic choice (default), 1 = none, K = fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", dest="sub", action="store_false", help="only the headline measurement (no sub-records, no parity replay)")
     args = ap.parse_args()

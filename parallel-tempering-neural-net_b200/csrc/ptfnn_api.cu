@@ -42,7 +42,7 @@ static int fail(ptfnn_sampler *s, int code, const char *fmt, ...);
 #include "ptfnn_registry.h"
 #include "ptfnn_topologies.h"
 typedef PtfnnKernelSet KernelSet;
-static const int kMaxSpec = 16;                 // deepest speculative window (CTAs per temperature)
+static const int kMaxSpec = kMaxSpecK;          // most CTAs per temperature (speculative windows)
 
 #define X(NAME, TASK, I, H, O, NT, MINB) const PtfnnKernelSet *ptfnn_kernelset_##NAME();
 PTFNN_TOPOLOGIES(X)
@@ -119,7 +119,9 @@ struct ptfnn_sampler {
     unsigned int fetch_seq = 0;
     // acceptance feedback for the automatic depth of the speculative windows: after every launch the sum of the
     // replicas' acceptance counters is copied (asynchronously) into a small page-locked ring; the next launch looks at
-    // the newest copy that has ARRIVED -- no synchronisation, the estimate is one or two launches old
+    // the newest copy that has arrived, and waits for the copy of the launch before the previous one if it has not:
+    // the host never runs more than two launches ahead of the estimate it steers by (a caller that queues a whole
+    // run of launches at once would otherwise decide all of them blind)
     struct AccSample { long long *host = nullptr; cudaEvent_t ev = nullptr; int step = 0; bool used = false; };
     AccSample acc_ring[4];
     DevBuf<long long> acc_sum;
@@ -353,7 +355,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     ALLOC(lik_prop, R * S); ALLOC(rmse_tr, R * S); ALLOC(rmse_te, R * S); ALLOC(acc_tr, R * S); ALLOC(acc_te, R * S);
     ALLOC(n_acc, R); ALLOC(init_count, R); ALLOC(gd_valid, R); ALLOC(accept_list, R * S);
     if (cfg->debug_traces) { ALLOC(dbg_prior, R * S); ALLOC(dbg_diff, R * S); ALLOC(dbg_mh, R * S); ALLOC(dbg_acc, R * S); }
-    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, 2 * kMaxPeers); ALLOC(probe_count, 2); ALLOC(spec_bar, R); ALLOC(spec_flag, R * kMaxSpec);
+    ALLOC(swap_log, (size_t)rounds * std::max(Rg - 1, 1)); ALLOC(barrier, 1); ALLOC(swap_counters, 2); ALLOC(peer_flags, 2 * kMaxPeers); ALLOC(probe_count, 2); ALLOC(spec_bar, R); ALLOC(spec_flag, R * kSpecWords);
     ALLOC(d_src, (size_t)Rg); ALLOC(smsp_load, (size_t)s->num_sms * 4 + 64); ALLOC(swap_src, R); ALLOC(d_swapped, (size_t)std::max(Rg - 1, 1)); ALLOC(d_scratch, 16);
 #undef ALLOC
     cudaMemcpy(s->temperature.p, temperatures, R * sizeof(double), cudaMemcpyHostToDevice);
@@ -361,7 +363,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
     cudaMemset(s->peer_flags.p, 0, 2 * kMaxPeers * sizeof(unsigned int));
     cudaMemset(s->probe_count.p, 0, 2 * sizeof(unsigned int));
     cudaMemset(s->spec_bar.p, 0, R * sizeof(GridBarrier));
-    cudaMemset(s->spec_flag.p, 0, R * kMaxSpec * sizeof(unsigned int));
+    cudaMemset(s->spec_flag.p, 0, R * kSpecWords * sizeof(unsigned int));
     cudaMemset(s->smsp_load.p, 0, s->smsp_load.n * sizeof(int));
     cudaMemset(s->swap_counters.p, 0, 2 * sizeof(long long));
     cudaMemset(s->swap_log.p, 0, s->swap_log.n);
@@ -485,7 +487,7 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     CU_TRY(s, cudaMemsetAsync(s->swap_log.p, 0, s->swap_log.n, s->stream));
     CU_TRY(s, cudaMemsetAsync(s->barrier.p, 0, sizeof(GridBarrier), s->stream));
     CU_TRY(s, cudaMemsetAsync(s->spec_bar.p, 0, R * sizeof(GridBarrier), s->stream));
-    CU_TRY(s, cudaMemsetAsync(s->spec_flag.p, 0, R * kMaxSpec * sizeof(unsigned int), s->stream));
+    CU_TRY(s, cudaMemsetAsync(s->spec_flag.p, 0, R * kSpecWords * sizeof(unsigned int), s->stream));
     if (s->cfg.debug_traces) {
         CU_TRY(s, cudaMemsetAsync(s->dbg_prior.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_diff.p, 0, R * S * 8, s->stream));
         CU_TRY(s, cudaMemsetAsync(s->dbg_mh.p, 0, R * S * 8, s->stream)); CU_TRY(s, cudaMemsetAsync(s->dbg_acc.p, 0, R * S, s->stream));
@@ -708,7 +710,12 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     int spec = 1;
     const bool spec_possible = s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms;
     const bool spec_auto = spec_possible && c.speculation == 0;
-    if (spec_auto) {                                     // newest acceptance sample that has arrived (never waits)
+    const bool spec_feedback = spec_auto && R * 2 > s->num_sms;    // (tiny ladders do not steer by the acceptance rate)
+    if (spec_feedback) {
+        if (s->acc_seq >= 2) {                           // bound the lag: the sample of the launch before the previous one
+            ptfnn_sampler::AccSample &old = s->acc_ring[(s->acc_seq - 2) & 3];
+            if (old.used) CU_TRY(s, cudaEventSynchronize(old.ev));
+        }
         for (int k = 0; k < 4; ++k) {
             ptfnn_sampler::AccSample &a = s->acc_ring[(s->acc_seq + 3 - k) & 3];
             if (!a.used || cudaEventQuery(a.ev) != cudaSuccess) continue;
@@ -756,13 +763,13 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     else CU_TRY(s, cudaLaunchCooperativeKernel(chain_fn, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());
     s->step = end;
-    if (spec_auto) {
+    if (spec_feedback) {
         ptfnn_sampler::AccSample &a = s->acc_ring[s->acc_seq & 3];
         if (!a.host) {
             CU_TRY(s, cudaHostAlloc((void **)&a.host, sizeof(long long), cudaHostAllocDefault));
             CU_TRY(s, cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
         }
-        if (!a.used || cudaEventQuery(a.ev) == cudaSuccess) {         // (a slot whose copy is still in flight is left alone)
+        if (!a.used || cudaEventSynchronize(a.ev) == cudaSuccess) {   // (the slot of four launches ago: long finished)
             CU_TRY(s, s->acc_sum.ensure(1));
             sum_int_kernel<<<1, 256, 0, s->stream>>>(s->n_acc.p, R, s->acc_sum.p);
             CU_TRY(s, cudaMemcpyAsync(a.host, s->acc_sum.p, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));

@@ -1180,7 +1180,7 @@ struct ChainParams {
     //      consecutive steps at once, each assuming that the earlier ones are rejected
     int spec_k;
     GridBarrier *spec_bar;         // [R]         barrier of the CTAs of one temperature
-    unsigned int *spec_flag;       // [R][spec_k] (window base + 1) << 1 | accepted
+    unsigned int *spec_flag;       // [R][kSpecWords]: per step of the window, then per CTA of the group (chain_body)
     // ---- multi-GPU ladder through peer memory (n_ranks > 1): every rank's pub_lhood / pub_rows / peer_flags
     //      are mapped into this process (CUDA IPC); entry q of the tables points at rank q's buffer
     int n_ranks, rank;
@@ -1202,6 +1202,10 @@ struct ChainParams {
     int swap_kind;
     const double *temperature_global;   // [Rg] (swap_kind != 0 only)
 };
+constexpr int kSpecWin = 32;       // most steps one speculative window covers
+constexpr int kMaxSpecK = 16;      // most CTAs per temperature
+constexpr int kSpecWords = 64;     // control words per temperature: kSpecWin step flags, then kMaxSpecK CTA flags
+constexpr int kSpecLgCost = 8;     // planning weight of a Langevin step in random-walk steps (measured 7-13)
 constexpr int kRowTail = 2;        // words behind the P weights of a published row: eta as raw fp64 bits (R:430 moves the float64)
 
 __device__ __forceinline__ bool swap_due(int rule, int s, int i) {
@@ -1506,6 +1510,8 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
     const bool is_sgd_warp = warp == sgd_warp;
     const int lik_tid = (warp < sgd_warp ? tid : tid - 32);     // index inside the team of the other warps
 
+    __shared__ int s_plan[SPEC_T ? kSpecWin + 1 : 1];      // owner CTA of each step of the window; [kSpecWin] = its length
+    __shared__ int s_res[2];                                // the window's first accepted step; first CTA holding the base gradient
     const int nblocks = gridDim.x;
     // speculative windows: K CTAs per temperature (host guarantees gridDim.x == R * K and co-residency)
     const int K = (SPEC_T && !TEAM && p.spec_k > 1) ? p.spec_k : 1;
@@ -1558,30 +1564,59 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
             const uint32_t gr = (uint32_t)(p.replica_offset + r);
             const uint32_t rng_stream = p.crn ? kStreamCommon : gr;
 
-            // One iteration = one step, or (speculative windows) W consecutive steps evaluated by the W
-            // first CTAs of the group, each from the state at the window base, i.e. as if the earlier steps
-            // of the window were rejected.  The first accepted step k* makes steps 0..k* stand; its CTA
+            // One iteration = one step, or (speculative windows) W consecutive steps shared out among the K
+            // CTAs of the group, each step evaluated from the state at the window base, i.e. as if the earlier
+            // steps of the window were rejected.  The first accepted step k* makes steps 0..k* stand; its CTA
             // installs the new state and the window after it starts at base + k* + 1.  Results are those of
             // the sequential chain bit for bit: the draws are indexed by the step, a rejected step leaves
             // nothing behind but its trace row and tau, and trace rows past k* are rewritten later.
+            // The window is PACKED by cost: a Langevin step (two SGD epochs) takes a CTA of its own, the
+            // random-walk steps between them -- several times cheaper -- ride together on the remaining CTAs,
+            // so one window of about one Langevin step's duration covers ~2K steps instead of K.  Every CTA
+            // of the group derives the same plan from the lx draws of the steps ahead.
             int ibase = step;
             while (ibase <= seg_last) {
                 int W = 1;
                 if (SPEC) {
                     if (ibase != step) load_state();
-                    W = min(K, seg_last - ibase + 1);
+                    int wcap = min(kSpecWin, seg_last - ibase + 1);
                     // the temperature switch (a11) changes the state whatever the MH outcome: the step that
                     // performs it opens a window of its own and no window runs across it
                     const int sw = (int)p.pt_samples;
                     if (init_count == 0 && (double)sw == p.pt_samples) {
-                        if (ibase == sw) W = 1;
-                        else if (ibase < sw && ibase + W > sw) W = sw - ibase;
+                        if (ibase == sw) wcap = 1;
+                        else if (ibase < sw && ibase + wcap > sw) wcap = sw - ibase;
                     }
+                    // warp 0 plans: the j-th Langevin step of the window goes to CTA j, the m-th random-walk step to CTA
+                    // K-1 - m/pack (from the top, `pack` to a CTA); the window ends before the step that would make the
+                    // two ranges meet
+                    if (tid < 32) {
+                        bool lgt = false;
+                        if (tid < wcap) {
+                            const int it = ibase + tid;
+                            float lxt;
+                            if (p.replay) lxt = p.lx[(size_t)r * p.replay_n + (it - p.step_begin)];
+                            else lxt = philox_step_scalars(p.seed, (uint32_t)it, p.crn ? kStreamCommon : (uint32_t)(p.replica_offset + r), (uint32_t)(p.replica_offset + r)).lx;
+                            lgt = p.use_lg && ((double)lxt < p.l_prob);
+                        }
+                        const unsigned int in_cap = wcap >= 32 ? 0xffffffffu : ((1u << wcap) - 1u);
+                        const unsigned int lgm = __ballot_sync(0xffffffffu, lgt) & in_cap;
+                        const unsigned int upto = tid == 31 ? 0xffffffffu : ((2u << tid) - 1u);
+                        const int n_lg = __popc(lgm & upto), n_rw = __popc(~lgm & in_cap & upto);
+                        const int pack = p.use_lg ? kSpecLgCost : 1;
+                        const bool fits = tid < wcap && n_lg + (n_rw + pack - 1) / pack <= K;      // (monotone in the step)
+                        const unsigned int fm = __ballot_sync(0xffffffffu, fits);
+                        s_plan[tid] = lgt ? n_lg - 1 : K - 1 - (n_rw - 1) / pack;
+                        if (tid == 0) s_plan[kSpecWin] = __popc(fm);
+                    }
+                    __syncthreads();
+                    W = s_plan[kSpecWin];
                 }
-                const int i = ibase + kq;
                 const int gd_valid0 = gd_valid;      // langevin_gradient(w) known at the window base?
                 bool accept = false;
-                if (kq < W) {
+                for (int t = 0; t < W && !accept; ++t) {
+                if (SPEC && s_plan[t] != kq) continue;
+                const int i = ibase + t;
                 // ---- a11: temperature schedule inside the chain (R:317-324)
                 double adapt = init_count ? 1.0 : temperature;
                 if ((double)i == p.pt_samples && init_count == 0) {
@@ -1774,36 +1809,42 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
                     const float *prev = p.pos_w + ((size_t)r * p.S + ibase) * P;      // the row before the window
                     for (int j = tid; j < P; j += NT) pw[j] = __ldcg(&prev[j]);         // (maybe written by another CTA)
                 }
-                }   // kq < W
+                if (SPEC && tid == 0) p.spec_flag[r * kSpecWords + t] = ((unsigned int)(ibase + 1) << 1) | (accept ? 1u : 0u);
+                }   // the steps of this CTA
                 if (!SPEC) {
                     if (tid == 0) atomicAdd(p.heartbeat, 1u);     // progress, as seen by the waits of other CTAs / ranks
                     ++ibase; continue;
                 }
                 // ---- resolve the window
-                // flag = (window base + 1) << 2 | computed langevin_gradient(w) of the base state << 1 | accepted
-                const bool made_gd = kq < W && !accept && p.memo && gd_valid && !gd_valid0;
+                // step flag = (window base + 1) << 1 | accepted;  CTA flag = (window base + 1) << 1 | this CTA
+                // computed langevin_gradient(w) of the base state
+                const bool made_gd = !accept && p.memo && gd_valid && !gd_valid0;
                 if (tid == 0) {
-                    p.spec_flag[r * K + kq] = ((unsigned int)(ibase + 1) << 2) | (made_gd ? 2u : 0u) | ((kq < W && accept) ? 1u : 0u);
+                    p.spec_flag[r * kSpecWords + kSpecWin + kq] = ((unsigned int)(ibase + 1) << 1) | (made_gd ? 1u : 0u);
                     atomicAdd(p.heartbeat, 1u);
                 }
                 if (!grid_barrier(&p.spec_bar[r], (unsigned int)K, p.wait_limit, p.heartbeat, /*spin=*/true)) goto chain_exit;
-                int kstar = W, kgd = W;
-                for (int q = 0; q < W; ++q) {
-                    const unsigned int f = __ldcg(&p.spec_flag[r * K + q]);
-                    if ((f >> 2) != (unsigned int)(ibase + 1)) continue;
-                    if ((f & 2u) && kgd == W) kgd = q;
-                    if (f & 1u) { kstar = q; break; }
+                int kstar = W, kgd = K;
+                if (tid < 32) {                              // one load per step of the window, first acceptance by ballot
+                    const unsigned int want = ((unsigned int)(ibase + 1) << 1) | 1u;
+                    const bool hit = tid < W && __ldcg(&p.spec_flag[r * kSpecWords + tid]) == want;
+                    const bool hgd = tid < K && __ldcg(&p.spec_flag[r * kSpecWords + kSpecWin + tid]) == want;
+                    const unsigned int hm = __ballot_sync(0xffffffffu, hit), gm = __ballot_sync(0xffffffffu, hgd);
+                    if (tid == 0) { s_res[0] = hm ? __ffs(hm) - 1 : W; s_res[1] = gm ? __ffs(gm) - 1 : K; }
                 }
+                __syncthreads();
+                kstar = s_res[0]; kgd = s_res[1];
                 const int committed = min(kstar, W - 1);     // the last step of the window that stands
-                // its CTA holds exactly the chain's state after that step: the accepted vector, or (no
+                const int owner = s_plan[committed];         // its CTA
+                // that CTA holds exactly the chain's state after that step: the accepted vector, or (no
                 // acceptance) the unchanged state with the last proposed tau.  Without an acceptance the memo
                 // langevin_gradient(w) stays valid for the next window: the first CTA that computed it stores it.
-                if (kstar == W && kgd < W) {
-                    if (kq == kgd && kq != committed)
+                if (kstar == W && kgd < K) {
+                    if (kq == kgd && kq != owner)
                         for (int j = tid; j < P; j += NT) p.gd_cache[(size_t)r * P + j] = s_gd[j];
-                    if (kq == committed && !gd_valid) gd_valid = -1;        // valid, but this CTA does not hold the vector
+                    if (kq == owner && !gd_valid) gd_valid = -1;        // valid, but this CTA does not hold the vector
                 }
-                if (kq == committed) store_state();
+                if (kq == owner) store_state();
                 if (!grid_barrier(&p.spec_bar[r], (unsigned int)K, p.wait_limit, p.heartbeat, /*spin=*/true)) goto chain_exit;
                 ibase += committed + 1;
             }

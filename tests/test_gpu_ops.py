@@ -141,10 +141,11 @@ def test_swap_sweep_matches_reference_rule():
 
 def test_on_demand_topologies_match_oracle():
     """Topologies outside csrc/ptfnn_topologies.h are compiled on first use (capi.ensure_topology): narrow,
-    two-units-per-lane and wide (team kernel, H = 100) hidden layers, regression and classification."""
+    two-units-per-lane and wide (team kernel, H = 90, 100 and 300) hidden layers, regression and classification."""
     rs = np.random.RandomState(17)
     for task, topo in ((on.REGRESSION, (3, 7, 1)), (on.CLASSIFICATION, (6, 40, 4)), (on.CLASSIFICATION, (5, 100, 3)),
-                       (on.CLASSIFICATION, (51, 90, 2))):      # the last one: the shape of the reference's Bank set (C:958-971)
+                       (on.CLASSIFICATION, (51, 90, 2)),       # the shape of the reference's Bank set (C:958-971)
+                       (on.CLASSIFICATION, (6, 300, 3))):      # wider than 256: three hidden units per team thread
         I, H, O = topo
         n = 300
         y = rs.rand(n, 1) if task == on.REGRESSION else rs.randint(0, O, size=(n, 1)).astype(float)
