@@ -355,8 +355,10 @@ class Bench:
         si = w["swap_interval"]
         adv = (lambda: ladder.run(si)) if ladder is not None else (lambda: smp.run(si))
         self.align(smp, ladder, si)
-        for _ in range(n_warm):
+        for _ in range(n_warm):                                  # warm-up = the same calls (the first read-back page-locks its slots)
+            smp.set_data(w["train"], w["test"])
             adv()
+            smp.traces_end(smp.traces_begin(smp.step - si + 1, si, pos_w=True))
         self.barrier()
         t0 = time.perf_counter()
         d2h, pending, checksum = 0, None, 0.0

@@ -742,7 +742,9 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
             if (R * 2 <= s->num_sms)      // tiny ladders: one CTA per SM for Langevin runs; none for random-walk runs (a step is shorter than a window's two group barriers)
                 want = c.use_langevin_gradients ? std::max(1, s->num_sms / R) : 1;
             else
-                want = a < 0.0 ? 1 : a <= 0.30 ? cap : a <= 0.60 ? std::min(cap, 4) : 1;
+                // (measured, 4-64-1: two CTAs per temperature pay below ~4 % acceptance -- the doubled residency slows every
+                //  step by a quarter -- four or more already at 8 %: 31.5 against 38.8 ms per 10 steps of 128 temperatures)
+                want = a < 0.0 ? 1 : cap <= 2 ? (a <= 0.04 ? cap : 1) : cap == 3 ? (a <= 0.08 ? cap : 1) : a <= 0.30 ? cap : a <= 0.60 ? std::min(cap, 4) : 1;
         }
         spec = std::max(1, std::min(want, cap));
     }

@@ -1205,7 +1205,7 @@ struct ChainParams {
 constexpr int kSpecWin = 32;       // most steps one speculative window covers
 constexpr int kMaxSpecK = 16;      // most CTAs per temperature
 constexpr int kSpecWords = 64;     // control words per temperature: kSpecWin step flags, then kMaxSpecK CTA flags
-constexpr int kSpecLgCost = 8;     // planning weight of a Langevin step in random-walk steps (measured 7-13)
+constexpr int kSpecRwRun = 8;      // random-walk steps one CTA takes in a row (a Langevin step costs 7-13 of them)
 constexpr int kRowTail = 2;        // words behind the P weights of a published row: eta as raw fp64 bits (R:430 moves the float64)
 
 __device__ __forceinline__ bool swap_due(int rule, int s, int i) {
@@ -1570,10 +1570,10 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
             // installs the new state and the window after it starts at base + k* + 1.  Results are those of
             // the sequential chain bit for bit: the draws are indexed by the step, a rejected step leaves
             // nothing behind but its trace row and tau, and trace rows past k* are rewritten later.
-            // The window is PACKED by cost: a Langevin step (two SGD epochs) takes a CTA of its own, the
-            // random-walk steps between them -- several times cheaper -- ride together on the remaining CTAs,
-            // so one window of about one Langevin step's duration covers ~2K steps instead of K.  Every CTA
-            // of the group derives the same plan from the lx draws of the steps ahead.
+            // The window is PACKED by cost: every CTA takes one Langevin step (two SGD epochs) and the
+            // random-walk steps right before it -- several times cheaper -- so one window of little more than
+            // one Langevin step's duration covers ~K / l_prob steps instead of K.  Every CTA of the group
+            // derives the same plan from the lx draws of the steps ahead.
             int ibase = step;
             while (ibase <= seg_last) {
                 int W = 1;
@@ -1587,9 +1587,10 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
                         if (ibase == sw) wcap = 1;
                         else if (ibase < sw && ibase + wcap > sw) wcap = sw - ibase;
                     }
-                    // warp 0 plans: the j-th Langevin step of the window goes to CTA j, the m-th random-walk step to CTA
-                    // K-1 - m/pack (from the top, `pack` to a CTA); the window ends before the step that would make the
-                    // two ranges meet
+                    // warp 0 plans: a step goes to the CTA whose index is the number of Langevin steps before it in the
+                    // window, i.e. every CTA evaluates the random-walk steps that precede "its" Langevin step and
+                    // then that step (in step order); a run of random-walk steps longer than kSpecRwRun moves on to
+                    // the next CTA.  The window ends before the first step that would need CTA K.
                     if (tid < 32) {
                         bool lgt = false;
                         if (tid < wcap) {
@@ -1601,12 +1602,10 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
                         }
                         const unsigned int in_cap = wcap >= 32 ? 0xffffffffu : ((1u << wcap) - 1u);
                         const unsigned int lgm = __ballot_sync(0xffffffffu, lgt) & in_cap;
-                        const unsigned int upto = tid == 31 ? 0xffffffffu : ((2u << tid) - 1u);
-                        const int n_lg = __popc(lgm & upto), n_rw = __popc(~lgm & in_cap & upto);
-                        const int pack = p.use_lg ? kSpecLgCost : 1;
-                        const bool fits = tid < wcap && n_lg + (n_rw + pack - 1) / pack <= K;      // (monotone in the step)
-                        const unsigned int fm = __ballot_sync(0xffffffffu, fits);
-                        s_plan[tid] = lgt ? n_lg - 1 : K - 1 - (n_rw - 1) / pack;
+                        const int n_before = __popc(lgm & ((1u << tid) - 1u));
+                        const int owner = p.use_lg ? max(n_before, tid / (kSpecRwRun + 1)) : tid;      // (non-decreasing in the step)
+                        const unsigned int fm = __ballot_sync(0xffffffffu, tid < wcap && owner < K);
+                        s_plan[tid] = owner;
                         if (tid == 0) s_plan[kSpecWin] = __popc(fm);
                     }
                     __syncthreads();

@@ -10,11 +10,11 @@ BURN = int(os.environ.get("PROBE_BURN", "0"))          # steps run (untimed) bef
 for R in [int(a) for a in sys.argv[1:]] or [128]:
     for spec in (1, 0, 4, 8):
         n = 30
-        s = Sampler(0, (4, 64, 1), geometric_ladder(R, 2), 10 * n + 2 + BURN, 10, learn_rate=0.01, l_prob=0.5, seed=2026, memoize_gradient=0,
+        s = Sampler(0, (4, 64, 1), geometric_ladder(R, 2), 10 * n + 3 + BURN, 10, learn_rate=0.01, l_prob=0.5, seed=2026, memoize_gradient=0,
                     stream=torch.cuda.current_stream(), speculation=spec)
         s.set_data(tr, te)
         s.init_chains(np.random.RandomState(1000).randn(R, s.P))
-        if BURN: s.run(BURN)
+        s.run(BURN + 1)            # + 1: launches of 10 steps end on the swap rounds (R:427)
         acc0 = s.get_state()["num_accepted"].sum()
         ev = []
         for k in range(n):
