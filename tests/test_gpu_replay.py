@@ -222,6 +222,42 @@ def test_speculative_windows_are_bit_identical(memo):
             assert np.array_equal(st[k], st1[k]), (depth, k)
 
 
+@pytest.mark.parametrize("task,l_prob,use_lg", [(0, 0.08, True), (0, 1.0, True), (0, 0.5, False), (1, 0.3, True)])
+def test_packed_window_plans_are_bit_identical(task, l_prob, use_lg):
+    """The window plan (DESIGN section 5: a step belongs to the CTA indexed by the number of Langevin steps before it;
+    runs of more than eight random-walk steps move on; at most 32 steps per window) at its corners: long random-walk
+    runs (l_prob 0.08), Langevin steps only, random-walk chains (one step per CTA) and a classification chain whose
+    swap segments (40 steps) are longer than a window.  Depths 2, 5 and 16 against the sequential chain, bit for bit."""
+    if task == 0:
+        tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+        topo, kind, lr = (4, 5, 1), on.REGRESSION, 0.1
+    else:
+        tr, te = cm.dataset(on.CLASSIFICATION, "Iris")
+        topo, kind, lr = (4, 12, 3), on.CLASSIFICATION, 0.01
+    P = topo[0] * topo[1] + topo[1] * topo[2] + topo[1] + topo[2]
+    R, S, si = 6, 161, 40
+    from ptnn_b200.sampler import geometric_ladder
+    temps = geometric_ladder(R, 2)
+    w0 = np.random.RandomState(11).randn(R, P) * 0.5
+    out = {}
+    for depth in (1, 2, 5, 16):
+        with Sampler(kind, topo, temps, S, si, use_langevin_gradients=use_lg, l_prob=l_prob, learn_rate=lr, seed=77,
+                     common_random_numbers=False, memoize_gradient=depth % 2, debug_traces=True, speculation=depth) as s:
+            s.set_data(tr, te)
+            s.init_chains(w0)
+            assert s.run() == S - 1
+            out[depth] = (s.traces(), s.swap_stats(), s.get_state())
+    t1, sw1, st1 = out[1]
+    assert t1["accepted"].sum() > 0 and sw1[0] > 0            # (an all-Langevin Sunspot chain accepts rarely)
+    for depth in (2, 5, 16):
+        t, sw, st = out[depth]
+        for k in t1:
+            assert np.array_equal(t[k], t1[k]), (depth, k)
+        assert sw[0] == sw1[0] and sw[1] == sw1[1] and np.array_equal(sw[2], sw1[2]), depth
+        for k in ("w", "eta", "lik", "prior", "tau", "num_accepted"):
+            assert np.array_equal(st[k], st1[k]), (depth, k)
+
+
 def test_automatic_window_depth_follows_acceptance_and_changes_nothing():
     """Ladders that leave CTA slots free (here 96 temperatures of the 4-64-1 net: ~10 slots each) get speculative
     windows whose depth follows the acceptance rate observed so far on the run -- launches early in
