@@ -122,12 +122,19 @@ struct ptfnn_sampler {
     // the newest copy that has arrived, and waits for the copy of the launch before the previous one if it has not:
     // the host never runs more than two launches ahead of the estimate it steers by (a caller that queues a whole
     // run of launches at once would otherwise decide all of them blind)
-    struct AccSample { long long *host = nullptr; cudaEvent_t ev = nullptr; int step = 0; bool used = false; };
+    // The same sample times the launch (events around it) and counts its Langevin / random-walk steps: cost per
+    // random-walk-equivalent step of the two "arms" -- sequential, windows -- is what finally picks between them.
+    struct AccSample { long long *host = nullptr; cudaEvent_t ev = nullptr, t0 = nullptr, t1 = nullptr; int step = 0, arm = 0, launch = 0; bool used = false, timed = false; };
     AccSample acc_ring[4];
     DevBuf<long long> acc_sum;
     unsigned int acc_seq = 0;
     long long acc_prev_sum = 0; int acc_prev_step = 0; bool acc_have_prev = false;
     double acc_est = -1.0;            // < 0: nothing known yet
+    double arm_cost[2] = {-1.0, -1.0};   // ms per random-walk-equivalent step: [0] sequential, [1] windows; < 0: unknown
+    int arm_launched[2] = {-1, -1};      // feedback launch index at which the arm ran last
+    double arm_acc[2] = {1.0, 1.0};      // acceptance estimate at that launch
+    int arm_timed[2] = {-100, -100};     // launch index of the arm's last harvested timing
+    int fb_launches = 0;
 
     bool have_data = false, have_state = false, summary_smem_opted = false;
     int n_train = 0, n_test = 0;
@@ -170,6 +177,8 @@ struct ptfnn_sampler {
         for (auto &a : acc_ring) {
             if (a.host) cudaFreeHost(a.host);
             if (a.ev) cudaEventDestroy(a.ev);
+            if (a.t0) cudaEventDestroy(a.t0);
+            if (a.t1) cudaEventDestroy(a.t1);
             a = AccSample();
         }
         acc_sum.release();
@@ -512,6 +521,7 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     s->device_failed = false;
     s->acc_est = -1.0; s->acc_have_prev = false; s->acc_prev_sum = 0; s->acc_prev_step = 0;
     for (auto &a : s->acc_ring) a.used = false;
+    s->arm_cost[0] = s->arm_cost[1] = -1.0; s->arm_launched[0] = s->arm_launched[1] = -1; s->arm_acc[0] = s->arm_acc[1] = 1.0; s->arm_timed[0] = s->arm_timed[1] = -100; s->fb_launches = 0;
     s->step = 0; s->rounds_done = 0; s->swap_pending = false; s->pending_final = false;
     s->host_num_swap = 0; s->host_total_prop = 0; s->host_swap_log.clear(); s->host_swap_log_round.clear();
     s->have_state = true;
@@ -716,14 +726,27 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
             ptfnn_sampler::AccSample &old = s->acc_ring[(s->acc_seq - 2) & 3];
             if (old.used) CU_TRY(s, cudaEventSynchronize(old.ev));
         }
+        for (int k = 3; k >= 0; --k) {                   // launch timings, oldest first, each sample once
+            ptfnn_sampler::AccSample &a = s->acc_ring[(s->acc_seq + 3 - k) & 3];
+            if (!a.used || a.timed || cudaEventQuery(a.ev) != cudaSuccess) continue;
+            a.timed = true;
+            float ms = 0.0f;
+            const double units = (double)kSpecRwRun * (double)a.host[1] + (double)a.host[2];
+            if (cudaEventElapsedTime(&ms, a.t0, a.t1) == cudaSuccess && units > 0.0) {
+                const double c = (double)ms / units;
+                // (a timing after a pause replaces the old estimate: the run has moved on meanwhile)
+                s->arm_cost[a.arm] = (s->arm_cost[a.arm] < 0.0 || a.launch - s->arm_timed[a.arm] > 4) ? c : 0.5 * s->arm_cost[a.arm] + 0.5 * c;
+                s->arm_timed[a.arm] = a.launch;
+            }
+        }
         for (int k = 0; k < 4; ++k) {
             ptfnn_sampler::AccSample &a = s->acc_ring[(s->acc_seq + 3 - k) & 3];
             if (!a.used || cudaEventQuery(a.ev) != cudaSuccess) continue;
             if (s->acc_have_prev && a.step > s->acc_prev_step) {
-                const double rate = (double)(*a.host - s->acc_prev_sum) / ((double)R * (a.step - s->acc_prev_step));
+                const double rate = (double)(a.host[0] - s->acc_prev_sum) / ((double)R * (a.step - s->acc_prev_step));
                 s->acc_est = s->acc_est < 0.0 ? rate : 0.5 * s->acc_est + 0.5 * rate;
             }
-            if (!s->acc_have_prev || a.step > s->acc_prev_step) { s->acc_prev_sum = *a.host; s->acc_prev_step = a.step; s->acc_have_prev = true; }
+            if (!s->acc_have_prev || a.step > s->acc_prev_step) { s->acc_prev_sum = a.host[0]; s->acc_prev_step = a.step; s->acc_have_prev = true; }
             break;
         }
     }
@@ -745,6 +768,26 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
                 // (measured, 4-64-1: two CTAs per temperature pay below ~4 % acceptance -- the doubled residency slows every
                 //  step by a quarter -- four or more already at 8 %: 31.5 against 38.8 ms per 10 steps of 128 temperatures)
                 want = a < 0.0 ? 1 : cap <= 2 ? (a <= 0.04 ? cap : 1) : cap == 3 ? (a <= 0.08 ? cap : 1) : a <= 0.30 ? cap : a <= 0.60 ? std::min(cap, 4) : 1;
+            // ... and the clock has the last word.  The rate above is this rank's mean; what a segment costs with windows
+            // is set by the temperature with the MOST acceptances in it, of the whole ladder (every one of them costs that
+            // temperature another window and everybody meets at the swap round): 8 GPUs x 128 temperatures at 11 % ran
+            // 45.5 ms per 10 steps with windows against ~36 sequentially, although 128 temperatures alone gain.  So both
+            // ways of running are timed on this run (cost per random-walk-equivalent step, see the harvest above), the
+            // cheaper one is used, and the other one is tried again every kReprobe launches.
+            if (spec_feedback && a >= 0.0 && a <= 0.60 && cap > 1) {
+                const int kReprobe = 32, L = s->fb_launches;
+                const int kwin = want > 1 ? want : (a <= 0.30 ? cap : std::min(cap, 4));
+                // (stale: not run for kReprobe launches, or the acceptance rate has fallen by a third since -- windows get
+                //  cheaper quickly while a run burns in)
+                auto stale = [&](int arm) { return s->arm_launched[arm] < 0 || L - s->arm_launched[arm] >= kReprobe || (arm == 1 && a < 0.67 * s->arm_acc[1]); };
+                int arm;
+                if (stale(0)) arm = 0;
+                else if (stale(1)) arm = 1;
+                else if (s->arm_cost[0] < 0.0) arm = 0;            // launched, not timed yet: stay until it is
+                else if (s->arm_cost[1] < 0.0) arm = 1;
+                else arm = s->arm_cost[1] < 0.97 * s->arm_cost[0] ? 1 : 0;
+                want = arm ? kwin : 1;
+            }
         }
         spec = std::max(1, std::min(want, cap));
     }
@@ -761,24 +804,34 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     }
     // many temperatures per SM: keep the serial warps' sub-partitions quiet (see chain_kernel)
     void *args[] = {&p};
+    ptfnn_sampler::AccSample *fb = nullptr;
+    if (spec_feedback) {
+        fb = &s->acc_ring[s->acc_seq & 3];
+        if (!fb->host) {
+            CU_TRY(s, cudaHostAlloc((void **)&fb->host, 3 * sizeof(long long), cudaHostAllocDefault));
+            CU_TRY(s, cudaEventCreateWithFlags(&fb->ev, cudaEventDisableTiming));
+            CU_TRY(s, cudaEventCreate(&fb->t0));
+            CU_TRY(s, cudaEventCreate(&fb->t1));
+        }
+        if (fb->used && cudaEventSynchronize(fb->ev) != cudaSuccess) fb = nullptr;   // (the slot of four launches ago: long finished)
+    }
+    if (fb) CU_TRY(s, cudaEventRecord(fb->t0, s->stream));
     if (uses_tmem) CU_TRY(s, cudaLaunchKernel(s->ks->chain, dim3(grid), dim3(NT), args, L.total, s->stream));
     else CU_TRY(s, cudaLaunchCooperativeKernel(chain_fn, dim3(grid), dim3(NT), args, L.total, s->stream));
     CU_TRY(s, cudaGetLastError());
     s->step = end;
-    if (spec_feedback) {
-        ptfnn_sampler::AccSample &a = s->acc_ring[s->acc_seq & 3];
-        if (!a.host) {
-            CU_TRY(s, cudaHostAlloc((void **)&a.host, sizeof(long long), cudaHostAllocDefault));
-            CU_TRY(s, cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
-        }
-        if (!a.used || cudaEventSynchronize(a.ev) == cudaSuccess) {   // (the slot of four launches ago: long finished)
-            CU_TRY(s, s->acc_sum.ensure(1));
-            sum_int_kernel<<<1, 256, 0, s->stream>>>(s->n_acc.p, R, s->acc_sum.p);
-            CU_TRY(s, cudaMemcpyAsync(a.host, s->acc_sum.p, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
-            CU_TRY(s, cudaEventRecord(a.ev, s->stream));
-            a.step = end; a.used = true;
-            s->acc_seq += 1;
-        }
+    if (fb) {
+        CU_TRY(s, cudaEventRecord(fb->t1, s->stream));
+        CU_TRY(s, s->acc_sum.ensure(3));
+        const uint32_t gr0 = (uint32_t)c.replica_offset;
+        feedback_kernel<<<1, 256, 0, s->stream>>>(s->n_acc.p, R, c.seed, begin, n, c.common_random_numbers ? kStreamCommon : gr0, gr0,
+                                                  d ? p.lx : nullptr, c.use_langevin_gradients ? 1 : 0, (double)c.l_prob, s->acc_sum.p);
+        CU_TRY(s, cudaMemcpyAsync(fb->host, s->acc_sum.p, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(s, cudaEventRecord(fb->ev, s->stream));
+        fb->step = end; fb->used = true; fb->timed = false; fb->arm = spec > 1 ? 1 : 0; fb->launch = s->fb_launches;
+        s->arm_launched[fb->arm] = s->fb_launches; s->arm_acc[fb->arm] = s->acc_est < 0.0 ? 1.0 : s->acc_est;
+        s->fb_launches += 1;
+        s->acc_seq += 1;
     }
     if (external) {
         if (rounds_in_span > 0) { s->swap_pending = true; s->pending_final = false; }

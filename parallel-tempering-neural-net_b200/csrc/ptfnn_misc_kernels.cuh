@@ -41,18 +41,26 @@ __global__ void op_prior_kernel(int task, int I, int H, int O, const float *w, d
     }
 }
 
-// sum of an int array (the replicas' acceptance counters: feedback for the speculative-window depth)
-__global__ void sum_int_kernel(const int *v, int n, long long *out) {
-    __shared__ long long red[8];
-    long long a = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) a += v[k];
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+// Feedback sample for the automatic depth of the speculative windows: out[0] = sum of the replicas' acceptance
+// counters, out[1] / out[2] = Langevin / random-walk steps among the n steps the launch just made (first replica's
+// stream; lx != nullptr: replayed draws).
+__global__ void feedback_kernel(const int *n_acc, int R, uint64_t seed, int step0, int n, uint32_t stream, uint32_t gr,
+                                const float *lx, int use_lg, double l_prob, long long *out) {
+    __shared__ long long red[8][2];
+    long long a = 0, g = 0;
+    for (int k = threadIdx.x; k < R; k += blockDim.x) a += n_acc[k];
+    if (use_lg)
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const float x = lx ? lx[k] : philox_step_scalars(seed, (uint32_t)(step0 + k), stream, gr).lx;
+            g += ((double)x < l_prob) ? 1 : 0;
+        }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); g += __shfl_xor_sync(0xffffffffu, g, o); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = g; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
-        *out = t;
+        long long t = 0, u = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { t += red[k][0]; u += red[k][1]; }
+        out[0] = t; out[1] = u; out[2] = n - u;
     }
 }
 
