@@ -76,9 +76,11 @@ typedef struct ptfnn_config {
                                      * leaves state and traces untouched and makes every later call on the
                                      * handle fail with PTFNN_E_CUDA until ptfnn_init_chains */
     int32_t debug_traces;           /* 1 = also record prior_prop / diff_prop / mh_prob / accepted */
-    int32_t speculation;            /* small ladders: CTAs per temperature that evaluate consecutive steps
-                                     * speculatively (results are those of the sequential chain, bit for bit);
-                                     * 0 = automatic, 1 = off, K = that depth */
+    int32_t speculation;            /* ladders that leave CTA slots free: CTAs per temperature that evaluate the
+                                     * next steps speculatively, each as if the steps before it were rejected
+                                     * (results are those of the sequential chain, bit for bit);
+                                     * 0 = automatic (follows the acceptance rate and the launch times observed on
+                                     * the run), 1 = off, K = that many (clamped to what is co-resident, <= 16) */
     int32_t swap_kind;              /* PTFNN_SWAP_KIND_* */
     int32_t reserved0;              /* 0 */
     uint64_t seed;                  /* Philox key (free-running mode) */

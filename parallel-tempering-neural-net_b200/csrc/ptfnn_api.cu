@@ -715,8 +715,9 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
     }
     int grid = uses_tmem ? std::min(R, s->verified_grid) : std::min(R, per_sm * s->num_sms);
     // Small ladders leave most of the GPU idle (10 temperatures = 10 of 148 SMs): K CTAs per temperature
-    // evaluate K consecutive steps speculatively (chain_kernel, "speculative windows").  cfg.speculation:
-    // 0 = automatic, 1 = off, K > 1 = that depth (clamped to what is co-resident).
+    // evaluate the steps ahead speculatively, a Langevin step and the random-walk steps before it per CTA
+    // (chain_body, "speculative windows").  cfg.speculation: 0 = automatic, 1 = off, K > 1 = that many CTAs
+    // (clamped to what is co-resident).
     int spec = 1;
     const bool spec_possible = s->ks->chain_spec && !external && R * 2 <= per_sm * s->num_sms;
     const bool spec_auto = spec_possible && c.speculation == 0;

@@ -1176,8 +1176,8 @@ struct ChainParams {
     int max_rounds;
     int *swap_src;                 // [R] origin slot of the vector that ends in each local slot (per round)
     int P;
-    // ---- speculative windows for small ladders (spec_k > 1): spec_k CTAs per temperature evaluate spec_k
-    //      consecutive steps at once, each assuming that the earlier ones are rejected
+    // ---- speculative windows for ladders that leave CTA slots free (spec_k > 1): spec_k CTAs per temperature
+    //      share the next steps out among themselves (chain_body), each step assuming the earlier ones rejected
     int spec_k;
     GridBarrier *spec_bar;         // [R]         barrier of the CTAs of one temperature
     unsigned int *spec_flag;       // [R][kSpecWords]: per step of the window, then per CTA of the group (chain_body)

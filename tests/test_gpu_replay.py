@@ -191,7 +191,7 @@ def test_wide_hidden_chain_replay(memo):
 
 @pytest.mark.parametrize("memo", [0, 1])
 def test_speculative_windows_are_bit_identical(memo):
-    """Small ladders: K CTAs per temperature evaluate K consecutive steps at once, each assuming the earlier
+    """Small ladders: K CTAs per temperature evaluate the steps ahead at once, each step assuming the earlier
     ones rejected.  Every depth must give the sequential chain bit for bit: traces, swap
     decisions, counters and final state -- through swap rounds, the left-over round and the 60% temperature
     switch (step 120 of 200)."""
