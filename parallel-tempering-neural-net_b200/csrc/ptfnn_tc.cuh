@@ -270,7 +270,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 #ifdef PTFNN_TC_TRACE      // measurement builds only (tools/tc_trace.cu): clock stamps of the first tiles, per role
 __device__ long long g_tc_trace[2][8][64];
-#define TC_STAMP(role, k) do { if (lane == 0 && (role == 1 || warp == 0) && t < 8) g_tc_trace[role][t][k] = clock64(); } while (0)
+#define TC_STAMP(role, k) do { if (blockIdx.x == 0 && lane == 0 && (role == 1 || warp == 0) && t < 8) g_tc_trace[role][t][k] = clock64(); } while (0)
 #else
 #define TC_STAMP(role, k) do { } while (0)
 #endif

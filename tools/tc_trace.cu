@@ -34,7 +34,7 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, a, b);
         printf("grid %3d: %.3f ms = %.0f cycles per 128-row tile and CTA (%s)\n", grid, ms, ms * 1e-3 * 1.965e9 / ntiles, cudaGetErrorString(e));
-        if (grid == 1) {
+        {
             static long long tr[2][8][64];
             cudaMemcpyFromSymbol(tr, tc::g_tc_trace, sizeof tr);
             for (int t = 2; t < 5; ++t) {
