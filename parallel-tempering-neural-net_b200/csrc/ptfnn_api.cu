@@ -134,6 +134,7 @@ struct ptfnn_sampler {
     int arm_launched[2] = {-1, -1};      // feedback launch index at which the arm ran last
     double arm_acc[2] = {1.0, 1.0};      // acceptance estimate at that launch
     int arm_timed[2] = {-100, -100};     // launch index of the arm's last harvested timing
+    int arm_interval[2] = {32, 32};      // launches between two tries of the arm while it loses (doubles every time it loses again)
     int fb_launches = 0;
 
     bool have_data = false, have_state = false, summary_smem_opted = false;
@@ -521,7 +522,7 @@ extern "C" int ptfnn_init_chains(ptfnn_sampler *s, const double *w) {
     s->device_failed = false;
     s->acc_est = -1.0; s->acc_have_prev = false; s->acc_prev_sum = 0; s->acc_prev_step = 0;
     for (auto &a : s->acc_ring) a.used = false;
-    s->arm_cost[0] = s->arm_cost[1] = -1.0; s->arm_launched[0] = s->arm_launched[1] = -1; s->arm_acc[0] = s->arm_acc[1] = 1.0; s->arm_timed[0] = s->arm_timed[1] = -100; s->fb_launches = 0;
+    s->arm_cost[0] = s->arm_cost[1] = -1.0; s->arm_launched[0] = s->arm_launched[1] = -1; s->arm_acc[0] = s->arm_acc[1] = 1.0; s->arm_timed[0] = s->arm_timed[1] = -100; s->arm_interval[0] = s->arm_interval[1] = 32; s->fb_launches = 0;
     s->step = 0; s->rounds_done = 0; s->swap_pending = false; s->pending_final = false;
     s->host_num_swap = 0; s->host_total_prop = 0; s->host_swap_log.clear(); s->host_swap_log_round.clear();
     s->have_state = true;
@@ -736,8 +737,11 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
             if (cudaEventElapsedTime(&ms, a.t0, a.t1) == cudaSuccess && units > 0.0) {
                 const double c = (double)ms / units;
                 // (a timing after a pause replaces the old estimate: the run has moved on meanwhile)
-                s->arm_cost[a.arm] = (s->arm_cost[a.arm] < 0.0 || a.launch - s->arm_timed[a.arm] > 4) ? c : 0.5 * s->arm_cost[a.arm] + 0.5 * c;
+                const bool retry = a.launch - s->arm_timed[a.arm] > 4;
+                s->arm_cost[a.arm] = (s->arm_cost[a.arm] < 0.0 || retry) ? c : 0.5 * s->arm_cost[a.arm] + 0.5 * c;
                 s->arm_timed[a.arm] = a.launch;
+                if (retry && s->arm_cost[1 - a.arm] >= 0.0)       // a retry that lost again waits twice as long for the next one
+                    s->arm_interval[a.arm] = s->arm_cost[a.arm] > s->arm_cost[1 - a.arm] ? std::min(512, 2 * s->arm_interval[a.arm]) : 32;
             }
         }
         for (int k = 0; k < 4; ++k) {
@@ -774,13 +778,13 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
             // temperature another window and everybody meets at the swap round): 8 GPUs x 128 temperatures at 11 % ran
             // 45.5 ms per 10 steps with windows against ~36 sequentially, although 128 temperatures alone gain.  So both
             // ways of running are timed on this run (cost per random-walk-equivalent step, see the harvest above), the
-            // cheaper one is used, and the other one is tried again every kReprobe launches.
+            // cheaper one is used, and the other one is tried again every 32 launches -- twice as many after every try it loses.
             if (spec_feedback && a >= 0.0 && a <= 0.60 && cap > 1) {
-                const int kReprobe = 32, L = s->fb_launches;
+                const int L = s->fb_launches;
                 const int kwin = want > 1 ? want : (a <= 0.30 ? cap : std::min(cap, 4));
                 // (stale: not run for kReprobe launches, or the acceptance rate has fallen by a third since -- windows get
                 //  cheaper quickly while a run burns in)
-                auto stale = [&](int arm) { return s->arm_launched[arm] < 0 || L - s->arm_launched[arm] >= kReprobe || (arm == 1 && a < 0.67 * s->arm_acc[1]); };
+                auto stale = [&](int arm) { return s->arm_launched[arm] < 0 || L - s->arm_launched[arm] >= s->arm_interval[arm] || (arm == 1 && a < 0.67 * s->arm_acc[1]); };
                 int arm;
                 if (stale(0)) arm = 0;
                 else if (stale(1)) arm = 1;
@@ -846,7 +850,30 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
 
 extern "C" int ptfnn_run(ptfnn_sampler *s, int32_t n_steps, int32_t *steps_done) {
     if (!s) return fail(nullptr, PTFNN_E_INVALID, "null handle");
-    return launch_chain(s, n_steps, nullptr, steps_done);
+    // Ladders on which the automatic speculation steers by what earlier launches of the run showed (launch_chain:
+    // acceptance rate, launch times) get a long request in pieces that end on swap rounds -- otherwise a caller that
+    // asks for the whole chain at once would run all of it on the decision of step 0.  Pieces cost a launch (~10 us) per
+    // >= 64 steps.  (Replayed draws, fixed depths, tiny and full ladders: one launch, as asked.)
+    const ptfnn_config &c = s->cfg;
+    const bool host_rounds = c.n_replicas_global > c.n_replicas && s->n_ranks == 1;
+    const bool adaptive = s->ks && s->ks->chain_spec && c.speculation == 0 && !host_rounds && c.n_replicas_global > 1 &&
+                          2 * c.n_replicas > s->num_sms && c.n_replicas <= 8 * s->num_sms;
+    if (!adaptive) return launch_chain(s, n_steps, nullptr, steps_done);
+    if (steps_done) *steps_done = 0;
+    const int rounds_per_piece = std::max(1, (64 + c.swap_interval - 1) / c.swap_interval);
+    int remaining = n_steps, total = 0;
+    while (remaining > 0) {
+        int piece = remaining, rounds = 0;
+        for (int k = 0; k < remaining; ++k)
+            if (h_swap_due(s->swap_rule, c.swap_interval, s->step + k) && ++rounds == rounds_per_piece) { piece = k + 1; break; }
+        int32_t done = 0;
+        const int rc = launch_chain(s, piece, nullptr, &done);
+        if (rc != PTFNN_OK) return rc;
+        total += done; remaining -= piece;
+        if (steps_done) *steps_done = total;
+        if (done < piece) break;          // the end of the chain
+    }
+    return PTFNN_OK;
 }
 
 extern "C" int ptfnn_replay(ptfnn_sampler *s, const ptfnn_draws *d, int32_t *steps_done) {

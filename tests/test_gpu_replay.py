@@ -271,11 +271,14 @@ def test_automatic_window_depth_follows_acceptance_and_changes_nothing():
     temps = geometric_ladder(R, 2)
     w0 = np.random.RandomState(5).randn(R, 385) * 0.5
     out = {}
-    for depth in (1, 0, 6):                 # sequential | automatic | fixed
+    for depth in (1, 0, 6, "0, one call"):  # sequential | automatic | fixed | automatic, the whole chain asked for at once
         with Sampler(on.REGRESSION, (4, 64, 1), temps, S, si, use_langevin_gradients=True, l_prob=0.5, learn_rate=0.01,
-                     seed=9, common_random_numbers=True, memoize_gradient=1, debug_traces=True, speculation=depth) as s:
+                     seed=9, common_random_numbers=True, memoize_gradient=1, debug_traces=True,
+                     speculation=depth if isinstance(depth, int) else 0) as s:
             s.set_data(tr, te)
             s.init_chains(w0)
+            if isinstance(depth, str):
+                assert s.run() == S - 1     # (the library launches it in pieces that end on swap rounds, and steers between them)
             while s.step < S - 1:
                 s.run(si)
                 s.sync()                    # (gives the asynchronous acceptance sample time to arrive: the depth may change)
@@ -283,7 +286,7 @@ def test_automatic_window_depth_follows_acceptance_and_changes_nothing():
     t1, sw1, st1 = out[1]
     acc_rate = t1["accepted"][:, 60:].mean()
     assert acc_rate < 0.6                   # the regime in which the automatic policy opens windows
-    for depth in (0, 6):
+    for depth in (0, 6, "0, one call"):
         t, sw, st = out[depth]
         for k in t1:
             assert np.array_equal(t[k], t1[k]), (depth, k)
