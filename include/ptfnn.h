@@ -146,7 +146,9 @@ int ptfnn_destroy(ptfnn_sampler *s);
 int ptfnn_set_stream(ptfnn_sampler *s, void *cuda_stream); /* cudaStream_t, e.g. torch's current stream */
 
 /* traindata / testdata as passed to ParallelTempering (R:491-492): row-major [rows, n_cols] float64,
- * inputs in columns [0, I), target (R:201) or integer class label (C:210) in column I. */
+ * inputs in columns [0, I), target (R:201) or integer class label (C:210) in column I.
+ * The arrays are read before the call returns (caller keeps them); the upload itself is queued on the handle's
+ * stream from page-locked staging and does not wait for the device. */
 int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_train, const double *test,
                    int32_t n_test, int32_t n_cols);
 

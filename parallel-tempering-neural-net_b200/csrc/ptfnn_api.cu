@@ -114,6 +114,10 @@ struct ptfnn_sampler {
     // overlapped read-back (ptfnn_traces_begin / _end): two page-locked slots filled on a copy stream
     struct FetchSlot { void *buf = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; size_t off[7] = {}; bool has_w = false; int first = 0, count = 0; bool busy = false; };
     FetchSlot slot[2];
+    // ptfnn_set_data: page-locked staging of the packed data set, double buffered (no wait for the device)
+    struct StageSlot { float *buf = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool used = false; };
+    StageSlot stage[2];
+    unsigned int stage_seq = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_compute = nullptr;
     unsigned int fetch_seq = 0;
@@ -174,6 +178,11 @@ struct ptfnn_sampler {
             if (f.buf) cudaFreeHost(f.buf);
             if (f.done) cudaEventDestroy(f.done);
             f = FetchSlot();
+        }
+        for (auto &g : stage) {
+            if (g.buf) cudaFreeHost(g.buf);
+            if (g.done) cudaEventDestroy(g.done);
+            g = StageSlot();
         }
         for (auto &a : acc_ring) {
             if (a.host) cudaFreeHost(a.host);
@@ -405,10 +414,9 @@ static const char *kDeviceFailedMsg = "a device-side wait of an earlier launch t
                                       "traces were left untouched -- call ptfnn_init_chains to start over";
 
 // row-major float64 [rows, n_cols] -> padded float32 X [rows][IP] + y [pad4(rows)]
-static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP, std::vector<float> &x,
-                         std::vector<float> &y) {
-    x.assign((size_t)rows * IP, 0.0f);
-    y.assign((size_t)((rows + 3) & ~3), 0.0f);
+static void pack_dataset(const double *data, int rows, int n_cols, int I, int IP, float *x, float *y) {
+    memset(x, 0, (size_t)rows * IP * sizeof(float));
+    memset(y, 0, (size_t)((rows + 3) & ~3) * sizeof(float));
     for (int r = 0; r < rows; ++r) {
         for (int i = 0; i < I; ++i) x[(size_t)r * IP + i] = (float)data[(size_t)r * n_cols + i];
         y[r] = (float)data[(size_t)r * n_cols + I];
@@ -438,23 +446,40 @@ extern "C" int ptfnn_set_data(ptfnn_sampler *s, const double *train, int32_t n_t
         if (bad >= 0) return fail(s, PTFNN_E_INVALID, "test row %d: label %g outside [0, %d)", bad, test[(size_t)bad * n_cols + s->cfg.n_in], s->cfg.n_out);
     }
     CU_TRY(s, cudaSetDevice(s->cfg.device));
-    std::vector<float> x, y;
-    pack_dataset(train, n_train, n_cols, s->cfg.n_in, s->IP, x, y);
-    CU_TRY(s, s->train_x.ensure(x.size())); CU_TRY(s, s->train_y.ensure(y.size()));
-    CU_TRY(s, cudaMemcpyAsync(s->train_x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    CU_TRY(s, cudaMemcpyAsync(s->train_y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
-    pack_dataset(test, n_test, n_cols, s->cfg.n_in, s->IP, x, y);
-    CU_TRY(s, s->test_x.ensure(x.size())); CU_TRY(s, s->test_y.ensure(y.size()));
-    CU_TRY(s, cudaMemcpyAsync(s->test_x.p, x.data(), x.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    CU_TRY(s, cudaMemcpyAsync(s->test_y.p, y.data(), y.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    // The rows are packed (fp32, padded to IP floats) into one of two page-locked staging slots and copied behind
+    // whatever the stream is doing: the call does not wait for the device -- a caller that uploads a data set between
+    // two launches keeps the GPU busy meanwhile (bench.py's e2e loop).  A slot is reused two calls later, after the
+    // event recorded behind its copies.
+    const int IP = s->IP, I = s->cfg.n_in;
+    const size_t nx_tr = (size_t)n_train * IP, ny_tr = (size_t)((n_train + 3) & ~3);
+    const size_t nx_te = (size_t)n_test * IP, ny_te = (size_t)((n_test + 3) & ~3);
+    const size_t need = (nx_tr + ny_tr + nx_te + ny_te) * sizeof(float);
+    ptfnn_sampler::StageSlot &st = s->stage[s->stage_seq & 1];
+    s->stage_seq += 1;
+    if (st.used) CU_TRY(s, cudaEventSynchronize(st.done));
+    if (st.bytes < need) {
+        if (st.buf) CU_TRY(s, cudaFreeHost(st.buf));
+        st.buf = nullptr; st.bytes = 0;
+        CU_TRY(s, cudaHostAlloc((void **)&st.buf, need, cudaHostAllocDefault));
+        st.bytes = need;
+    }
+    if (!st.done) CU_TRY(s, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    float *hx_tr = st.buf, *hy_tr = hx_tr + nx_tr, *hx_te = hy_tr + ny_tr, *hy_te = hx_te + nx_te;
+    pack_dataset(train, n_train, n_cols, I, IP, hx_tr, hy_tr);
+    pack_dataset(test, n_test, n_cols, I, IP, hx_te, hy_te);
+    CU_TRY(s, s->train_x.ensure(nx_tr)); CU_TRY(s, s->train_y.ensure(ny_tr));
+    CU_TRY(s, s->test_x.ensure(nx_te)); CU_TRY(s, s->test_y.ensure(ny_te));
+    CU_TRY(s, cudaMemcpyAsync(s->train_x.p, hx_tr, nx_tr * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->train_y.p, hy_tr, ny_tr * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->test_x.p, hx_te, nx_te * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemcpyAsync(s->test_y.p, hy_te, ny_te * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaEventRecord(st.done, s->stream));
+    st.used = true;
     s->n_train = n_train; s->n_test = n_test;
     if (s->ks->fwd_tc) {
         int rc = pack_a_tiles(s, s->ks, s->train_x.p, n_train, s->IP, s->a_train, s->stream);
         if (!rc) rc = pack_a_tiles(s, s->ks, s->test_x.p, n_test, s->IP, s->a_test, s->stream);
         if (rc) return rc;
-        CU_TRY(s, cudaStreamSynchronize(s->stream));
     }
     s->have_data = true;
     return PTFNN_OK;
@@ -1435,8 +1460,8 @@ static int op_prepare(int device, int task, int I, int H, int O, const double *d
         if (rows < 1 || n_cols < I + 1) return fail(nullptr, PTFNN_E_INVALID, "bad data shape [%d,%d]", rows, n_cols);
         const int bad = task == PTFNN_TASK_CLASSIFICATION ? first_bad_label(data, rows, n_cols, I, O) : -1;
         if (bad >= 0 && labels_used) return fail(nullptr, PTFNN_E_INVALID, "row %d: label %g outside [0, %d)", bad, data[(size_t)bad * n_cols + I], O);
-        std::vector<float> x, y;
-        pack_dataset(data, rows, n_cols, I, IP, x, y);
+        std::vector<float> x((size_t)rows * IP), y((size_t)((rows + 3) & ~3));
+        pack_dataset(data, rows, n_cols, I, IP, x.data(), y.data());
         if (bad >= 0)                                            // evaluate_proposal never looks at the labels (C:134-153): any valid class keeps the kernel in bounds
             for (int r = 0; r < rows; ++r) y[r] = std::min(std::max(y[r], 0.0f), (float)(O - 1));
         CU_TRY(nullptr, od.x.ensure(x.size())); CU_TRY(nullptr, od.y.ensure(y.size()));
