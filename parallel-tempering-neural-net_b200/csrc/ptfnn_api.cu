@@ -822,6 +822,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
         spec = std::max(1, std::min(want, cap));
     }
     p.spec_k = spec; p.spec_bar = s->spec_bar.p; p.spec_flag = s->spec_flag.p;
+    { const char *e = getenv("PTFNN_SPEC_PLAN"); p.spec_plan = e ? atoi(e) : 0; }      // measurement knob (tools/): results do not depend on it
     const void *chain_fn = s->ks->chain;
     if (spec > 1) {
         chain_fn = s->ks->chain_spec;

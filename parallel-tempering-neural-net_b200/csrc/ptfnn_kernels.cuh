@@ -1179,6 +1179,7 @@ struct ChainParams {
     // ---- speculative windows for ladders that leave CTA slots free (spec_k > 1): spec_k CTAs per temperature
     //      share the next steps out among themselves (chain_body), each step assuming the earlier ones rejected
     int spec_k;
+    int spec_plan;                 // 0 = choose per window; 1 = "apart", 2 = "riding" (measurement knob, chain_body)
     GridBarrier *spec_bar;         // [R]         barrier of the CTAs of one temperature
     unsigned int *spec_flag;       // [R][kSpecWords]: per step of the window, then per CTA of the group (chain_body)
     // ---- multi-GPU ladder through peer memory (n_ranks > 1): every rank's pub_lhood / pub_rows / peer_flags
@@ -1587,10 +1588,17 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
                         if (ibase == sw) wcap = 1;
                         else if (ibase < sw && ibase + wcap > sw) wcap = sw - ibase;
                     }
-                    // warp 0 plans: a step goes to the CTA whose index is the number of Langevin steps before it in the
-                    // window, i.e. every CTA evaluates the random-walk steps that precede "its" Langevin step and
-                    // then that step (in step order); a run of random-walk steps longer than kSpecRwRun moves on to
-                    // the next CTA.  The window ends before the first step that would need CTA K.
+                    // warp 0 plans.  Two ways to share the steps out, both with one Langevin step per CTA at most:
+                    //   "apart":  the j-th Langevin step goes to CTA j, the random-walk steps to CTAs K-1, K-2, ...
+                    //             (kSpecRwRun to a CTA): nothing runs before a Langevin step, the window lasts one of them;
+                    //             it ends before the step at which the two ranges would meet.
+                    //   "riding": a step goes to the CTA whose index is the number of Langevin steps before it, i.e. a CTA
+                    //             evaluates the random-walk steps that precede "its" Langevin step and then that step (a run
+                    //             of more than kSpecRwRun random-walk steps moves on): K Langevin steps per window, each
+                    //             a few random-walk steps late.
+                    // "apart" is used unless "riding" covers more steps (with few CTAs per temperature it does).  Measured on one
+                    // box, apart | riding: Sunspot (K = 14) 737 k | 660 k replica-steps/s; 10 steps of 128 temperatures (K = 8)
+                    // 11.7 | 12.6 ms, of 256 (K = 4) 20.0 | 19.3 ms, of 512 (K = 2) 39.3 | 33.9 ms.
                     if (tid < 32) {
                         bool lgt = false;
                         if (tid < wcap) {
@@ -1602,11 +1610,16 @@ __device__ __forceinline__ void chain_body(const ChainParams &p) {
                         }
                         const unsigned int in_cap = wcap >= 32 ? 0xffffffffu : ((1u << wcap) - 1u);
                         const unsigned int lgm = __ballot_sync(0xffffffffu, lgt) & in_cap;
-                        const int n_before = __popc(lgm & ((1u << tid) - 1u));
-                        const int owner = p.use_lg ? max(n_before, tid / (kSpecRwRun + 1)) : tid;      // (non-decreasing in the step)
-                        const unsigned int fm = __ballot_sync(0xffffffffu, tid < wcap && owner < K);
-                        s_plan[tid] = owner;
-                        if (tid == 0) s_plan[kSpecWin] = __popc(fm);
+                        const unsigned int before = (1u << tid) - 1u;
+                        const int n_before = __popc(lgm & before), m_before = __popc(~lgm & in_cap & before);
+                        const int n_incl = n_before + (lgt ? 1 : 0), m_incl = m_before + (lgt ? 0 : 1);
+                        const int owner_apart = lgt ? n_before : K - 1 - m_before / kSpecRwRun;
+                        const int owner_riding = p.use_lg ? max(n_before, tid / (kSpecRwRun + 1)) : tid;      // (non-decreasing in the step)
+                        const int w_apart = __popc(__ballot_sync(0xffffffffu, tid < wcap && n_incl + (m_incl + kSpecRwRun - 1) / kSpecRwRun <= K));
+                        const int w_riding = __popc(__ballot_sync(0xffffffffu, tid < wcap && owner_riding < K));
+                        const bool apart = p.use_lg && (p.spec_plan == 1 || (p.spec_plan == 0 && w_apart + (K >= 8 ? 2 : 0) >= w_riding));
+                        s_plan[tid] = apart ? owner_apart : owner_riding;
+                        if (tid == 0) s_plan[kSpecWin] = apart ? w_apart : w_riding;
                     }
                     __syncthreads();
                     W = s_plan[kSpecWin];
