@@ -804,9 +804,9 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
             // 45.5 ms per 10 steps with windows against ~36 sequentially, although 128 temperatures alone gain.  So both
             // ways of running are timed on this run (cost per random-walk-equivalent step, see the harvest above), the
             // cheaper one is used, and the other one is tried again every 32 launches -- twice as many after every try it loses.
-            if (spec_feedback && a >= 0.0 && a <= 0.60 && cap > 1) {
+            if (spec_feedback && want > 1) {                       // (where the rate rules windows out they are not tried either)
                 const int L = s->fb_launches;
-                const int kwin = want > 1 ? want : (a <= 0.30 ? cap : std::min(cap, 4));
+                const int kwin = want;
                 // (stale: not run for kReprobe launches, or the acceptance rate has fallen by a third since -- windows get
                 //  cheaper quickly while a run burns in)
                 auto stale = [&](int arm) { return s->arm_launched[arm] < 0 || L - s->arm_launched[arm] >= s->arm_interval[arm] || (arm == 1 && a < 0.67 * s->arm_acc[1]); };
