@@ -1,6 +1,6 @@
 """Measurement helper: where the time of a small-ladder run with speculative windows goes.  Runs the Sunspot
-configuration of the bench, then replays the window plan (chain_body: owner = Langevin steps before the step, runs of
-more than 8 random-walk steps move on, 32 steps at most) on the recorded acceptances and lx draws, and compares the
+configuration of the bench, then replays the window plan of chain_body (32 steps at most, one Langevin step per CTA,
+"apart" or "riding") on the recorded acceptances and lx draws, and compares the
 number of windows of the slowest temperature per swap segment with the measured time."""
 import os, sys
 import numpy as np
@@ -30,11 +30,19 @@ for g in range(nseg):
         L, A = lg[r, g * si:(g + 1) * si], acc[r, g * si:(g + 1) * si]
         i, nw = 0, 0
         while i < si:
-            n_lg, w = 0, 0
-            while i + w < si and w < 32:
-                owner = max(n_lg, w // 9)
-                if owner >= K: break
-                n_lg += int(L[i + w]); w += 1
+            # chain_body's plan: "apart" (Langevin step j on CTA j, random-walk steps eight to a CTA from the top) unless
+            # "riding" (owner = Langevin steps before the step) covers more than two steps more
+            wcap = min(32, si - i)
+            n_lg = m = w_apart = w_riding = 0
+            for t in range(wcap):
+                if max(n_lg, t // 9) >= K: break
+                n_lg += int(L[i + t]); w_riding += 1
+            n_lg = 0
+            for t in range(wcap):
+                n2, m2 = n_lg + int(L[i + t]), m + int(not L[i + t])
+                if n2 + (m2 + 7) // 8 > K: break
+                n_lg, m, w_apart = n2, m2, w_apart + 1
+            w = w_apart if w_apart + (2 if K >= 8 else 0) >= w_riding else w_riding
             hit = np.flatnonzero(A[i:i + w])
             i += (hit[0] + 1) if hit.size else w
             nw += 1
