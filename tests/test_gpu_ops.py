@@ -343,3 +343,39 @@ def test_a_wait_that_gives_up_fails_closed():
         except OSError:
             pass
         idle.wait(timeout=60)
+
+
+def test_set_data_between_launches_does_not_wait_and_is_stream_ordered():
+    """ptfnn_set_data packs into page-locked staging and queues the upload behind the running launch (no wait for the
+    device; two slots, reused two calls later).  Data sets swapped between launches without any synchronisation in
+    between -- three times, so that a staging slot is reused -- must give exactly the chain that waits after every call,
+    also for the tcgen05 topology, whose A tiles are repacked on the device by the same call."""
+    from ptnn_b200.sampler import Sampler, geometric_ladder
+    from ptnn_b200 import datasets
+    for task, topo, lr in ((on.REGRESSION, (4, 5, 1), 0.1), (on.CLASSIFICATION, (16, 256, 10), 0.01)):
+        if task == on.REGRESSION:
+            tr, te = cm.dataset(on.REGRESSION, "Sunspot")
+            sets = [(tr, te), (tr[::-1].copy(), te), (tr[:200], te[:100]), (tr, te[::-1].copy())]
+        else:
+            tr, te = datasets.synthetic_pendigit(n_train=700, n_test=300)
+            sets = [(tr, te), (tr[::-1].copy(), te), (tr[:300], te[:130]), (tr, te[::-1].copy())]
+        R, S, n = 4, 4 * 12 + 2, 12
+        P = topo[0] * topo[1] + topo[1] * topo[2] + topo[1] + topo[2]
+        w0 = np.random.RandomState(2).randn(R, P) * 0.3
+        out = []
+        for wait in (True, False):
+            with Sampler(task, topo, geometric_ladder(R, 2), S, 5, learn_rate=lr, seed=11, debug_traces=True) as s:
+                s.set_data(*sets[0])
+                s.init_chains(w0)
+                for a, b in sets:
+                    s.set_data(a, b)
+                    if wait:
+                        s.sync()
+                    s.run(n)
+                    if wait:
+                        s.sync()
+                out.append((s.traces(), s.get_state()))
+        for k in out[0][0]:
+            assert np.array_equal(out[0][0][k], out[1][0][k]), (topo, k)
+        for k in ("w", "eta", "lik", "prior", "tau", "num_accepted"):
+            assert np.array_equal(out[0][1][k], out[1][1][k]), (topo, k)
