@@ -20,13 +20,13 @@ for name in ("Iris", "Ionosphere", "Cancer"):
 R, n_launch = 10, 6
 for c in cases:
     tr, te = d[c["name"] + "_train"], d[c["name"] + "_test"]
-    S = c["si"] * (n_launch + 2) + 2
+    S = c["si"] * (n_launch + 2) + 3
     for memo in (0, 1):
         s = Sampler(c["task"], c["topo"], geometric_ladder(R, c["maxtemp"]), S, c["si"], use_langevin_gradients=c["lg"],
                     l_prob=0.5, learn_rate=c["lr"], memoize_gradient=memo, seed=1, stream=torch.cuda.current_stream())
         s.set_data(tr, te)
         s.init_chains(np.random.RandomState(0).randn(R, s.P))
-        s.run(2 * c["si"])
+        s.run(2 * c["si"] + (1 if c["task"] == 0 else 0))      # launches end on swap rounds (R:427 | C:438)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); a.record()
         for _ in range(n_launch):
