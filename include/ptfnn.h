@@ -82,7 +82,9 @@ typedef struct ptfnn_config {
                                      * 0 = automatic (follows the acceptance rate and the launch times observed on
                                      * the run), 1 = off, K = that many (clamped to what is co-resident, <= 16) */
     int32_t swap_kind;              /* PTFNN_SWAP_KIND_* */
-    int32_t reserved0;              /* 0 */
+    int32_t window_plan;            /* shape of the speculative windows (measurement only; the results do not depend
+                                     * on it): 0 = chosen per window (default), 1 = random-walk steps on CTAs of their
+                                     * own ("apart"), 2 = before the CTA's Langevin step ("riding") */
     uint64_t seed;                  /* Philox key (free-running mode) */
     double l_prob;                  /* langevin_prob, R:174 (C:192 fixes 0.5) */
     double learn_rate;              /* R:172 */

@@ -45,7 +45,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "task", "n_in", "n_hidden", "n_out", "n_replicas", "n_replicas_global", "replica_offset",
         "samples", "swap_interval", "swap_rule", "use_langevin_gradients", "common_random_numbers",
-        "memoize_gradient", "device", "barrier_timeout_ms", "debug_traces", "speculation", "swap_kind", "reserved0")] + \
+        "memoize_gradient", "device", "barrier_timeout_ms", "debug_traces", "speculation", "swap_kind", "window_plan")] + \
         [("seed", C.c_uint64)] + \
         [(n, C.c_double) for n in ("l_prob", "learn_rate", "step_w", "step_eta", "sigma_squared", "nu_1", "nu_2",
                                    "pt_fraction")]

@@ -324,6 +324,7 @@ extern "C" int ptfnn_create(const ptfnn_config *cfg, const double *temperatures,
         return fail(nullptr, PTFNN_E_INVALID, "bad swap_rule %d", cfg->swap_rule);
     if (cfg->swap_kind != PTFNN_SWAP_KIND_REFERENCE && cfg->swap_kind != PTFNN_SWAP_KIND_RATIO_TEMPERATURE)
         return fail(nullptr, PTFNN_E_INVALID, "bad swap_kind %d", cfg->swap_kind);
+    if (cfg->window_plan < 0 || cfg->window_plan > 2) return fail(nullptr, PTFNN_E_INVALID, "bad window_plan %d", cfg->window_plan);
     if (cfg->barrier_timeout_ms < 0) return fail(nullptr, PTFNN_E_INVALID, "barrier_timeout_ms %d < 0", cfg->barrier_timeout_ms);
     if (!(cfg->l_prob >= 0.0 && cfg->l_prob <= 1.0) || !std::isfinite(cfg->learn_rate) || !(cfg->step_w >= 0.0) || !(cfg->step_eta >= 0.0) ||
         !(cfg->sigma_squared > 0.0) || !std::isfinite(cfg->nu_1) || !std::isfinite(cfg->nu_2) || !(cfg->pt_fraction >= 0.0))
@@ -822,7 +823,7 @@ static int launch_chain(ptfnn_sampler *s, int n_steps, const ptfnn_draws *d, int
         spec = std::max(1, std::min(want, cap));
     }
     p.spec_k = spec; p.spec_bar = s->spec_bar.p; p.spec_flag = s->spec_flag.p;
-    { const char *e = getenv("PTFNN_SPEC_PLAN"); p.spec_plan = e ? atoi(e) : 0; }      // measurement knob (tools/): results do not depend on it
+    p.spec_plan = c.window_plan;                       // measurement knob (tools/): results do not depend on it
     const void *chain_fn = s->ks->chain;
     if (spec > 1) {
         chain_fn = s->ks->chain_spec;

@@ -34,7 +34,7 @@ class Sampler:
                  l_prob=0.5, learn_rate=0.1, seed=0, common_random_numbers=True, memoize_gradient=True,
                  device=0, debug_traces=False, swap_rule=capi.SWAP_RULE_AUTO, n_replicas_global=None,
                  replica_offset=0, step_w=0.025, step_eta=0.2, sigma_squared=25.0, nu_1=0.0, nu_2=0.0,
-                 pt_fraction=0.6, stream=None, speculation=0, swap_kind=capi.SWAP_KIND_REFERENCE, barrier_timeout_ms=0):
+                 pt_fraction=0.6, stream=None, speculation=0, swap_kind=capi.SWAP_KIND_REFERENCE, barrier_timeout_ms=0, window_plan=0):
         lib = capi.load()
         capi.ensure_topology(task, topology)      # compiles a specialisation on first use of a new topology
         c = capi.default_config()
@@ -45,6 +45,7 @@ class Sampler:
         c.n_replicas_global = int(n_replicas_global or c.n_replicas)
         c.replica_offset = int(replica_offset)
         c.speculation = int(speculation)      # small ladders: 0 automatic, 1 off, K CTAs per temperature
+        c.window_plan = int(window_plan)      # measurement only: 0 per window, 1 'apart', 2 'riding' (same results)
         c.swap_kind = int(swap_kind)          # 0 = the reference's swap probability (R:674); 1 = the drafts' temperature-aware rule
         c.barrier_timeout_ms = int(barrier_timeout_ms)   # device-side waits give up after this long without progress (0 = 20 s)
         c.samples, c.swap_interval, c.swap_rule = int(samples), int(swap_interval), int(swap_rule)

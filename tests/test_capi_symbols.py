@@ -84,7 +84,8 @@ def test_argument_validation_happens_before_cuda(lib):
         Sampler(capi.TASK_REGRESSION, (4, 5, 1), [1.0, 2.0], 1, 5)            # samples < 2
     assert e.value.code == capi.E_INVALID
     for temps, kw in (([1.0, 0.0], {}), ([1.0, float("nan")], {}), ([1.0, -2.0], {}),          # the likelihood is divided by T (R:204)
-                      ([1.0, 2.0], {"l_prob": 1.5}), ([1.0, 2.0], {"learn_rate": float("inf")})):
+                      ([1.0, 2.0], {"l_prob": 1.5}), ([1.0, 2.0], {"learn_rate": float("inf")}),
+                      ([1.0, 2.0], {"window_plan": 3}), ([1.0, 2.0], {"swap_kind": 7}), ([1.0, 2.0], {"barrier_timeout_ms": -1})):
         with pytest.raises(capi.PtfnnError) as e:
             Sampler(capi.TASK_REGRESSION, (4, 5, 1), temps, 10, 5, **kw)
         assert e.value.code == capi.E_INVALID
