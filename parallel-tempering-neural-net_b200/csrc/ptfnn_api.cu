@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -57,7 +58,11 @@ static std::vector<const KernelSet *> &kernel_sets() {
     return v;      // + specialisations registered at run time (ptfnn_register_kernels)
 }
 
+// handles may be created from several host threads while another one registers a specialisation
+static std::mutex &kernel_sets_mutex() { static std::mutex m; return m; }
+
 static const KernelSet *find_kernels(int task, int I, int H, int O) {
+    std::lock_guard<std::mutex> g(kernel_sets_mutex());
     for (const KernelSet *k : kernel_sets())
         if (k->task == task && k->I == I && k->H == H && k->O == O) return k;
     return nullptr;
@@ -66,6 +71,7 @@ static const KernelSet *find_kernels(int task, int I, int H, int O) {
 static std::string supported_list() {
     std::string s;
     char buf[64];
+    std::lock_guard<std::mutex> g(kernel_sets_mutex());
     for (const KernelSet *k : kernel_sets()) {
         snprintf(buf, sizeof buf, "%s[%d,%d,%d] ", k->task == kTaskReg ? "reg" : "cls", k->I, k->H, k->O);
         s += buf;
@@ -243,15 +249,12 @@ static int h_total_rounds(const ptfnn_sampler *s) {
 extern "C" int ptfnn_abi_version(void) { return PTFNN_ABI_VERSION; }
 
 extern "C" const char *ptfnn_build_info(void) {
-    static std::string info;
-    static size_t n_sets = 0;
-    if (info.empty() || n_sets != kernel_sets().size()) {
-        n_sets = kernel_sets().size();
-        char buf[256];
-        snprintf(buf, sizeof buf, "libptfnn abi %d, sm_100a, nvcc %d.%d, tile_rows %d, topologies: ", PTFNN_ABI_VERSION,
-                 __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, kTileRows);
-        info = buf + supported_list();
-    }
+    // one string per calling thread: the pointer stays valid for the caller while other threads register topologies
+    static thread_local std::string info;
+    char buf[256];
+    snprintf(buf, sizeof buf, "libptfnn abi %d, sm_100a, nvcc %d.%d, tile_rows %d, topologies: ", PTFNN_ABI_VERSION,
+             __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, kTileRows);
+    info = buf + supported_list();
     return info.c_str();
 }
 
@@ -263,6 +266,7 @@ extern "C" int ptfnn_register_kernels(const void *kernel_set, int32_t registry_v
     if (registry_version != PTFNN_REGISTRY_VERSION) return fail(nullptr, PTFNN_E_INVALID, "kernel registry version %d != %d: rebuild the specialisation", registry_version, PTFNN_REGISTRY_VERSION);
     const KernelSet *k = (const KernelSet *)kernel_set;
     if (find_kernels(k->task, k->I, k->H, k->O)) return PTFNN_OK;
+    std::lock_guard<std::mutex> g(kernel_sets_mutex());
     kernel_sets().push_back(k);
     return PTFNN_OK;
 }
