@@ -200,11 +200,17 @@ def make_gpu_ladder(task, topology, temperatures_global, samples, swap_interval,
     ``peer=False``: the host completes them with all_gather + isend/irecv."""
     import torch
     import torch.distributed as dist
+    from . import capi
     from .sampler import Sampler
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     temps = np.asarray(temperatures_global, dtype=np.float64)
     lo, n = partition(len(temps), world, rank)
     dev_index = torch.cuda.current_device() if device is None else device
+    if world > 1 and not capi.has_topology(task, topology):
+        # a topology that is compiled on demand: rank 0 compiles it once, the others load the cached library afterwards
+        if rank == 0:
+            capi.ensure_topology(task, topology)
+        dist.barrier(group)
     smp = Sampler(task, topology, temps[lo:lo + n], samples, swap_interval, n_replicas_global=len(temps),
                   replica_offset=lo, device=dev_index, **sampler_kw)
     chains = GpuChains(smp, torch.device("cuda", dev_index))
